@@ -1,0 +1,210 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- numpy restatement of Fermi.jl's RCCSD(T).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product path (fermi.jl_b200) never does.
+
+Follows, line for line, the reference's default (T) algorithm
+    src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:20-150
+(`RCCSDpT(ccsd, moints, ::ijk)`), and cross-checks it against the explicit-GEMM form of
+    src/Methods/CoupledCluster/PerturbativeTriples/ijk2.jl:21-190
+and against an independent spin-orbital brute-force (T) (`pt_spinorbital_bruteforce`).
+
+PARITY PIN: the reference itself (Julia) cannot run in the build container, and its only direct (T)
+tests need SCF+CCSD inputs.  The pin is therefore (a) this transcription == the ijk2 transcription ==
+spin-orbital brute force, and (b) the known answer printed by the reference for water/STO-3G
+(examples/Juliacon2022.ipynb:613-615, E(T) = -0.0000738086, CCSD(T) = -75.0187834019), reproduced by
+oracle/mini_ccsd.py feeding this function (see tests/test_oracle_kat.py).
+
+All arrays are in the reference's index order: T1[i,a], T2[i,j,a,b], OVVV[i,a,b,c]=(ia|bc),
+OOOV[i,j,k,a]=(ij|ka), OVOV[i,a,j,b]=(ia|jb), fo[i], fv[a].  numpy arrays of any memory order are
+accepted (indexing is by axis, not by layout).
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+
+def _energy_from_WV(W, V, Dijk, fv, dij, djk):
+    """ijk.jl:120-136 -- scalar a>=b>=c loop, vectorised over an index mask (same arithmetic)."""
+    v = W.shape[0]
+    a, b, c = np.meshgrid(np.arange(v), np.arange(v), np.arange(v), indexing="ij")
+    m = (a >= b) & (b >= c)
+    a, b, c = a[m], b[m], c[m]
+    Wabc, Wacb, Wbac, Wbca, Wcab, Wcba = W[a, b, c], W[a, c, b], W[b, a, c], W[b, c, a], W[c, a, b], W[c, b, a]
+    Vabc, Vacb, Vbac, Vbca, Vcab, Vcba = V[a, b, c], V[a, c, b], V[b, a, c], V[b, c, a], V[c, a, b], V[c, b, a]
+    X = Wabc * Vabc + Wacb * Vacb + Wbac * Vbac + Wbca * Vbca + Wcab * Vcab + Wcba * Vcba  # :129
+    Y = Vabc + Vbca + Vcab  # :130
+    Z = Vacb + Vbac + Vcba  # :131
+    Ef = (Y - 2 * Z) * (Wabc + Wbca + Wcab) + (Z - 2 * Y) * (Wacb + Wbac + Wcba) + 3 * X  # :132
+    Dd = Dijk - fv[a] - fv[b] - fv[c]  # :122,124,127
+    dab = (a == b).astype(float)
+    dbc = (b == c).astype(float)
+    return float(np.sum(Ef * (2 - dij - djk) / (Dd * (1 + dab + dbc))))  # :133
+
+
+def triplet_WV(T1, T2, OVVV, OOOV, OVOV, i, j, k):
+    """W and V for one (i,j,k) -- ijk.jl:108-117 with the permutes of :24-32 undone."""
+    es = np.einsum
+    W = es("abd,cd->abc", OVVV[i], T2[k, j]) - es("lb,lca->abc", OOOV[:, i, j, :], T2[k])  # :109
+    W += es("bad,cd->abc", OVVV[j], T2[k, i]) - es("la,lcb->abc", OOOV[:, j, i, :], T2[k])  # :110
+    W += es("cad,bd->abc", OVVV[k], T2[j, i]) - es("la,lbc->abc", OOOV[:, k, i, :], T2[j])  # :111
+    W += es("cbd,da->abc", OVVV[k], T2[j, i]) - es("lb,lac->abc", OOOV[:, k, j, :], T2[i])  # :112
+    W += es("acd,db->abc", OVVV[i], T2[k, j]) - es("lc,lba->abc", OOOV[:, i, k, :], T2[j])  # :113
+    W += es("bcd,da->abc", OVVV[j], T2[k, i]) - es("lc,lab->abc", OOOV[:, j, k, :], T2[i])  # :114
+    V = (
+        W
+        + es("a,bc->abc", T1[i], OVOV[j, :, k, :])
+        + es("ac,b->abc", OVOV[i, :, k, :], T1[j])
+        + es("ab,c->abc", OVOV[i, :, j, :], T1[k])
+    )  # :116
+    return W, V
+
+
+def pt_ijk(T1, T2, OVVV, OOOV, OVOV, fo, fv, triplets=None):
+    """E(T) following ijk.jl:20-150.  `triplets` (iterable of (i,j,k), 0-based, i>=j>=k) restricts the
+    sum to a subset (used for bounded CPU-baseline samples and for sharding tests)."""
+    o, v = T1.shape
+    if triplets is None:
+        triplets = ((i, j, k) for i in range(o) for j in range(i + 1) for k in range(j + 1))  # :49,63,83
+    Et = 0.0
+    for i, j, k in triplets:
+        W, V = triplet_WV(T1, T2, OVVV, OOOV, OVOV, i, j, k)
+        Dijk = fo[i] + fo[j] + fo[k]
+        Et += _energy_from_WV(W, V, Dijk, fv, float(i == j), float(j == k))
+    return Et  # :145
+
+
+def pt_ijk2(T1, T2, OVVV, OOOV, OVOV, fo, fv):
+    """E(T) following the explicit-GEMM formulation ijk2.jl:26-33,110-176."""
+    o, v = T1.shape
+
+    def X(p, q, r):
+        # X(p;q,r)[x,y,z] = sum_d OVVV[p,y,x,d] t2[r,q,z,d] - sum_l t2[p,l,y,x] OOOV[l,q,r,z]
+        return np.einsum("yxd,zd->xyz", OVVV[p], T2[r, q]) - np.einsum("lyx,lz->xyz", T2[p], OOOV[:, q, r, :])
+
+    Et = 0.0
+    for i in range(o):
+        for j in range(i + 1):
+            for k in range(j + 1):
+                W = X(j, i, k).copy()  # abc  :110-114
+                W += X(k, i, j).transpose(0, 2, 1)  # acb  :116-123
+                W += X(i, j, k).transpose(1, 0, 2)  # bac  :125-131
+                W += X(k, j, i).transpose(2, 0, 1)  # bca  :133-139  (W[a,b,c] += X[b,c,a])
+                W += X(i, k, j).transpose(1, 2, 0)  # cab  :141-147  (W[a,b,c] += X[c,a,b])
+                W += X(j, k, i).transpose(2, 1, 0)  # cba  :149-153
+                V = (
+                    W
+                    + np.einsum("a,bc->abc", T1[i], OVOV[j, :, k, :])
+                    + np.einsum("ac,b->abc", OVOV[i, :, k, :], T1[j])
+                    + np.einsum("ab,c->abc", OVOV[i, :, j, :], T1[k])
+                )  # :155-157
+                Et += _energy_from_WV(W, V, fo[i] + fo[j] + fo[k], fv, float(i == j), float(j == k))
+    return Et
+
+
+def pt_ijk_loops(T1, T2, OVVV, OOOV, OVOV, fo, fv):
+    """Pure-Python scalar loops over (a,b,c) for the energy stage (tiny shapes only): the literal
+    ijk.jl:120-136 nest, used to validate the vectorised `_energy_from_WV`."""
+    o, v = T1.shape
+    Et = 0.0
+    for i in range(o):
+        for j in range(i + 1):
+            for k in range(j + 1):
+                W, V = triplet_WV(T1, T2, OVVV, OOOV, OVOV, i, j, k)
+                Dijk = fo[i] + fo[j] + fo[k]
+                dij, djk = float(i == j), float(j == k)
+                for a in range(v):
+                    for b in range(a + 1):
+                        for c in range(b + 1):
+                            Dd = Dijk - fv[a] - fv[b] - fv[c]
+                            X = (W[a, b, c] * V[a, b, c] + W[a, c, b] * V[a, c, b] + W[b, a, c] * V[b, a, c]
+                                 + W[b, c, a] * V[b, c, a] + W[c, a, b] * V[c, a, b] + W[c, b, a] * V[c, b, a])
+                            Y = V[a, b, c] + V[b, c, a] + V[c, a, b]
+                            Z = V[a, c, b] + V[b, a, c] + V[c, b, a]
+                            Ef = ((Y - 2 * Z) * (W[a, b, c] + W[b, c, a] + W[c, a, b])
+                                  + (Z - 2 * Y) * (W[a, c, b] + W[b, a, c] + W[c, b, a]) + 3 * X)
+                            Et += Ef * (2 - dij - djk) / (Dd * (1 + float(a == b) + float(b == c)))
+    return Et
+
+
+def pt_spinorbital_bruteforce(T1, T2, OVVV, OOOV, OVOV, fo, fv):
+    """Independent check: textbook spin-orbital (T) with antisymmetrised integrals,
+       E = (1/36) sum C (C + S) / D,  built from the closed-shell arrays.  O((2o)^3 (2v)^3 (2v+2o))
+       -- only for o<=3, v<=5.  Shares no contraction code with pt_ijk."""
+    o, v = T1.shape
+    no, nv = 2 * o, 2 * v
+    so = lambda P: (P // 2, P % 2)  # spatial index, spin
+    # spin-orbital amplitudes
+    t1 = np.zeros((no, nv))
+    t2 = np.zeros((no, no, nv, nv))
+    for I in range(no):
+        i, si = so(I)
+        for A in range(nv):
+            a, sa = so(A)
+            if si == sa:
+                t1[I, A] = T1[i, a]
+    for I, J, A, B in itertools.product(range(no), range(no), range(nv), range(nv)):
+        (i, si), (j, sj), (a, sa), (b, sb) = so(I), so(J), so(A), so(B)
+        val = 0.0
+        if si == sa and sj == sb:
+            val += T2[i, j, a, b]
+        if si == sb and sj == sa:
+            val -= T2[j, i, a, b]
+        t2[I, J, A, B] = val
+    # antisymmetrised physicist integrals <pq||rs> = (pr|qs) d(sp,sr) d(sq,ss) - (ps|qr) d(sp,ss) d(sq,sr)
+    # needed blocks: <ei||bc> -> <vo||vv> via (ia|bc) ; <ma||jk> -> <ov||oo> via (ij|ka) ; <jk||bc> via (ia|jb)
+    def vovv(E, I, B, C):  # <ei||bc> = (eb|ic) - (ec|ib)
+        (e, se), (i, si), (b, sb), (c, sc) = so(E), so(I), so(B), so(C)
+        r = 0.0
+        if se == sb and si == sc:
+            r += OVVV[i, c, e, b]  # (ic|eb)
+        if se == sc and si == sb:
+            r -= OVVV[i, b, e, c]  # (ib|ec)
+        return r
+
+    def ovoo(M, A, J, K):  # <ma||jk> = (mj|ak) - (mk|aj)
+        (m, sm), (a, sa), (j, sj), (k, sk) = so(M), so(A), so(J), so(K)
+        r = 0.0
+        if sm == sj and sa == sk:
+            r += OOOV[m, j, k, a]  # (mj|ka)
+        if sm == sk and sa == sj:
+            r -= OOOV[m, k, j, a]  # (mk|ja)
+        return r
+
+    def oovv(J, K, B, C):  # <jk||bc> = (jb|kc) - (jc|kb)
+        (j, sj), (k, sk), (b, sb), (c, sc) = so(J), so(K), so(B), so(C)
+        r = 0.0
+        if sj == sb and sk == sc:
+            r += OVOV[j, b, k, c]
+        if sj == sc and sk == sb:
+            r -= OVOV[j, c, k, b]
+        return r
+
+    VOVV = np.zeros((nv, no, nv, nv))
+    for E, I, B, C in itertools.product(range(nv), range(no), range(nv), range(nv)):
+        VOVV[E, I, B, C] = vovv(E, I, B, C)
+    OVOO = np.zeros((no, nv, no, no))
+    for M, A, J, K in itertools.product(range(no), range(nv), range(no), range(no)):
+        OVOO[M, A, J, K] = ovoo(M, A, J, K)
+    OOVV = np.zeros((no, no, nv, nv))
+    for J, K, B, C in itertools.product(range(no), range(no), range(nv), range(nv)):
+        OOVV[J, K, B, C] = oovv(J, K, B, C)
+    eo = np.repeat(np.asarray(fo), 2)
+    ev = np.repeat(np.asarray(fv), 2)
+
+    # connected:   base_c[i,j,k,a,b,c] = sum_e t_jk^ae <ei||bc> - sum_m t_im^bc <ma||jk>
+    base_c = np.einsum("jkae,eibc->ijkabc", t2, VOVV) - np.einsum("imbc,majk->ijkabc", t2, OVOO)
+    base_d = np.einsum("ia,jkbc->ijkabc", t1, OOVV)
+
+    def P_perm(x):
+        # P(i/jk) f = f(ijk) - f(jik) - f(kji) ; P(a/bc) likewise on the last three axes
+        y = x - x.transpose(1, 0, 2, 3, 4, 5) - x.transpose(2, 1, 0, 3, 4, 5)
+        return y - y.transpose(0, 1, 2, 4, 3, 5) - y.transpose(0, 1, 2, 5, 4, 3)
+
+    C = P_perm(base_c)
+    S = P_perm(base_d)
+    D = (eo[:, None, None, None, None, None] + eo[None, :, None, None, None, None] + eo[None, None, :, None, None, None]
+         - ev[None, None, None, :, None, None] - ev[None, None, None, None, :, None] - ev[None, None, None, None, None, :])
+    return float(np.sum(C * (C + S) / D) / 36.0)
