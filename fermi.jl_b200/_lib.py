@@ -1,0 +1,129 @@
+"""ctypes binding of libfermi_pt_b200.so -- the same C ABI (include/fermi_pt_b200.h) the Julia `ccall` glue uses.
+Fails loudly when the library or a GPU is missing: there is no CPU fallback on the product path."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_LIB = None
+
+
+class FermiException(Exception):
+    """Mirror of Fermi.Options.FermiException (Options.jl:196-199)."""
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("upload_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
+                ("flops", ctypes.c_double), ("h2d_bytes", ctypes.c_double), ("n_items", ctypes.c_longlong),
+                ("n_triplets", ctypes.c_longlong), ("n_launches", ctypes.c_int), ("n_sm", ctypes.c_int)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df",
+           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_last_error", "fpt_version"]
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise FermiException(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
+    L = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    L.fpt_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(vp)]
+    L.fpt_destroy.argtypes = [vp]
+    L.fpt_triples_conv.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
+    L.fpt_triples_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
+    L.fpt_upload_conv.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7
+    L.fpt_upload_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
+    L.fpt_num_items.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    L.fpt_compute.argtypes = [vp, ctypes.c_longlong, ctypes.c_longlong, _dp, ctypes.POINTER(Stats)]
+    L.fpt_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp]
+    L.fpt_last_error.restype = ctypes.c_char_p
+    L.fpt_version.restype = ctypes.c_char_p
+    for f in EXPORTS[:9]:
+        getattr(L, f).restype = ctypes.c_int
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    """Pointer for an input array: numpy (host, made Fortran-contiguous f64) or a torch tensor (host or CUDA).
+    Returns (address, keepalive)."""
+    if hasattr(a, "data_ptr"):  # torch tensor: must already be laid out column-major by the caller (see host.as_colmajor)
+        return ctypes.c_void_p(a.data_ptr()), a
+    arr = np.asfortranarray(a, dtype=np.float64)
+    return ctypes.c_void_p(arr.ctypes.data), arr
+
+
+class Engine:
+    """Owns one fpt_handle (one GPU).  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device: int | None = None):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        devs = (ctypes.c_int * 1)(device) if device is not None else None
+        self._check(self._L.fpt_create(1, devs, ctypes.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FermiException(self._L.fpt_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._L.fpt_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def triples_conv(self, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, OVVV, OOOV, OVOV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_conv(self._h, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def triples_df(self, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def upload_conv(self, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, OVVV, OOOV, OVOV, fo, fv)]
+        self._check(self._L.fpt_upload_conv(self._h, o, v, *[p for p, _ in ps]))
+
+    def upload_df(self, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
+        self._check(self._L.fpt_upload_df(self._h, o, v, naux, *[p for p, _ in ps]))
+
+    def num_items(self) -> int:
+        n = ctypes.c_longlong()
+        self._check(self._L.fpt_num_items(self._h, ctypes.byref(n)))
+        return n.value
+
+    def compute(self, item_begin: int = 0, item_end: int = -1):
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_compute(self._h, item_begin, item_end, ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def fp64_peak(self, variant: int = 0, ms_target: float = 200.0) -> float:
+        t = ctypes.c_double()
+        self._check(self._L.fpt_fp64_peak(self._h, variant, ms_target, ctypes.byref(t)))
+        return t.value

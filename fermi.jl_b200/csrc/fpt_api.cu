@@ -1,0 +1,398 @@
+// C-ABI of libfermi_pt_b200.so (declared in include/fermi_pt_b200.h) and the host-side driver of the (T) path:
+// device buffer pool, host->device staging, layout prep / DF assembly launches, the persistent fused kernel launch
+// and the final reduction.  Replaces the driver loop + accumulation of
+//   src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:20-150 (reference, Julia threads)
+// No CPU fallback: every entry point fails loudly without a CUDA device.
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fermi_pt_b200.h"
+#include "fpt_kernels.cuh"
+
+using namespace fpt;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    double* d() const { return (double*)p; }
+};
+
+struct fpt_handle {
+    int dev = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // resident operands
+    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out;
+    // staging for raw inputs
+    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
+    Problem prob{};
+    bool loaded = false;
+    fpt_stats last{};
+    int launches = 0;
+};
+
+extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.1 (sm_100a)"; }
+
+extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
+{
+    if (!out) return fail("fpt_create: out is NULL");
+    *out = nullptr;
+    if (ngpu != 1) return fail("fpt_create: this build drives one GPU per handle (got ngpu=%d); use one process per GPU", ngpu);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("fpt_create: no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString(e));
+    int dev = 0;
+    if (devices) dev = devices[0]; else CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ndev) return fail("fpt_create: device %d out of range (have %d)", dev, ndev);
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail("fpt_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    fpt_handle* h = new fpt_handle();
+    h->dev = dev;
+    h->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    CK(cudaFuncSetAttribute(triples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    *out = h;
+    return 0;
+}
+
+extern "C" int fpt_destroy(fpt_handle* h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->dev);
+    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out,
+                      &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
+    for (DevBuf* b : bufs) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+static bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Returns a device pointer for `src` (n doubles): src itself if already on the device, else a staged copy.
+static int stage_in(fpt_handle* h, DevBuf& buf, const double* src, size_t n, const double** dptr, double* h2d_bytes)
+{
+    if (is_device_ptr(src)) { *dptr = src; return 0; }
+    if (buf.ensure(n * sizeof(double))) return 1;
+    CK(cudaMemcpyAsync(buf.p, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    *h2d_bytes += (double)n * sizeof(double);
+    *dptr = buf.d();
+    return 0;
+}
+
+static int setup_problem(fpt_handle* h, int o, int v)
+{
+    if (o < 1 || v < 1) return fail("invalid dimensions o=%d v=%d", o, v);
+    Problem& P = h->prob;
+    P.o = o; P.v = v;
+    P.vp = padded_v(v);
+    P.nt = num_tiles(v);
+    P.Kp = roundup(v + o, KGROUP);
+    P.G = P.Kp / KGROUP;
+    P.npair = o * (o + 1) / 2;
+    P.nb = num_blocks(P.nt);
+    std::vector<i64> prefix(P.npair + 1);
+    i64 acc = 0;
+    for (int pr = 0; pr < P.npair; pr++) {
+        int i, j;
+        tri_decode(pr, i, j);
+        prefix[pr] = acc;
+        acc += (i64)num_k(i, j) * P.nb;
+    }
+    prefix[P.npair] = acc;
+    P.nitems = acc;
+    if (h->Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
+    if (h->Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
+    if (h->OV2.ensure((size_t)o * o * v * v * sizeof(double))) return 1;
+    if (h->T1d.ensure((size_t)o * v * sizeof(double))) return 1;
+    if (h->fo.ensure((size_t)o * sizeof(double))) return 1;
+    if (h->fv.ensure((size_t)v * sizeof(double))) return 1;
+    if (h->prefix.ensure(prefix.size() * sizeof(i64))) return 1;
+    if (h->partials.ensure((size_t)h->n_sm * 4 * sizeof(double))) return 1;
+    if (h->counter.ensure(sizeof(unsigned long long))) return 1;
+    if (h->out.ensure(sizeof(double))) return 1;
+    CK(cudaMemcpyAsync(h->prefix.p, prefix.data(), prefix.size() * sizeof(i64), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // `prefix` is a local
+    P.Pt = h->Pt.d(); P.Qt = h->Qt.d(); P.OV2 = h->OV2.d(); P.T1d = h->T1d.d();
+    P.fo = h->fo.d(); P.fv = h->fv.d(); P.pair_prefix = (const i64*)h->prefix.p;
+    return 0;
+}
+
+static int grid1d(i64 n, int block = 256) { i64 g = (n + block - 1) / block; if (g > 148 * 32) g = 148 * 32; if (g < 1) g = 1; return (int)g; }
+
+// the parts common to conventional and DF uploads: T1, T2 -> T1d, Pt hole part, Qt particle part; fo, fv
+static int upload_common(fpt_handle* h, const double* T1, const double* T2, const double* fo, const double* fv,
+                         const double** dT2, double* h2d)
+{
+    const Problem& P = h->prob;
+    const int o = P.o, v = P.v;
+    const double* dT1;
+    if (stage_in(h, h->sT1, T1, (size_t)o * v, &dT1, h2d)) return 1;
+    if (stage_in(h, h->sT2, T2, (size_t)o * o * v * v, dT2, h2d)) return 1;
+    CK(cudaMemcpyAsync(h->fo.p, fo, o * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->fv.p, fv, v * sizeof(double), cudaMemcpyDefault, h->stream));
+    if (!is_device_ptr(fo)) *h2d += (o + v) * sizeof(double);
+    CK(cudaMemsetAsync(h->Pt.p, 0, (size_t)o * P.vp * P.vp * P.Kp * sizeof(double), h->stream));
+    prep_t1<<<grid1d(o * v), 256, 0, h->stream>>>(P, h->T1d.d(), dT1);
+    prep_pt_hole<<<grid1d((i64)o * o * v * v), 256, 0, h->stream>>>(P, h->Pt.d(), *dT2);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                               const double* OOOV, const double* OVOV, const double* fo, const double* fv)
+{
+    if (!h) return fail("fpt_upload_conv: NULL handle");
+    if (!T1 || !T2 || !OVVV || !OOOV || !OVOV || !fo || !fv) return fail("fpt_upload_conv: NULL array argument");
+    CK(cudaSetDevice(h->dev));
+    auto t0 = std::chrono::steady_clock::now();
+    h->loaded = false;
+    h->launches = 0;
+    if (setup_problem(h, o, v)) return 1;
+    const Problem& P = h->prob;
+    double h2d = 0.0;
+    const double* dT2;
+    if (upload_common(h, T1, T2, fo, fv, &dT2, &h2d)) return 1;
+    const double *dOOOV, *dOVOV;
+    if (stage_in(h, h->sOOOV, OOOV, (size_t)o * o * o * v, &dOOOV, &h2d)) return 1;
+    if (stage_in(h, h->sOVOV, OVOV, (size_t)o * v * o * v, &dOVOV, &h2d)) return 1;
+    prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, h->stream>>>(P, h->Qt.d(), dT2, dOOOV);
+    prep_ov2<<<grid1d((i64)o * o * v * v), 256, 0, h->stream>>>(P, h->OV2.d(), dOVOV);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    // OVVV -> Pt particle part, in chunks over the slowest index d
+    const size_t slab = (size_t)o * v * v;   // doubles per d
+    const bool on_dev = is_device_ptr(OVVV);
+    int dchunk = v;
+    if (!on_dev) {
+        const size_t budget = (size_t)512 << 20;
+        dchunk = (int)(budget / (slab * sizeof(double)));
+        if (dchunk < 1) dchunk = 1;
+        if (dchunk > v) dchunk = v;
+        if (h->sChunk.ensure((size_t)dchunk * slab * sizeof(double))) return 1;
+    }
+    for (int d0 = 0; d0 < v; d0 += dchunk) {
+        const int dn = (v - d0 < dchunk) ? v - d0 : dchunk;
+        const double* src = OVVV + (size_t)d0 * slab;
+        if (!on_dev) {
+            CK(cudaMemcpyAsync(h->sChunk.p, src, (size_t)dn * slab * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            h2d += (double)dn * slab * sizeof(double);
+            src = h->sChunk.d();
+        }
+        dim3 grid((unsigned)(((size_t)o * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
+        prep_pt_particle<<<grid, dim3(32, 8), 0, h->stream>>>(P, h->Pt.d(), src, d0, dn);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->loaded = true;
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h2d;
+    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+extern "C" int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                             const double* BOV, const double* BVV, const double* fo, const double* fv)
+{
+    if (!h) return fail("fpt_upload_df: NULL handle");
+    if (!T1 || !T2 || !BOO || !BOV || !BVV || !fo || !fv) return fail("fpt_upload_df: NULL array argument");
+    if (naux < 1) return fail("fpt_upload_df: invalid naux=%d", naux);
+    CK(cudaSetDevice(h->dev));
+    auto t0 = std::chrono::steady_clock::now();
+    h->loaded = false;
+    h->launches = 0;
+    if (setup_problem(h, o, v)) return 1;
+    const Problem& P = h->prob;
+    double h2d = 0.0;
+    const double* dT2;
+    if (upload_common(h, T1, T2, fo, fv, &dT2, &h2d)) return 1;
+    const double *dBOO, *dBOV, *dBVV;
+    if (stage_in(h, h->sBOO, BOO, (size_t)naux * o * o, &dBOO, &h2d)) return 1;
+    if (stage_in(h, h->sBOV, BOV, (size_t)naux * o * v, &dBOV, &h2d)) return 1;
+    if (stage_in(h, h->sBVV, BVV, (size_t)naux * v * v, &dBVV, &h2d)) return 1;
+    // Qt: T2 part by the gather kernel (OOOV argument unused for kappa >= v when we overwrite below) -> pass a
+    // zero-filled dummy?  Instead: prep_qt with OOOV = nullptr is not allowed, so build the T2 part with a DF-aware call:
+    // stage 1 fills everything (hole part from a temporary zero source is avoided by the kernel's branch order).
+    if (h->sOOOV.ensure((size_t)o * o * o * v * sizeof(double))) return 1;
+    CK(cudaMemsetAsync(h->sOOOV.p, 0, (size_t)o * o * o * v * sizeof(double), h->stream));
+    prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, h->stream>>>(P, h->Qt.d(), dT2, h->sOOOV.d());
+    {   // OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z]  -> Qt hole part        (DFERI.jl:88-112)
+        const int M = o * o, N = o * v;
+        dim3 grid((M + 63) / 64, (N + 63) / 64);
+        df_gemm_kernel<1><<<grid, 128, 0, h->stream>>>(P, h->Qt.d(), dBOO, dBOV, M, N, naux);
+    }
+    {   // OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z]  -> OV2                 (DFERI.jl:139-154)
+        const int M = o * v, N = o * v;
+        dim3 grid((M + 63) / 64, (N + 63) / 64);
+        df_gemm_kernel<2><<<grid, 128, 0, h->stream>>>(P, h->OV2.d(), dBOV, dBOV, M, N, naux);
+    }
+    {   // OVVV[p,y,x,d] = sum_Q BOV[Q,p,y] BVV[Q,x,d]  -> Pt particle part    (DFERI.jl:156-180, never on the host)
+        const int M = o * v, N = v * v;
+        dim3 grid((M + 63) / 64, (N + 63) / 64);
+        df_gemm_kernel<0><<<grid, 128, 0, h->stream>>>(P, h->Pt.d(), dBOV, dBVV, M, N, naux);
+    }
+    h->launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->loaded = true;
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h2d;
+    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+extern "C" int fpt_num_items(fpt_handle* h, long long* n)
+{
+    if (!h || !n) return fail("fpt_num_items: NULL argument");
+    if (!h->loaded) return fail("fpt_num_items: no problem uploaded");
+    *n = h->prob.nitems;
+    return 0;
+}
+
+extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et, fpt_stats* st)
+{
+    if (!h || !Et) return fail("fpt_compute: NULL argument");
+    if (!h->loaded) return fail("fpt_compute: no problem uploaded");
+    CK(cudaSetDevice(h->dev));
+    const Problem& P = h->prob;
+    if (item_end < 0 || item_end > P.nitems) item_end = P.nitems;
+    if (item_begin < 0) item_begin = 0;
+    if (item_begin > item_end) item_begin = item_end;
+    const i64 n = item_end - item_begin;
+    int grid = h->n_sm;
+    if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
+    CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    triples_kernel<<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(P, item_begin, item_end,
+                                                                      (unsigned long long*)h->counter.p, h->partials.d());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    reduce_partials<<<1, 32, 0, h->stream>>>(h->partials.d(), grid, h->out.d());
+    CK(cudaGetLastError());
+    double e = 0.0;
+    CK(cudaMemcpyAsync(&e, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *Et = e;
+    const double ntrip = (double)P.o * (P.o + 1) * (P.o + 2) / 6.0 - P.o;
+    h->last.kernel_ms = ms;
+    h->last.n_items = n;
+    h->last.n_triplets = (long long)ntrip;
+    h->last.flops = 12.0 * P.v * (double)P.v * P.v * (P.v + P.o) * ntrip * (P.nitems ? (double)n / (double)P.nitems : 0.0);
+    h->last.n_launches = h->launches + 2;
+    h->last.n_sm = h->n_sm;
+    if (st) *st = h->last;
+    return 0;
+}
+
+extern "C" int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                                const double* OOOV, const double* OVOV, const double* fo, const double* fv, double* Et,
+                                fpt_stats* st)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    if (fpt_upload_conv(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv)) return 1;
+    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
+    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (st) *st = h->last;
+    return 0;
+}
+
+extern "C" int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                              const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
+                              fpt_stats* st)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    if (fpt_upload_df(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)) return 1;
+    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
+    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (st) *st = h->last;
+    return 0;
+}
+
+extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops)
+{
+    if (!h || !tflops) return fail("fpt_fp64_peak: NULL argument");
+    CK(cudaSetDevice(h->dev));
+    if (h->out.ensure(sizeof(double))) return 1;
+    const int iters = 4096;
+    const int grid = h->n_sm * 8;   // 8 CTAs x 8 warps per SM -> 16 warps per SMSP
+    // flops per launch
+    const double fl = (variant == 0) ? (double)grid * 8 /*warps*/ * iters * 16.0 * 512.0
+                                     : (double)grid * 256 /*threads*/ * iters * 16.0 * 2.0;
+    auto launch = [&]() {
+        if (variant == 0) peak_dmma_kernel<<<grid, 256, 0, h->stream>>>(h->out.d(), iters, 1e-3);
+        else peak_dfma_kernel<<<grid, 256, 0, h->stream>>>(h->out.d(), iters, 1e-3);
+    };
+    launch();
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    // calibrate launch count
+    CK(cudaEventRecord(h->ev0, h->stream));
+    launch();
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms1 = 0.f;
+    CK(cudaEventElapsedTime(&ms1, h->ev0, h->ev1));
+    int reps = (int)(ms_target / (ms1 > 1e-3f ? ms1 : 1e-3f));
+    if (reps < 1) reps = 1;
+    if (reps > 20000) reps = 20000;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int t = 0; t < reps; t++) launch();
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *tflops = fl * reps / (ms * 1e-3) / 1e12;
+    return 0;
+}

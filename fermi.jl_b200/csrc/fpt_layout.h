@@ -1,0 +1,272 @@
+// Index algebra of the B200 (T) path, shared by the CUDA kernels (fpt_kernels.cuh) and by the host-side
+// emulator used in the CPU tests (tests/emul/emul_main.cpp).  Everything here is __host__ __device__ and
+// free of CUDA runtime calls.
+//
+// Math being laid out (reference: src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:108-136 and the
+// GEMM form ijk2.jl:26-33,110-153).  For occupied p and an ordered pair (q,r):
+//
+//     X(p;q,r)[x,y,z] = sum_kappa  P_p[(x,y),kappa] * Q_qr[kappa,z]
+//     P_p[(x,y),kappa] = OVVV[p,y,x,d]   (kappa = d < v)      |  -T2[p,l,y,x]   (kappa = v+l)
+//     Q_qr[kappa,z]    = T2[r,q,z,d]     (kappa = d < v)      |  OOOV[l,q,r,z]  (kappa = v+l)
+//
+//     W_ijk[a,b,c] = X(j;i,k)[a,b,c] + X(k;i,j)[a,c,b] + X(i;j,k)[b,a,c]
+//                  + X(k;j,i)[b,c,a] + X(i;k,j)[c,a,b] + X(j;k,i)[c,b,a]
+//
+// i.e. X(p;q,r)[x,y,z] lands on the W element whose i/j/k-paired virtual is  x<->q, y<->p, z<->r.
+//
+// Device-resident operand layouts (built once per call by the prep kernels):
+//     Pt [p][y][x][kappa]          kappa contiguous, Kp = roundup8(v+o) doubles per row, x,y < vp (zero padded)
+//     Qt [q*o+r][g][z][8]          kappa = 8g + (0..7), z < vp (zero padded)
+//     OV2[q*o+r][y][z] = OVOV[q,y,r,z]     T1d[p][x] = T1[p,x]
+//
+// Work decomposition: virtual range [0,vp) is cut into tiles (edge 16, last tile 4/8/12); a *block* is a
+// tile triple A>=B>=C; an *item* is (i>=j, block, k<=j) ordered pair-major / block / k-fastest so that
+// concurrently running CTAs share the P_i and P_j rows in L2.  One CTA owns one item at a time: it keeps
+// W_ijk on all distinct permutations of the tile triple (<= 6 slots of TA*TB*TC doubles) in shared memory,
+// accumulates 3*nslot P-stationary GEMMs into them and then evaluates ijk.jl:120-136 for the a>=b>=c
+// points of the block without W or V ever leaving the SM.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FPT_HD __host__ __device__ __forceinline__
+#else
+#define FPT_HD inline
+#endif
+
+namespace fpt {
+
+constexpr int TMAX = 16;       // largest tile edge
+constexpr int KGROUP = 8;      // kappa per group: one 16-byte load per lane feeds two DMMA.8x8x4
+constexpr int CHUNK_GROUPS = 4;  // kappa groups per shared-memory Q stage (32 kappa)
+constexpr int MAX_SLOTS = 6;
+constexpr int MAX_GEMMS = 18;
+
+typedef long long i64;
+
+FPT_HD int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- tiles ---------------------------------------------------------------------------------------
+// vp = roundup4(v); tiles of 16 then one remainder tile (4, 8 or 12).
+FPT_HD int padded_v(int v) { return roundup(v, 4); }
+FPT_HD int num_tiles(int v) { return (padded_v(v) + TMAX - 1) / TMAX; }
+FPT_HD int tile_start(int t) { return t * TMAX; }
+FPT_HD int tile_size(int t, int vp) { int s = vp - t * TMAX; return s > TMAX ? TMAX : s; }
+
+// ---- tetrahedral / triangular decodes ----------------------------------------------------------------
+// n -> (A,B,C), A>=B>=C>=0, n = A(A+1)(A+2)/6 + B(B+1)/2 + C
+FPT_HD void tetra_decode(i64 n, int& A, int& B, int& C)
+{
+    int a = 0;
+    while ((i64)(a + 1) * (a + 2) * (a + 3) / 6 <= n) a++;
+    n -= (i64)a * (a + 1) * (a + 2) / 6;
+    int b = 0;
+    while ((i64)(b + 1) * (b + 2) / 2 <= n) b++;
+    n -= (i64)b * (b + 1) / 2;
+    A = a; B = b; C = (int)n;
+}
+FPT_HD void tri_decode(int n, int& i, int& j)
+{
+    int a = 0;
+    while ((a + 1) * (a + 2) / 2 <= n) a++;
+    i = a; j = n - a * (a + 1) / 2;
+}
+FPT_HD i64 num_blocks(int nt) { return (i64)nt * (nt + 1) * (nt + 2) / 6; }
+// k values for pair (i,j): k in [0, j], minus the zero-weight i=j=k triplet (ijk.jl:133)
+FPT_HD int num_k(int i, int j) { return (i == j) ? j : j + 1; }
+
+// ---- shared-memory W slots ---------------------------------------------------------------------------
+// Element (la,lb,lc) of a slot with dims (Ta,Tb,Tc), lc fastest, with a bank swizzle on lc chosen so that
+//  (1) a 4x4 patch in any two coordinates (lo-2-bits aligned) and (2) a run of 16 in any single coordinate
+// hit 16 distinct 8-byte banks (RMW epilogue of the GEMMs, and the energy stage's permuted reads).
+FPT_HD int slot_index(int la, int lb, int lc, int Tb, int Tc)
+{
+    int lcs;
+    if (Tc == 16) {
+        int h = ((lb & 3) + (lc & 3) + (lc >> 2) + (la >> 2)) & 3;
+        int l = ((la & 3) + (lc & 3) + (lb >> 2)) & 3;
+        lcs = (h << 2) | l;
+    } else {
+        lcs = (lc + 3 * la + 4 * lb) % Tc;
+    }
+    return (la * Tb + lb) * Tc + lcs;
+}
+
+// perm m of three things, m = 0..5: (0,1,2),(0,2,1),(1,0,2),(1,2,0),(2,0,1),(2,1,0); perm3(m,c) = c-th entry
+FPT_HD int perm3(int m, int c)
+{
+    const int f = m >> 1;
+    if (c == 0) return f;
+    const int lo = (f == 0) ? 1 : 0, hi = (f == 2) ? 1 : 2;
+    return ((c == 1) == ((m & 1) == 0)) ? lo : hi;
+}
+
+struct BlockDesc {
+    int tile[3];       // tile indices (A,B,C), A>=B>=C
+    int t0[3];         // tile starts
+    int ts[3];         // tile sizes
+    int nslot;         // distinct permuted tile triples
+    int slot_of_perm[6];   // perm m of (A,B,C) -> compact slot id
+    int perm_of_slot[6];   // representative perm for each slot
+    int slot_elems;        // TA*TB*TC
+};
+
+FPT_HD void make_block(int A, int B, int C, int vp, BlockDesc& bd)
+{
+    bd.tile[0] = A; bd.tile[1] = B; bd.tile[2] = C;
+    for (int c = 0; c < 3; c++) { bd.t0[c] = tile_start(bd.tile[c]); bd.ts[c] = tile_size(bd.tile[c], vp); }
+    bd.slot_elems = bd.ts[0] * bd.ts[1] * bd.ts[2];
+    bd.nslot = 0;
+    for (int m = 0; m < 6; m++) {
+        int found = -1;
+        for (int m2 = 0; m2 < m; m2++) {
+            bool same = true;
+            for (int c = 0; c < 3; c++) same = same && (bd.tile[perm3(m, c)] == bd.tile[perm3(m2, c)]);
+            if (same) { found = bd.slot_of_perm[m2]; break; }
+        }
+        if (found < 0) { bd.perm_of_slot[bd.nslot] = m; found = bd.nslot++; }
+        bd.slot_of_perm[m] = found;
+    }
+}
+
+// One P-stationary GEMM:  D[(x,y), (s,z)] = sum_kappa P_p[(x,y),kappa] * Q_{s}[kappa,z],
+//   s=0: Q_{q r}, s=1: Q_{r q};  x in tile X (rows x fastest), y in tile Y, z in tile Z.
+struct GemmDesc {
+    int p, q, r;            // occupied orbital numbers
+    int x0, y0, z0;         // tile starts of X, Y, Z
+    int TX, TY, TZ;         // tile sizes
+    // destination of D[...,s,...]: slot base (doubles), which of (x,y,z) supplies (la,lb,lc), and dest Tb,Tc
+    int dbase[2];
+    int dsel[2];            // packed: ra | rb<<2 | rc<<4   (0=x,1=y,2=z)
+    int dTb[2], dTc[2];
+};
+
+// occ = (i,j,k).  Builds the 3*nslot GEMMs of an item.  Returns their number.
+FPT_HD int make_gemms(const BlockDesc& bd, int i, int j, int k, GemmDesc* gd)
+{
+    const int occ[3] = {i, j, k};
+    int n = 0;
+    for (int sl = 0; sl < bd.nslot; sl++) {
+        const int m = bd.perm_of_slot[sl];
+        const int cx = perm3(m, 0), cy = perm3(m, 1), cz = perm3(m, 2);  // which of A/B/C plays X, Y, Z
+        for (int pi = 0; pi < 3; pi++) {
+            GemmDesc& g = gd[n++];
+            const int qi = (pi == 0) ? 1 : 0, ri = (pi == 2) ? 1 : 2;  // the two other positions, ascending
+            g.p = occ[pi]; g.q = occ[qi]; g.r = occ[ri];
+            g.x0 = bd.t0[cx]; g.y0 = bd.t0[cy]; g.z0 = bd.t0[cz];
+            g.TX = bd.ts[cx]; g.TY = bd.ts[cy]; g.TZ = bd.ts[cz];
+            for (int s = 0; s < 2; s++) {
+                // pairing: x <-> (s ? r : q), y <-> p, z <-> (s ? q : r).  sel[pos] = which of x/y/z pairs with occ pos
+                int sel[3];
+                sel[pi] = 1;
+                sel[s ? ri : qi] = 0;
+                sel[s ? qi : ri] = 2;
+                // destination tile triple in terms of A/B/C positions: (c_of[sel[0]], c_of[sel[1]], c_of[sel[2]])
+                const int cxyz[3] = {cx, cy, cz};
+                const int da = cxyz[sel[0]], db = cxyz[sel[1]], dc = cxyz[sel[2]];
+                // find the perm producing the same tile triple
+                int dslot = -1;
+                for (int m2 = 0; m2 < 6 && dslot < 0; m2++)
+                    if (bd.tile[perm3(m2, 0)] == bd.tile[da] && bd.tile[perm3(m2, 1)] == bd.tile[db] &&
+                        bd.tile[perm3(m2, 2)] == bd.tile[dc])
+                        dslot = bd.slot_of_perm[m2];
+                g.dbase[s] = dslot * bd.slot_elems;
+                g.dsel[s] = sel[0] | (sel[1] << 2) | (sel[2] << 4);
+                g.dTb[s] = bd.ts[db];
+                g.dTc[s] = bd.ts[dc];
+            }
+        }
+    }
+    return n;
+}
+
+FPT_HD int pick3(int sel, int x, int y, int z) { return sel == 0 ? x : (sel == 1 ? y : z); }
+
+// smem offset (doubles) of the destination of D element (xl,yl,zl) for column set s
+FPT_HD int gemm_dest(const GemmDesc& g, int s, int xl, int yl, int zl)
+{
+    const int sel = g.dsel[s];
+    const int la = pick3(sel & 3, xl, yl, zl), lb = pick3((sel >> 2) & 3, xl, yl, zl), lc = pick3((sel >> 4) & 3, xl, yl, zl);
+    return g.dbase[s] + slot_index(la, lb, lc, g.dTb[s], g.dTc[s]);
+}
+
+// ---- problem description --------------------------------------------------------------------------
+struct Problem {
+    int o, v, vp, nt, Kp, G;
+    int npair;
+    i64 nb;        // blocks per triplet
+    i64 nitems;
+    const double* Pt;
+    const double* Qt;
+    const double* OV2;
+    const double* T1d;
+    const double* fo;
+    const double* fv;
+    const i64* pair_prefix;   // npair+1 entries: first item of pair (i,j), pair index = i(i+1)/2+j
+};
+
+FPT_HD i64 pt_row(const Problem& P, int p, int y, int x) { return (((i64)p * P.vp + y) * P.vp + x) * P.Kp; }
+FPT_HD i64 qt_row(const Problem& P, int q, int r, int g, int z) { return ((((i64)q * P.o + r) * P.G + g) * P.vp + z) * KGROUP; }
+
+struct ItemDesc { int i, j, k; int A, B, C; };
+
+FPT_HD void item_decode(const Problem& P, i64 item, ItemDesc& it)
+{
+    int lo = 0, hi = P.npair;   // find pair with prefix[pr] <= item < prefix[pr+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (P.pair_prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    tri_decode(lo, it.i, it.j);
+    const i64 rem = item - P.pair_prefix[lo];
+    const int nk = num_k(it.i, it.j);
+    it.k = (int)(rem % nk);
+    tetra_decode(rem / nk, it.A, it.B, it.C);
+}
+
+// ---- energy of one (a,b,c) point, ijk.jl:127-133 ---------------------------------------------------------
+// w[m], vv[m] in perm order m: (abc),(acb),(bac),(bca),(cab),(cba)
+FPT_HD double point_energy(const double* w, const double* vv, double Dd, int a, int b, int c, double wijk)
+{
+    const double X = w[0] * vv[0] + w[1] * vv[1] + w[2] * vv[2] + w[3] * vv[3] + w[4] * vv[4] + w[5] * vv[5];
+    const double Y = vv[0] + vv[3] + vv[4];
+    const double Z = vv[1] + vv[2] + vv[5];
+    const double Ef = (Y - 2.0 * Z) * (w[0] + w[3] + w[4]) + (Z - 2.0 * Y) * (w[1] + w[2] + w[5]) + 3.0 * X;
+    const double den = Dd * (double)(1 + (a == b) + (b == c));
+    return Ef * wijk / den;
+}
+
+// Energy contribution of point `pt` (linear index, c fastest) of the block held in the W slots `Wsm`:
+// V build ijk.jl:116 and the a>=b>=c body ijk.jl:127-133.  Returns 0 for padded or non-canonical points.
+FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int pt)
+{
+    const int TB = bd.ts[1], TC = bd.ts[2];
+    const int v = P.v, o = P.o;
+    const int cl = pt % TC;
+    const int t2 = pt / TC;
+    const int bl = t2 % TB, al = t2 / TB;
+    const int a = bd.t0[0] + al, b = bd.t0[1] + bl, c = bd.t0[2] + cl;
+    if (a >= v || b >= v || c >= v || a < b || b < c) return 0.0;
+    const double* t1i = P.T1d + (i64)i * v;
+    const double* t1j = P.T1d + (i64)j * v;
+    const double* t1k = P.T1d + (i64)k * v;
+    const double* ovjk = P.OV2 + ((i64)j * o + k) * v * v;
+    const double* ovik = P.OV2 + ((i64)i * o + k) * v * v;
+    const double* ovij = P.OV2 + ((i64)i * o + j) * v * v;
+    double w[6], vv[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int m = 0; m < 6; m++) {
+        const int c0 = perm3(m, 0), c1 = perm3(m, 1), c2 = perm3(m, 2);
+        const int x = pick3(c0, a, b, c), y = pick3(c1, a, b, c), z = pick3(c2, a, b, c);
+        const int lx = pick3(c0, al, bl, cl), ly = pick3(c1, al, bl, cl), lz = pick3(c2, al, bl, cl);
+        const int off = bd.slot_of_perm[m] * bd.slot_elems + slot_index(lx, ly, lz, bd.ts[c1], bd.ts[c2]);
+        w[m] = Wsm[off];
+        vv[m] = w[m] + t1i[x] * ovjk[(i64)y * v + z] + ovik[(i64)x * v + z] * t1j[y] + ovij[(i64)x * v + y] * t1k[z];
+    }
+    const double Dd = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[a] - P.fv[b] - P.fv[c];
+    return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));
+}
+
+}  // namespace fpt

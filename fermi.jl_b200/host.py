@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference's RCCSD(T) interface, in Python because Julia is not available in this image
+(the Julia glue a Fermi.jl maintainer would add is in julia/FermiB200.jl; same C ABI underneath).
+
+Mirrors, name for name:
+  RpTAlgorithm / get_rpt_alg / RCCSDpT(x...)     src/Methods/CoupledCluster/PerturbativeTriples/PerturbativeTriples.jl:1-63
+  RCCSDpT(ccsd, moints, alg)                     .../ijk.jl:20-150   <- the drop-in boundary
+  RCCSD struct (fields)                          src/Methods/CoupledCluster/RCCSD/RCCSD.jl:61-69
+  IntegralHelper (cache + lazy getindex)         src/Core/Integrals/IntegralHelper.jl:50-56,111-118
+  Options / output / FermiException              src/Core/Options.jl:40-199, src/Core/Output.jl:35-60
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import Engine, FermiException
+
+# ---- Options (only the keys the (T) path reads; Options.jl:40-104) -------------------------------------
+_DEFAULT = {"pt_alg": 4, "printstyle": "none", "output": "fermi.out", "return_ints": False, "df": False}
+Options = dict(_DEFAULT)
+
+
+def output(fmt: str, *args, ending: str = "\n") -> None:
+    """Output.jl:35-60."""
+    style = Options["printstyle"]
+    text = fmt.format(*args) + ending
+    if style == "none":
+        return
+    if style in ("file", "both"):
+        with open(Options["output"], "a") as fh:
+            fh.write(text)
+    if style in ("repl", "both"):
+        print(text, end="")
+    if style not in ("repl", "file", "both"):
+        raise FermiException(f"printing style not recognized: {style}. Accepted `printstyle` values: repl, file, both, and none")
+
+
+# ---- algorithm singletons (PerturbativeTriples.jl:1-11,41-49) ------------------------------------------------
+class RpTAlgorithm:
+    pass
+
+
+class B200(RpTAlgorithm):
+    """The new singleton: `struct B200 <: RpTAlgorithm end`; registered as pt_alg = 4."""
+
+
+class ijk(RpTAlgorithm):
+    """Reference CPU algorithms are not part of this package (no CPU fallback)."""
+
+
+def get_rpt_alg():
+    implemented = {4: B200()}
+    N = Options["pt_alg"]
+    try:
+        return implemented[N]
+    except KeyError:
+        raise FermiException(f"implementation number {N} not available for RCCSD(T).")
+
+
+# ---- inputs ------------------------------------------------------------------------------------------------
+@dataclass
+class RCCSD:
+    """RCCSD.jl:61-69."""
+    guessenergy: float
+    correlation: float
+    energy: float
+    T1: np.ndarray
+    T2: np.ndarray
+    e_conv: float = 0.0
+    t_conv: float = 0.0
+
+
+class IntegralHelper:
+    """The slice of IntegralHelper the (T) path touches: a string-keyed cache of MO arrays plus `eri_type`.
+    For a DF helper (eri_type in {"RIFIT","JKFIT"}, ERITypes.jl:19) the 4-index keys are *not* materialised
+    (the reference would do so lazily, DFERI.jl:88-180); the B200 path consumes BOO/BOV/BVV directly."""
+
+    def __init__(self, cache: dict | None = None, eri_type: str = "Chonky"):
+        self.cache = dict(cache or {})
+        self.eri_type = eri_type
+
+    @property
+    def is_df(self) -> bool:
+        return self.eri_type in ("RIFIT", "JKFIT", "AbstractDFERI")
+
+    def __getitem__(self, key: str):
+        if key in self.cache:
+            return self.cache[key]
+        raise FermiException(f"Invalid key for IntegralHelper: {key} (this mirror cannot compute integrals; fill the cache)")
+
+    def __setitem__(self, key: str, val) -> None:
+        self.cache[key] = val
+
+    def __contains__(self, key: str) -> bool:
+        return key in self.cache
+
+
+_ENGINES: dict = {}
+
+
+def _engine(device=None) -> Engine:
+    key = device
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device)
+    return _ENGINES[key]
+
+
+class RCCSDpT:
+    """Result struct `RCCSDpT{T}(CCSD, energy, correction)` (PerturbativeTriples.jl:21-25) whose constructor is the
+    reference's varargs entry `RCCSDpT(x...)` (:51-63): with no algorithm among the arguments the one selected by
+    Options["pt_alg"] is appended; `RCCSDpT(ccsd, moints, B200())` is the boundary method (ijk.jl:20)."""
+
+    def __init__(self, *x, device=None):
+        algs = [a for a in x if isinstance(a, RpTAlgorithm)]
+        if not algs:
+            x = x + (get_rpt_alg(),)
+        if not (len(x) == 3 and isinstance(x[0], RCCSD) and isinstance(x[1], IntegralHelper) and isinstance(x[2], B200)):
+            args = ", ".join(type(a).__name__ for a in x[:-1])
+            raise FermiException(f"invalid arguments for RCCSD(T) method: ({args})")
+        ccsd, moints, _ = x
+        output("\n   • Perturbative Triples Started\n")
+        output("   - Contraction Engine: B200 DMMA (libfermi_pt_b200)")
+        T1, T2 = ccsd.T1, ccsd.T2
+        o, v = T1.shape
+        if tuple(T2.shape) != (o, o, v, v):
+            raise FermiException(f"invalid T2 shape {tuple(T2.shape)} for T1 shape {(o, v)}")
+        fo, fv = moints["Fii"], moints["Faa"]
+        eng = _engine(device)
+        output("Computing energy contribution from occupied orbitals:")
+        t0 = time.perf_counter()
+        if moints.is_df and "OVVV" not in moints:
+            BOO, BOV, BVV = moints["BOO"], moints["BOV"], moints["BVV"]
+            naux = BOV.shape[0]
+            Et, st = eng.triples_df(o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)
+        else:
+            Et, st = eng.triples_conv(o, v, T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv)
+        t = time.perf_counter() - t0
+        output("Finished in {:5.5f} s", t)
+        output("Final (T) contribution: {:15.10f}", Et)
+        output("CCSD(T) energy:         {:15.10f}", Et + ccsd.energy)
+        self.CCSD = ccsd
+        self.energy = Et + ccsd.energy
+        self.correction = Et
+        self.stats = st
+
+
+# ---- static work list helpers (mirror of fpt_layout.h; used for sharding across ranks) -----------------------
+def work_layout(o: int, v: int):
+    """(nb, prefix): blocks per triplet and the first item of every (i>=j) pair; pair index = i(i+1)/2 + j.
+    Items are ordered pair-major, then block, then k (k fastest); the zero-weight i=j=k triplet is skipped."""
+    vp = (v + 3) // 4 * 4
+    nt = (vp + 15) // 16
+    nb = nt * (nt + 1) * (nt + 2) // 6
+    prefix = [0]
+    for i in range(o):
+        for j in range(i + 1):
+            nk = j if i == j else j + 1
+            prefix.append(prefix[-1] + nk * nb)
+    return nb, prefix
+
+
+def pair_range_items(o: int, v: int, pr0: int, pr1: int):
+    """Item range [b,e) covering pairs [pr0,pr1) and the matching range of the reference's flattened
+    (i,j,k) triplet list (k fastest) -- contiguous because pairs are."""
+    _, prefix = work_layout(o, v)
+
+    def first_triplet(pr):
+        i = 0
+        while (i + 1) * (i + 2) // 2 <= pr:
+            i += 1
+        j = pr - i * (i + 1) // 2
+        return i * (i + 1) * (i + 2) // 6 + j * (j + 1) // 2
+
+    return (prefix[pr0], prefix[pr1]), (first_triplet(pr0), first_triplet(pr1))
+
+
+def shard_items(n_items: int, rank: int, world: int):
+    """Static contiguous split of the work list across ranks (equal item counts)."""
+    return n_items * rank // world, n_items * (rank + 1) // world

@@ -1,0 +1,86 @@
+/*
+ * fermi_pt_b200.h -- C ABI of libfermi_pt_b200.so, the B200-native RCCSD(T) perturbative-triples engine.
+ *
+ * The reference (Fermi.jl, pure Julia) has no FFI for this path; its boundary is the Julia method
+ *     RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::ijk)        src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:20-150
+ * selected by dispatch on an `RpTAlgorithm` singleton                     .../PerturbativeTriples.jl:1-11,51-63
+ * The entry points below are exactly what a Julia `ccall` (or Python ctypes) binding of that method needs:
+ * plain pointers and sizes, no torch / CUDA types.  The Julia glue that binds them is in
+ * fermi.jl_b200/julia/FermiB200.jl and is described in INTEGRATION.md.
+ *
+ * Array arguments are the reference's own arrays, Float64, Julia column-major (first index fastest):
+ *     T1  [i,a]      (o,v)        ccsd.T1            RCCSD.jl:65
+ *     T2  [i,j,a,b]  (o,o,v,v)    ccsd.T2            RCCSD.jl:66
+ *     OVVV[i,a,b,c]  (o,v,v,v)    moints["OVVV"]     ijk.jl:28   (= (ia|bc))
+ *     OOOV[i,j,k,a]  (o,o,o,v)    moints["OOOV"]     ijk.jl:31   (= (ij|ka))
+ *     OVOV[i,a,j,b]  (o,v,o,v)    moints["OVOV"]     ijk.jl:32   (= (ia|jb))
+ *     fo  [i]        (o)          moints["Fii"]      ijk.jl:36
+ *     fv  [a]        (v)          moints["Faa"]      ijk.jl:37
+ *     BOO [Q,i,j]    (naux,o,o)   moints["BOO"]      DFERI.jl:15-29
+ *     BOV [Q,i,a]    (naux,o,v)   moints["BOV"]      DFERI.jl:31-51
+ *     BVV [Q,a,b]    (naux,v,v)   moints["BVV"]      DFERI.jl:53-69
+ * Pointers may be host memory (pageable or pinned) or device memory of the handle's GPU; they are read-only,
+ * caller-owned, and only need to stay valid for the duration of the call.
+ *
+ * Every function returns 0 on success and a nonzero status on failure; fpt_last_error() then describes it
+ * (the Julia glue rethrows it as FermiException, Options.jl:196-199).  There is no CPU fallback: if no
+ * usable GPU is present fpt_create fails.
+ */
+#ifndef FERMI_PT_B200_H
+#define FERMI_PT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fpt_handle fpt_handle;
+
+typedef struct fpt_stats {
+    double upload_ms;      /* host->device copies + layout prep (K4) or DF assembly (K3) of the last upload */
+    double kernel_ms;      /* fused triples kernel of the last compute, CUDA events on the launch stream */
+    double total_ms;       /* host wall clock of the last fpt_triples_* call */
+    double flops;          /* algorithmic flops of the last compute: 12 v^3 (v+o) per non-zero-weight triplet share */
+    double h2d_bytes;      /* bytes copied host->device by the last upload */
+    long long n_items;     /* work items (triplet x block) processed by the last compute */
+    long long n_triplets;  /* non-zero-weight triplets (i>=j>=k, not i=j=k) of the problem */
+    int n_launches;        /* kernels launched by the last upload + compute */
+    int n_sm;              /* SMs of the device */
+} fpt_stats;
+
+/* ngpu must be 1 in this build (multi-GPU runs use one process per GPU, see fpt_compute's item ranges).
+ * devices[0] = CUDA device ordinal (NULL -> current device). */
+int fpt_create(int ngpu, const int* devices, fpt_handle** out);
+int fpt_destroy(fpt_handle* h);
+
+/* replaces RCCSDpT(ccsd, moints, ::ijk) for conventional integrals (ijk.jl:20-150): Et = E(T) */
+int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                     const double* OOOV, const double* OVOV, const double* fo, const double* fv, double* Et,
+                     fpt_stats* stats);
+
+/* same, density-fitted: the (ia|bd), (ij|ka), (ia|jb) blocks that DFERI.jl:88-180 would materialise on the
+ * host are assembled on the device from the B factors */
+int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                   const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
+                   fpt_stats* stats);
+
+/* Staged form of the two calls above (used for sharded multi-GPU runs and kernel-only timing):
+ * upload = copy + layout prep, operands stay resident on the GPU; compute = fused kernel over the item range
+ * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T). */
+int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                    const double* OOOV, const double* OVOV, const double* fo, const double* fv);
+int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                  const double* BOV, const double* BVV, const double* fo, const double* fv);
+int fpt_num_items(fpt_handle* h, long long* n_items);
+int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et_partial, fpt_stats* stats);
+
+/* FP64 pipe calibration for the roofline denominator: variant 0 = DMMA.8x8x4 stream, 1 = DFMA stream.
+ * Returns sustained TFLOP/s over `ms_target` milliseconds of back-to-back launches. */
+int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
+
+const char* fpt_last_error(void);
+const char* fpt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,101 @@
+// Host-side emulator of the fused B200 (T) kernel's data flow (test infrastructure, CPU only).
+//
+// It includes the very same index algebra the CUDA kernels use (fermi.jl_b200/csrc/fpt_layout.h: item decode,
+// block/slot construction, GEMM descriptors, swizzled slot addressing, the per-point energy) and replaces only
+// the tensor-core GEMM and the thread mapping by plain loops.  tests/test_emulator.py builds it with g++ and
+// checks its E(T) against the oracle, so layout bugs are caught without a GPU.
+//
+// Exported C function:
+//   fpt_emulate(o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, item_begin, item_end, &Et)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../fermi.jl_b200/csrc/fpt_layout.h"
+
+using namespace fpt;
+
+extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
+                           const double* OVOV, const double* fo, const double* fv, long long item_begin, long long item_end,
+                           double* Et, long long* nitems_out)
+{
+    Problem P;
+    P.o = o; P.v = v; P.vp = padded_v(v); P.nt = num_tiles(v);
+    P.Kp = roundup(v + o, KGROUP); P.G = P.Kp / KGROUP;
+    P.npair = o * (o + 1) / 2; P.nb = num_blocks(P.nt);
+    std::vector<i64> prefix(P.npair + 1);
+    i64 acc = 0;
+    for (int pr = 0; pr < P.npair; pr++) { int i, j; tri_decode(pr, i, j); prefix[pr] = acc; acc += (i64)num_k(i, j) * P.nb; }
+    prefix[P.npair] = acc;
+    P.nitems = acc;
+    if (nitems_out) *nitems_out = acc;
+    P.pair_prefix = prefix.data();
+
+    // ---- layout prep (same formulas as prep_* kernels) ----
+    std::vector<double> Pt((size_t)o * P.vp * P.vp * P.Kp, 0.0), Qt((size_t)o * o * P.G * P.vp * KGROUP, 0.0),
+        OV2((size_t)o * o * v * v), T1d((size_t)o * v);
+    for (int p = 0; p < o; p++)
+        for (int y = 0; y < v; y++)
+            for (int x = 0; x < v; x++) {
+                double* row = Pt.data() + pt_row(P, p, y, x);
+                for (int d = 0; d < v; d++) row[d] = OVVV[p + (i64)o * (y + (i64)v * (x + (i64)v * d))];
+                for (int l = 0; l < o; l++) row[v + l] = -T2[p + (i64)o * (l + (i64)o * (y + (i64)v * x))];
+            }
+    for (int q = 0; q < o; q++)
+        for (int r = 0; r < o; r++)
+            for (int z = 0; z < v; z++)
+                for (int kappa = 0; kappa < v + o; kappa++) {
+                    double val = kappa < v ? T2[r + (i64)o * (q + (i64)o * (z + (i64)v * kappa))]
+                                           : OOOV[(kappa - v) + (i64)o * (q + (i64)o * (r + (i64)o * z))];
+                    Qt[qt_row(P, q, r, kappa >> 3, z) + (kappa & 7)] = val;
+                }
+    for (int q = 0; q < o; q++)
+        for (int r = 0; r < o; r++)
+            for (int y = 0; y < v; y++)
+                for (int z = 0; z < v; z++)
+                    OV2[(((i64)q * o + r) * v + y) * v + z] = OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))];
+    for (int p = 0; p < o; p++)
+        for (int x = 0; x < v; x++) T1d[(i64)p * v + x] = T1[p + (i64)o * x];
+    P.Pt = Pt.data(); P.Qt = Qt.data(); P.OV2 = OV2.data(); P.T1d = T1d.data(); P.fo = fo; P.fv = fv;
+
+    if (item_end < 0 || item_end > P.nitems) item_end = P.nitems;
+    std::vector<double> W((size_t)MAX_SLOTS * TMAX * TMAX * TMAX);
+    double E = 0.0;
+    for (i64 item = item_begin; item < item_end; item++) {
+        ItemDesc it;
+        item_decode(P, item, it);
+        if (!(it.i >= it.j && it.j >= it.k) || (it.i == it.j && it.j == it.k) || !(it.A >= it.B && it.B >= it.C) || it.A >= P.nt) {
+            fprintf(stderr, "bad item decode %lld -> %d %d %d / %d %d %d\n", item, it.i, it.j, it.k, it.A, it.B, it.C);
+            return 2;
+        }
+        BlockDesc bd;
+        make_block(it.A, it.B, it.C, P.vp, bd);
+        GemmDesc gd[MAX_GEMMS];
+        const int ng = make_gemms(bd, it.i, it.j, it.k, gd);
+        std::fill(W.begin(), W.begin() + (size_t)bd.nslot * bd.slot_elems, 0.0);
+        std::vector<int> hits((size_t)bd.nslot * bd.slot_elems, 0);
+        for (int g = 0; g < ng; g++) {
+            const GemmDesc& G = gd[g];
+            for (int m = 0; m < G.TX * G.TY; m++) {
+                const int yl = m / G.TX, xl = m % G.TX;
+                const double* prow = P.Pt + pt_row(P, G.p, G.y0 + yl, G.x0 + xl);
+                for (int s = 0; s < 2; s++)
+                    for (int zl = 0; zl < G.TZ; zl++) {
+                        double d = 0.0;
+                        for (int kappa = 0; kappa < P.Kp; kappa++)
+                            d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa >> 3, G.z0 + zl) + (kappa & 7)];
+                        const int off = gemm_dest(G, s, xl, yl, zl);
+                        if (off < 0 || off >= bd.nslot * bd.slot_elems) { fprintf(stderr, "dest out of range\n"); return 3; }
+                        W[off] += d;
+                        hits[off]++;
+                    }
+            }
+        }
+        for (size_t t = 0; t < hits.size(); t++)
+            if (hits[t] != 6) { fprintf(stderr, "slot element %zu received %d contributions (want 6)\n", t, hits[t]); return 4; }
+        for (int pt = 0; pt < bd.slot_elems; pt++) E += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
+    }
+    *Et = E;
+    return 0;
+}
