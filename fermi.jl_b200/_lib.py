@@ -27,7 +27,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df",
-           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_last_error", "fpt_version"]
+           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
 def library_path() -> str:
@@ -52,9 +52,11 @@ def load_library():
     L.fpt_num_items.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     L.fpt_compute.argtypes = [vp, ctypes.c_longlong, ctypes.c_longlong, _dp, ctypes.POINTER(Stats)]
     L.fpt_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp]
+    L.fpt_last_profile.argtypes = [vp, _dp]
+    L.fpt_dmma_sweep.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp]
     L.fpt_last_error.restype = ctypes.c_char_p
     L.fpt_version.restype = ctypes.c_char_p
-    for f in EXPORTS[:9]:
+    for f in EXPORTS[:11]:
         getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
@@ -126,4 +128,15 @@ class Engine:
     def fp64_peak(self, variant: int = 0, ms_target: float = 200.0) -> float:
         t = ctypes.c_double()
         self._check(self._L.fpt_fp64_peak(self._h, variant, ms_target, ctypes.byref(t)))
+        return t.value
+
+    def last_profile(self):
+        buf = (ctypes.c_double * 6)()
+        self._check(self._L.fpt_last_profile(self._h, buf))
+        names = ["setup", "zero_prologue", "kloops", "rmw", "energy", "total"]
+        return dict(zip(names, list(buf)))
+
+    def dmma_sweep(self, ilp: int, warps_per_sm: int) -> float:
+        t = ctypes.c_double()
+        self._check(self._L.fpt_dmma_sweep(self._h, ilp, warps_per_sm, ctypes.byref(t)))
         return t.value

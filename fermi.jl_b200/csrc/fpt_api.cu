@@ -56,13 +56,14 @@ struct fpt_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // resident operands
-    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out;
+    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out, prof;
     // staging for raw inputs
     DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
     Problem prob{};
     bool loaded = false;
     fpt_stats last{};
     int launches = 0;
+    int last_grid = 0;
 };
 
 extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
@@ -100,7 +101,7 @@ extern "C" int fpt_destroy(fpt_handle* h)
 {
     if (!h) return 0;
     cudaSetDevice(h->dev);
-    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out,
+    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof,
                       &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
     for (DevBuf* b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -159,6 +160,7 @@ static int setup_problem(fpt_handle* h, int o, int v)
     if (h->partials.ensure((size_t)h->n_sm * 4 * sizeof(double))) return 1;
     if (h->counter.ensure(sizeof(unsigned long long))) return 1;
     if (h->out.ensure(sizeof(double))) return 1;
+    if (h->prof.ensure((size_t)h->n_sm * 6 * sizeof(long long))) return 1;
     CK(cudaMemcpyAsync(h->prefix.p, prefix.data(), prefix.size() * sizeof(i64), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // `prefix` is a local
     P.Pt = h->Pt.d(); P.Qt = h->Qt.d(); P.OV2 = h->OV2.d(); P.T1d = h->T1d.d();
@@ -314,7 +316,9 @@ extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_e
     CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     triples_kernel<<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(P, item_begin, item_end,
-                                                                      (unsigned long long*)h->counter.p, h->partials.d());
+                                                                      (unsigned long long*)h->counter.p, h->partials.d(),
+                                                                      (long long*)h->prof.p);
+    h->last_grid = grid;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     reduce_partials<<<1, 32, 0, h->stream>>>(h->partials.d(), grid, h->out.d());
@@ -394,5 +398,55 @@ extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, doubl
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *tflops = fl * reps / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+// Phase breakdown of the last fpt_compute (cycles summed over CTAs, warp 0's view):
+// out[0..5] = setup, zero+prologue, k-loops, RMW epilogues, energy stage, total
+extern "C" int fpt_last_profile(fpt_handle* h, double* out6)
+{
+    if (!h || !out6) return fail("fpt_last_profile: NULL argument");
+    if (h->last_grid <= 0) return fail("fpt_last_profile: no compute yet");
+    CK(cudaSetDevice(h->dev));
+    std::vector<long long> buf((size_t)h->last_grid * 6);
+    CK(cudaMemcpy(buf.data(), h->prof.p, buf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < 6; t++) out6[t] = 0.0;
+    for (int b = 0; b < h->last_grid; b++)
+        for (int t = 0; t < 6; t++) out6[t] += (double)buf[(size_t)b * 6 + t];
+    return 0;
+}
+
+// DMMA issue study (design aid): sustained TFLOP/s with `ilp` independent accumulators per warp and
+// `warps_per_sm` warps on each SM (1 CTA/SM).
+extern "C" int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops)
+{
+    if (!h || !tflops) return fail("fpt_dmma_sweep: NULL argument");
+    CK(cudaSetDevice(h->dev));
+    if (h->out.ensure(sizeof(double))) return 1;
+    const int iters = 20000 / ilp;
+    const int threads = warps_per_sm * 32;
+    if (threads < 32 || threads > 1024) return fail("fpt_dmma_sweep: warps_per_sm out of range");
+    void (*k)(double*, int, double) = nullptr;
+    switch (ilp) {
+    case 1: k = dmma_ilp_kernel<1>; break;
+    case 2: k = dmma_ilp_kernel<2>; break;
+    case 4: k = dmma_ilp_kernel<4>; break;
+    case 8: k = dmma_ilp_kernel<8>; break;
+    case 16: k = dmma_ilp_kernel<16>; break;
+    case 32: k = dmma_ilp_kernel<32>; break;
+    default: return fail("fpt_dmma_sweep: ilp must be 1,2,4,8,16,32");
+    }
+    const size_t smem = 120 * 1024;   // > half of the SM: forces 1 CTA/SM
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<h->n_sm, threads, smem, h->stream>>>(h->out.d(), iters, 1e-3);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < 5; r++) k<<<h->n_sm, threads, smem, h->stream>>>(h->out.d(), iters, 1e-3);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *tflops = 5.0 * h->n_sm * warps_per_sm * (double)iters * ilp * 512.0 / (ms * 1e-3) / 1e12;
     return 0;
 }

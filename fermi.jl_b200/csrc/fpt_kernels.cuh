@@ -84,8 +84,9 @@ __device__ __forceinline__ void fill_q_stage(const Problem& P, const Ctl* ctl, d
 // ---------------------------------------------------------------------------------------------------
 template <int MTW, int NT>
 __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, double* Wsm, double* Qsm, int g, int& sp,
-                                          int nchunks, int tid)
+                                          int nchunks, int tid, long long* prof)
 {
+    const long long tg0 = clock64();
     const GemmDesc& gd = ctl->gemm[g];
     const int lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, kk = lane & 3;
@@ -141,38 +142,46 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, doub
 #pragma unroll
                 for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) {
-                        dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl & 1][mt].x, b[ct].x);
-                        dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl & 1][mt].y, b[ct].y);
-                    }
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl & 1][mt].x, b[ct].x);
+#pragma unroll
+                for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl & 1][mt].y, b[ct].y);
             }
         }
     }
 
-    // RMW epilogue: D element e of (mt,ct): row (xl,yl), zl = 4ct + kk, column set s = e
+    const long long tg1 = clock64();
+    // RMW epilogue: D element e of (mt,ct): row (xl,yl), zl = 4ct + kk, column set s = e.
+    // When X and Z are the same tile, D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of *different* warps hit the same W
+    // element, so the two column sets are separated by a barrier.
 #pragma unroll
-    for (int mt = 0; mt < MTW; mt++) {
-        if (valid[mt]) {
+    for (int e = 0; e < 2; e++) {
+        if (e == 1 && gd.diag_xz) __syncthreads();
 #pragma unroll
-            for (int ct = 0; ct < NT; ct++)
+        for (int mt = 0; mt < MTW; mt++) {
+            if (valid[mt]) {
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
+                for (int ct = 0; ct < NT; ct++) {
                     const int off = gemm_dest(gd, e, xl[mt], yl[mt], 4 * ct + kk);
                     Wsm[off] += acc[mt][ct][e];
                 }
+            }
         }
     }
+    prof[2] += tg1 - tg0;
+    prof[3] += clock64() - tg1;
 }
 
 template <int MTW>
 __device__ __forceinline__ void gemm_dispatch_nt(const Problem& P, const Ctl* ctl, double* Wsm, double* Qsm, int g, int& sp,
-                                                 int nchunks, int tid, int nt)
+                                                 int nchunks, int tid, int nt, long long* prof)
 {
     switch (nt) {
-    case 1: gemm_body<MTW, 1>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid); break;
-    case 2: gemm_body<MTW, 2>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid); break;
-    case 3: gemm_body<MTW, 3>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid); break;
-    default: gemm_body<MTW, 4>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid); break;
+    case 1: gemm_body<MTW, 1>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, prof); break;
+    case 2: gemm_body<MTW, 2>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, prof); break;
+    case 3: gemm_body<MTW, 3>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, prof); break;
+    default: gemm_body<MTW, 4>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, prof); break;
     }
 }
 
@@ -193,8 +202,10 @@ __device__ __forceinline__ double block_energy(const Problem& P, const Ctl* ctl,
 // The fused persistent kernel.  grid = #SMs (1 CTA/SM: ~220 KB smem), block = 256.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
-triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* counter, double* partials)
+triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* counter, double* partials, long long* prof_out)
 {
+    long long prof[6] = {0, 0, 0, 0, 0, 0};   // cycles: setup, zero+prologue, k-loops, RMW, energy, total (warp 0's view)
+    const long long tk0 = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Wsm = reinterpret_cast<double*>(smem_raw);
     double* Qsm = Wsm + WSLOT_DOUBLES;
@@ -204,6 +215,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     double esum = 0.0;
 
     for (;;) {
+        const long long ts0 = clock64();
         __syncthreads();
         if (tid == 0) {
             const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
@@ -216,6 +228,8 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         }
         __syncthreads();
         if (ctl->cur_item >= item_end) break;
+        const long long ts1 = clock64();
+        prof[0] += ts1 - ts0;
 
         {   // zero the live W slots
             const int nz = ctl->bd.nslot * ctl->bd.slot_elems;   // multiple of 64
@@ -226,22 +240,28 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         fill_q_stage(P, ctl, Qsm, 0, nchunks, tid);
         fill_q_stage(P, ctl, Qsm, 1, nchunks, tid);
         const int ngemm = ctl->ngemm;
+        prof[1] += clock64() - ts1;
         for (int g = 0; g < ngemm; g++) {
             const GemmDesc& gd = ctl->gemm[g];
             const int rt_total = (gd.TX * gd.TY) >> 3;
             const int mtw = (rt_total + NWARPS - 1) / NWARPS;
             const int nt = gd.TZ >> 2;
             switch (mtw) {
-            case 1: gemm_dispatch_nt<1>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt); break;
-            case 2: gemm_dispatch_nt<2>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt); break;
-            case 3: gemm_dispatch_nt<3>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt); break;
-            default: gemm_dispatch_nt<4>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt); break;
+            case 1: gemm_dispatch_nt<1>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt, prof); break;
+            case 2: gemm_dispatch_nt<2>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt, prof); break;
+            case 3: gemm_dispatch_nt<3>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt, prof); break;
+            default: gemm_dispatch_nt<4>(P, ctl, Wsm, Qsm, g, sp, nchunks, tid, nt, prof); break;
             }
         }
         cp_async_wait<0>();
         __syncthreads();
+        const long long te0 = clock64();
         esum += block_energy(P, ctl, Wsm, tid);
+        prof[4] += clock64() - te0;
     }
+    prof[5] = clock64() - tk0;
+    if (prof_out && tid == 0)
+        for (int t = 0; t < 6; t++) prof_out[blockIdx.x * 6 + t] = prof[t];
 
     // block reduction (warp shuffle, then one thread sums the 8 warp partials in fixed order)
 #pragma unroll
@@ -381,6 +401,24 @@ __global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, 
 #pragma unroll
         for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
     if (s == 12345.678) out[0] = s;   // keep the work alive
+}
+
+// DMMA issue study: ILP independent accumulators per warp, launched with 1 CTA/SM and a chosen warp count
+template <int ILP>
+__global__ void dmma_ilp_kernel(double* out, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - a;
+    double acc[ILP][2];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i][0] = acc[i][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;
 }
 
 __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters, double seed)

@@ -139,6 +139,7 @@ struct GemmDesc {
     int dbase[2];
     int dsel[2];            // packed: ra | rb<<2 | rc<<4   (0=x,1=y,2=z)
     int dTb[2], dTc[2];
+    int diag_xz;            // X and Z are the same tile: D(s=0) and D(s=1) of different threads alias in the W slot
 };
 
 // occ = (i,j,k).  Builds the 3*nslot GEMMs of an item.  Returns their number.
@@ -155,6 +156,7 @@ FPT_HD int make_gemms(const BlockDesc& bd, int i, int j, int k, GemmDesc* gd)
             g.p = occ[pi]; g.q = occ[qi]; g.r = occ[ri];
             g.x0 = bd.t0[cx]; g.y0 = bd.t0[cy]; g.z0 = bd.t0[cz];
             g.TX = bd.ts[cx]; g.TY = bd.ts[cy]; g.TZ = bd.ts[cz];
+            g.diag_xz = (bd.tile[cx] == bd.tile[cz]);
             for (int s = 0; s < 2; s++) {
                 // pairing: x <-> (s ? r : q), y <-> p, z <-> (s ? q : r).  sel[pos] = which of x/y/z pairs with occ pos
                 int sel[3];
