@@ -12,7 +12,8 @@
 #include <vector>
 
 #include "../../include/fermi_pt_b200.h"
-#include "fpt_kernels.cuh"
+#include "fpt_aux_kernels.cuh"
+#include "fpt_triples.cuh"
 
 using namespace fpt;
 
@@ -64,6 +65,8 @@ struct fpt_handle {
     fpt_stats last{};
     int launches = 0;
     int last_grid = 0;
+    bool profiling = false;
+    bool last_profiled = false;
 };
 
 extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
@@ -92,7 +95,8 @@ extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(triples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
     *out = h;
     return 0;
 }
@@ -315,10 +319,14 @@ extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_e
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
     CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    triples_kernel<<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(P, item_begin, item_end,
-                                                                      (unsigned long long*)h->counter.p, h->partials.d(),
-                                                                      (long long*)h->prof.p);
+    if (h->profiling)
+        triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(
+            P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
+    else
+        triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(
+            P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
     h->last_grid = grid;
+    h->last_profiled = h->profiling;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     reduce_partials<<<1, 32, 0, h->stream>>>(h->partials.d(), grid, h->out.d());
@@ -401,12 +409,19 @@ extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, doubl
     return 0;
 }
 
+extern "C" int fpt_set_profiling(fpt_handle* h, int on)
+{
+    if (!h) return fail("fpt_set_profiling: NULL handle");
+    h->profiling = on != 0;
+    return 0;
+}
+
 // Phase breakdown of the last fpt_compute (cycles summed over CTAs, warp 0's view):
 // out[0..5] = setup, zero+prologue, k-loops, RMW epilogues, energy stage, total
 extern "C" int fpt_last_profile(fpt_handle* h, double* out6)
 {
     if (!h || !out6) return fail("fpt_last_profile: NULL argument");
-    if (h->last_grid <= 0) return fail("fpt_last_profile: no compute yet");
+    if (h->last_grid <= 0 || !h->last_profiled) return fail("fpt_last_profile: the last compute was not profiled (fpt_set_profiling)");
     CK(cudaSetDevice(h->dev));
     std::vector<long long> buf((size_t)h->last_grid * 6);
     CK(cudaMemcpy(buf.data(), h->prof.p, buf.size() * sizeof(long long), cudaMemcpyDeviceToHost));

@@ -1,0 +1,248 @@
+// Auxiliary sm_100a kernels of the B200 RCCSD(T) path:
+//   K4  prep_*            layout prep (ijk.jl:24-32 replaced by one pass into the Pt/Qt/OV2/T1d layouts)
+//   K3  df_gemm_kernel    density-fitted assembly of the same layouts from BOO/BOV/BVV (DFERI.jl:88-180)
+//   reduce_partials       fixed-order final sum (ijk.jl:145)
+//   peak_* / dmma_ilp_*   FP64 pipe calibration (roofline denominator)
+#pragma once
+#include <cuda_runtime.h>
+#include "fpt_layout.h"
+#include "fpt_ptx.cuh"
+
+namespace fpt {
+
+__global__ void reduce_partials(const double* partials, int n, double* out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int t = 0; t < n; t++) s += partials[t];
+        out[0] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: layout prep.  Sources are the reference's column-major arrays (first index fastest).
+// ---------------------------------------------------------------------------------------------------
+// Pt[p][y][x][d] = OVVV[p,y,x,d] for d in [d0, d0+dn); `src` points at OVVV[:,:,:,d0].
+__global__ void prep_pt_particle(Problem P, double* Pt, const double* __restrict__ src, int d0, int dn)
+{
+    __shared__ double tile[32][33];
+    const int o = P.o, v = P.v;
+    const i64 ov = (i64)o * v;
+    const int x = blockIdx.z;
+    const i64 py0 = (i64)blockIdx.x * 32;
+    const int dd0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int kk = 0; kk < 32; kk += 8) {
+        const int dd = dd0 + ty + kk;
+        const i64 py = py0 + tx;
+        if (dd < dn && py < ov) tile[ty + kk][tx] = src[py + ov * ((i64)x + (i64)v * dd)];
+    }
+    __syncthreads();
+    for (int kk = 0; kk < 32; kk += 8) {
+        const i64 py = py0 + ty + kk;
+        const int dd = dd0 + tx;
+        if (dd < dn && py < ov) {
+            const int p = (int)(py % o), y = (int)(py / o);
+            Pt[pt_row(P, p, y, x) + d0 + dd] = tile[tx][ty + kk];
+        }
+    }
+}
+
+// Pt[p][y][x][v+l] = -T2[p,l,y,x]
+__global__ void prep_pt_hole(Problem P, double* Pt, const double* __restrict__ T2)
+{
+    const int o = P.o, v = P.v;
+    const i64 n = (i64)o * v * v * o;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int l = (int)(idx % o);
+        i64 t = idx / o;
+        const int x = (int)(t % v); t /= v;
+        const int y = (int)(t % v);
+        const int p = (int)(t / v);
+        Pt[pt_row(P, p, y, x) + v + l] = -T2[p + (i64)o * (l + (i64)o * (y + (i64)v * x))];
+    }
+}
+
+// Qt[(q,r)][g][z][kk8]: kappa<v: T2[r,q,z,kappa]; v<=kappa<v+o: OOOV[kappa-v,q,r,z]; else 0
+__global__ void prep_qt(Problem P, double* Qt, const double* __restrict__ T2, const double* __restrict__ OOOV)
+{
+    const int o = P.o, v = P.v;
+    const i64 n = (i64)o * o * P.G * P.vp * KGROUP;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int k8 = (int)(idx % KGROUP);
+        i64 t = idx / KGROUP;
+        const int z = (int)(t % P.vp); t /= P.vp;
+        const int g = (int)(t % P.G); t /= P.G;
+        const int r = (int)(t % o);
+        const int q = (int)(t / o);
+        const int kappa = g * KGROUP + k8;
+        double val = 0.0;
+        if (z < v) {
+            if (kappa < v) val = T2[r + (i64)o * (q + (i64)o * (z + (i64)v * kappa))];
+            else if (kappa < v + o) val = OOOV[(kappa - v) + (i64)o * (q + (i64)o * (r + (i64)o * z))];
+        }
+        Qt[idx] = val;
+    }
+}
+
+// OV2[(q,r)][y][z] = OVOV[q,y,r,z]
+__global__ void prep_ov2(Problem P, double* OV2, const double* __restrict__ OVOV)
+{
+    const int o = P.o, v = P.v;
+    const i64 n = (i64)o * o * v * v;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int z = (int)(idx % v);
+        i64 t = idx / v;
+        const int y = (int)(t % v); t /= v;
+        const int r = (int)(t % o);
+        const int q = (int)(t / o);
+        OV2[idx] = OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))];
+    }
+}
+
+// T1d[p][x] = T1[p,x]
+__global__ void prep_t1(Problem P, double* T1d, const double* __restrict__ T1)
+{
+    const int o = P.o, v = P.v;
+    const int n = o * v;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int x = idx % v, p = idx / v;
+        T1d[idx] = T1[p + (i64)o * x];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 pipe calibration (roofline denominator): register-resident DMMA.8x8x4 / DFMA streams
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x * 1e-9, a1 = a0 * 0.5, a2 = a0 * 0.25, a3 = a0 * 0.125;
+    double b0 = 1.0 + a0, b1 = 1.0 - a0, b2 = 0.5 + a0, b3 = 0.5 - a0;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+        const double av[4] = {a0, a1, a2, a3}, bv[4] = {b0, b1, b2, b3};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;   // keep the work alive
+}
+
+// DMMA issue study: ILP independent accumulators per warp, launched with 1 CTA/SM and a chosen warp count
+template <int ILP>
+__global__ void __launch_bounds__(1024) dmma_ilp_kernel(double* out, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - a;
+    double acc[ILP][2];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i][0] = acc[i][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters, double seed)
+{
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - a * 1e-3;
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = i * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], b, a);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace fpt
+
+// ---------------------------------------------------------------------------------------------------
+// K3: density-fitted assembly.  C(m,n) = sum_Q A[Q + naux*rowA(m)] * B[Q + naux*rowB(n)] on DMMA.8x8x4, written
+// straight into the device layouts (the o*v^3 tensor never exists on the host -- the reference materialises it in
+// DFERI.jl:156-180).  MODE 0: Pt particle part from BOV,BVV.  MODE 1: Qt hole part (OOOV) from BOO,BOV.
+// MODE 2: OV2 (OVOV) from BOV,BOV.  CTA = 4 warps, 64x64 tile, fragments loaded straight from global (L1-shared).
+// ---------------------------------------------------------------------------------------------------
+namespace fpt {
+
+template <int MODE>
+__device__ __forceinline__ void df_store(const Problem& P, double* out, int m, int n, double val)
+{
+    const int o = P.o, v = P.v;
+    if (MODE == 0) {
+        const int p = m % o, y = m / o, d = n % v, x = n / v;
+        out[pt_row(P, p, y, x) + d] = val;
+    } else if (MODE == 1) {
+        const int l = m % o, q = m / o, r = n % o, z = n / o;
+        const int kappa = v + l;
+        out[qt_row(P, q, r, kappa >> 3, z) + (kappa & 7)] = val;
+    } else {
+        const int q = m % o, y = m / o, r = n % o, z = n / o;
+        out[(((i64)q * o + r) * v + y) * v + z] = val;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) df_gemm_kernel(Problem P, double* out, const double* __restrict__ A,
+                                                      const double* __restrict__ B, int M, int N, int naux)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = lane >> 2, kk = lane & 3;
+    const int m0 = blockIdx.x * 64 + (warp >> 1) * 32;
+    const int n0 = blockIdx.y * 64 + (warp & 1) * 32;
+    const double* ap[4];
+    const double* bp[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        int m = m0 + 8 * t + r; if (m >= M) m = M - 1;
+        ap[t] = A + (i64)naux * m;
+        int n = n0 + 8 * t + r; if (n >= N) n = N - 1;
+        int rowb = n;
+        if (MODE == 0) { const int d = n % P.v, x = n / P.v; rowb = x + P.v * d; }
+        bp[t] = B + (i64)naux * rowb;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < naux; k0 += 4) {
+        const int k = k0 + kk;
+        const bool ok = k < naux;
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { a[t] = ok ? __ldg(ap[t] + k) : 0.0; b[t] = ok ? __ldg(bp[t] + k) : 0.0; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int m = m0 + 8 * i + r, n = n0 + 8 * j + 2 * kk + e;
+                if (m < M && n < N) df_store<MODE>(P, out, m, n, acc[i][j][e]);
+            }
+}
+
+}  // namespace fpt

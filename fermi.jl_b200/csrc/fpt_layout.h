@@ -192,6 +192,38 @@ FPT_HD int gemm_dest(const GemmDesc& g, int s, int xl, int yl, int zl)
     return g.dbase[s] + slot_index(la, lb, lc, g.dTb[s], g.dTc[s]);
 }
 
+// Fast form of gemm_dest for the RMW epilogue when the destination slot has Tc == 16: for a fixed thread
+// (xl, yl, kk) the element for column tile ct (zl = 4*ct + kk) is
+//     off(ct) = lin0 + ct*zs + ((((hh + dh*ct) & 3) << 2) | ((ll + dl*ct) & 3))
+// (derived from slot_index; which of la/lb/lc is supplied by z decides zs, dh, dl).
+struct DestIter { int lin0, zs, hh, ll, dh, dl; };
+
+FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, DestIter& it)
+{
+    if (g.dTc[s] != 16) return false;
+    const int sel = g.dsel[s];
+    const int sa = sel & 3, sb = (sel >> 2) & 3, sc = (sel >> 4) & 3;
+    const int Tb = g.dTb[s];
+    // coordinates with zl = kk (ct = 0)
+    const int la = pick3(sa, xl, yl, kk), lb = pick3(sb, xl, yl, kk), lc = pick3(sc, xl, yl, kk);
+    if (sc == 2) {
+        it.lin0 = (la * Tb + lb) * 16; it.zs = 0;
+        it.hh = (lb & 3) + kk + (la >> 2); it.ll = (la & 3) + kk + (lb >> 2); it.dh = 1; it.dl = 0;
+    } else if (sb == 2) {
+        it.lin0 = (la * Tb + kk) * 16; it.zs = 64;
+        it.hh = kk + (lc & 3) + (lc >> 2) + (la >> 2); it.ll = (la & 3) + (lc & 3); it.dh = 0; it.dl = 1;
+    } else {
+        it.lin0 = (kk * Tb + lb) * 16; it.zs = 64 * Tb;
+        it.hh = (lb & 3) + (lc & 3) + (lc >> 2); it.ll = kk + (lc & 3) + (lb >> 2); it.dh = 1; it.dl = 0;
+    }
+    it.lin0 += g.dbase[s];
+    return true;
+}
+FPT_HD int dest_iter_off(const DestIter& it, int ct)
+{
+    return it.lin0 + ct * it.zs + ((((it.hh + it.dh * ct) & 3) << 2) | ((it.ll + it.dl * ct) & 3));
+}
+
 // ---- problem description --------------------------------------------------------------------------
 struct Problem {
     int o, v, vp, nt, Kp, G;
@@ -252,9 +284,15 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     const double* t1i = P.T1d + (i64)i * v;
     const double* t1j = P.T1d + (i64)j * v;
     const double* t1k = P.T1d + (i64)k * v;
-    const double* ovjk = P.OV2 + ((i64)j * o + k) * v * v;
-    const double* ovik = P.OV2 + ((i64)i * o + k) * v * v;
-    const double* ovij = P.OV2 + ((i64)i * o + j) * v * v;
+    // OV2[(q,r)][y][z] = (qy|rz) = OV2[(r,q)][z][y]: always index so that the virtual that comes later in (a,b,c)
+    // is the contiguous one -- lanes run over c, so every load is either coalesced or a broadcast.
+    const i64 vv2 = (i64)v * v;
+    const double* ovjk = P.OV2 + ((i64)j * o + k) * vv2;
+    const double* ovkj = P.OV2 + ((i64)k * o + j) * vv2;
+    const double* ovik = P.OV2 + ((i64)i * o + k) * vv2;
+    const double* ovki = P.OV2 + ((i64)k * o + i) * vv2;
+    const double* ovij = P.OV2 + ((i64)i * o + j) * vv2;
+    const double* ovji = P.OV2 + ((i64)j * o + i) * vv2;
     double w[6], vv[6];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -265,7 +303,10 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
         const int lx = pick3(c0, al, bl, cl), ly = pick3(c1, al, bl, cl), lz = pick3(c2, al, bl, cl);
         const int off = bd.slot_of_perm[m] * bd.slot_elems + slot_index(lx, ly, lz, bd.ts[c1], bd.ts[c2]);
         w[m] = Wsm[off];
-        vv[m] = w[m] + t1i[x] * ovjk[(i64)y * v + z] + ovik[(i64)x * v + z] * t1j[y] + ovij[(i64)x * v + y] * t1k[z];
+        const double g_jk = (c2 > c1) ? ovjk[(i64)y * v + z] : ovkj[(i64)z * v + y];   // (jy|kz)
+        const double g_ik = (c2 > c0) ? ovik[(i64)x * v + z] : ovki[(i64)z * v + x];   // (ix|kz)
+        const double g_ij = (c1 > c0) ? ovij[(i64)x * v + y] : ovji[(i64)y * v + x];   // (ix|jy)
+        vv[m] = w[m] + t1i[x] * g_jk + g_ik * t1j[y] + g_ij * t1k[z];
     }
     const double Dd = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[a] - P.fv[b] - P.fv[c];
     return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));

@@ -1,0 +1,359 @@
+// K1+K2: the fused, persistent, warp-specialised RCCSD(T) kernel for sm_100a.
+//
+//   W build   ijk.jl:108-115 (== ijk2.jl:110-153)  FP64 tensor-core DMMA.8x8x4, P rows streamed global->registers,
+//                                                  Q rows staged by TMA bulk copies (cp.async.bulk + mbarrier)
+//   6-fold permutation + V + denominators + energy  ijk.jl:116-136, on the W slots held in shared memory;
+//                                                  W and V never go to HBM
+//   accumulation                                   ijk.jl:133,145: per-thread FP64 partial, warp-shuffle, per-CTA partial
+//
+// CTA = 8 consumer warps + 1 producer warp (288 threads, 168 registers each), 1 CTA / SM, grid = #SMs.
+//   producer (warp 16, lane 0): pulls items off the global counter, decodes them into a double-buffered control
+//       block (item / block / GEMM descriptors) and streams the Q operand chunks of all GEMMs of the item through a
+//       3-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
+//       through `empty` mbarriers, so it runs ahead of the consumers across GEMM and item boundaries.
+//   consumers: for each P-stationary GEMM  D[TX*TY x 2*TZ] = P_p . [Q_qr | Q_rq]  every warp owns <= 4 row tiles
+//       (8 rows) x all column tiles; A fragments come straight from global memory (each P row is used by exactly one
+//       warp, kappa-contiguous, 16 B per lane, prefetched one kappa-group ahead), B fragments from the ring.  The
+//       accumulators are then added into the W slots (swizzled, see fpt_layout.h), and after the last GEMM the
+//       energy of the block's a>=b>=c points is evaluated from the slots.
+#pragma once
+#include <cuda_runtime.h>
+#include "fpt_layout.h"
+#include "fpt_ptx.cuh"
+
+namespace fpt {
+
+constexpr int NCWARPS = 8;                         // consumer warps (9 warps -> 168 registers/thread)
+constexpr int NCTHREADS = NCWARPS * 32;            // 256
+constexpr int NTHREADS = NCTHREADS + 32;           // + producer warp
+constexpr int QSTAGES = 3;
+constexpr int QBLK = (TMAX + 1) * KGROUP;          // doubles per (group, s) block: TZ rows of 8 kappa + 64 B bank skew
+constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 1088 doubles = 8704 B
+constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
+constexpr int MTW_MAX = 4;
+constexpr int APREF = 1;                           // A-fragment prefetch distance in kappa groups
+constexpr int ABUF = 2;                            // group gg lives in buffer gg % ABUF = gl % ABUF (CHUNK_GROUPS is even)
+static_assert(CHUNK_GROUPS % ABUF == 0 && APREF < ABUF, "A-fragment ring is indexed by the group's position in its chunk");
+
+struct Ctl {
+    i64 cur_item;          // < 0: no more work
+    ItemDesc item;
+    BlockDesc bd;
+    int ngemm;
+    GemmDesc gemm[MAX_GEMMS];
+};
+
+struct SmemTail {
+    Ctl ctl[2];
+    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2];
+    double red[NCWARPS];
+};
+
+constexpr size_t TRIPLES_SMEM_BYTES = (size_t)(WSLOT_DOUBLES + QSTAGES * QSTAGE_DOUBLES) * sizeof(double) + sizeof(SmemTail);
+
+__device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
+
+// ---------------------------------------------------------------------------------------------------
+// producer: one thread
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
+                                           double* Qsm, SmemTail* tail)
+{
+    const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+    int stage = 0;
+    uint32_t sphase = 0;
+    for (uint32_t n = 0;; n++) {
+        const int slot = n & 1;
+        Ctl* ctl = &tail->ctl[slot];
+        mbar_wait((uint64_t*)&tail->item_empty[slot], ((n >> 1) & 1) ^ 1);
+        const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
+        if (it >= item_end) {
+            ctl->cur_item = -1;
+            mbar_arrive((uint64_t*)&tail->item_full[slot]);
+            break;
+        }
+        ctl->cur_item = it;
+        item_decode(P, it, ctl->item);
+        make_block(ctl->item.A, ctl->item.B, ctl->item.C, P.vp, ctl->bd);
+        ctl->ngemm = make_gemms(ctl->bd, ctl->item.i, ctl->item.j, ctl->item.k, ctl->gemm);
+        mbar_arrive((uint64_t*)&tail->item_full[slot]);
+        const int ngemm = ctl->ngemm;
+        for (int g = 0; g < ngemm; g++) {
+            const GemmDesc& gd = ctl->gemm[g];
+            const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
+            for (int c = 0; c < nchunks; c++) {
+                const int g0 = c * CHUNK_GROUPS;
+                const int ng = min(CHUNK_GROUPS, P.G - g0);
+                mbar_wait((uint64_t*)&tail->empty[stage], sphase ^ 1);
+                uint64_t* fb = (uint64_t*)&tail->full[stage];
+                mbar_arrive_expect_tx(fb, (uint32_t)ng * 2u * row_bytes);
+                double* st = Qsm + stage * QSTAGE_DOUBLES;
+                for (int gl = 0; gl < ng; gl++) {
+                    tma_bulk_g2s(st + (gl * 2 + 0) * QBLK, P.Qt + qt_row(P, gd.q, gd.r, g0 + gl, gd.z0), row_bytes, fb);
+                    tma_bulk_g2s(st + (gl * 2 + 1) * QBLK, P.Qt + qt_row(P, gd.r, gd.q, g0 + gl, gd.z0), row_bytes, fb);
+                }
+                if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumer: row pointers + first APREF A-fragment groups of a GEMM (issued before the previous GEMM's RMW epilogue so
+// that their latency hides behind it)
+// ---------------------------------------------------------------------------------------------------
+struct RowSet {
+    const double* base;        // P row of (x0, y0) for this p, + 2*kk   (warp-uniform part + lane kk)
+    int off[MTW_MAX];          // per row-tile offset in doubles
+    int nvalid;                // number of valid row tiles of this warp (0..mtw)
+    int rt0;                   // first row tile of this warp
+};
+
+__device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd, int warp, int lane, RowSet& rs)
+{
+    const int r = lane >> 2, kk = lane & 3;
+    const int rt_total = (gd.TX * gd.TY) >> 3;
+    const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
+    rs.base = P.Pt + pt_row(P, gd.p, gd.y0, gd.x0) + 2 * kk;
+    rs.nvalid = 0;
+    rs.rt0 = warp * mtw;
+#pragma unroll
+    for (int mt = 0; mt < MTW_MAX; mt++) {
+        const int rt = warp * mtw + mt;
+        const bool ok = (mt < mtw) && (rt < rt_total);
+        rs.nvalid += ok ? 1 : 0;
+        const int m = ok ? rt * 8 + r : r;
+        const int yl = m / gd.TX;
+        const int xl = m - yl * gd.TX;
+        rs.off[mt] = (yl * P.vp + xl) * P.Kp;
+    }
+}
+
+template <int MTW>
+__device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, double2 (&a)[ABUF][MTW_MAX])
+{
+#pragma unroll
+    for (int d = 0; d < APREF; d++)
+        if (d < P.G) {
+#pragma unroll
+            for (int mt = 0; mt < MTW; mt++) a[d][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + d * KGROUP);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// consumer: k-loop of one GEMM.  acc[mt][ct][e]: row tile mt, column tile ct, D element e.
+// Column n of tile ct is (zl = 4ct + (n>>1), s = n&1), so a lane's two D elements are (zl = 4ct + kk, s = e).
+// ---------------------------------------------------------------------------------------------------
+template <int MTW, int NT>
+__device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double2 (&a)[ABUF][MTW_MAX],
+                                           double (&acc)[MTW][NT][2], const double* Qsm, SmemTail* tail, int& stage,
+                                           uint32_t& sphase, int lane)
+{
+    const int kk = lane & 3, n = lane >> 2;
+    const int boff = ((n & 1) * QBLK) + (n >> 1) * KGROUP + 2 * kk;   // s block + row zl(ct=0) + kappa pair
+    const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+#pragma unroll
+    for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+        for (int ct = 0; ct < NT; ct++) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
+
+    for (int c = 0; c < nchunks; c++) {
+        const int g0 = c * CHUNK_GROUPS;
+        const int ng = min(CHUNK_GROUPS, P.G - g0);
+        mbar_wait((uint64_t*)&tail->full[stage], sphase);
+        const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
+#pragma unroll
+        for (int gl = 0; gl < CHUNK_GROUPS; gl++) {
+            if (gl < ng) {
+                const int gg = g0 + gl;
+                if (gg + APREF < P.G) {
+#pragma unroll
+                    for (int mt = 0; mt < MTW; mt++)
+                        a[(gl + APREF) % ABUF][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + (gg + APREF) * KGROUP);
+                }
+                double2 b[NT];
+#pragma unroll
+                for (int ct = 0; ct < NT; ct++)
+                    b[ct] = *reinterpret_cast<const double2*>(st + gl * 2 * QBLK + ct * 4 * KGROUP);
+#pragma unroll
+                for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[ct].x);
+#pragma unroll
+                for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[ct].y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive((uint64_t*)&tail->empty[stage]);
+        if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
+    }
+}
+
+// RMW of the accumulators into the W slots
+template <int MTW, int NT>
+__device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, const double (&acc)[MTW][NT][2], double* Wsm,
+                                         int lane)
+{
+    const int kk = lane & 3, r = lane >> 2;
+    int xl[MTW], yl[MTW];
+#pragma unroll
+    for (int mt = 0; mt < MTW; mt++) {
+        const int m = (rs.rt0 + mt) * 8 + r;
+        yl[mt] = m / gd.TX;
+        xl[mt] = m - yl[mt] * gd.TX;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
+        if (e == 1 && gd.diag_xz) consumer_bar();
+#pragma unroll
+        for (int mt = 0; mt < MTW; mt++) {
+            if (mt < rs.nvalid) {
+                DestIter it;
+                if (dest_iter_init(gd, e, xl[mt], yl[mt], kk, it)) {
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
+                } else {
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) Wsm[gemm_dest(gd, e, xl[mt], yl[mt], 4 * ct + kk)] += acc[mt][ct][e];
+                }
+            }
+        }
+    }
+}
+
+// one GEMM of an item: k-loop, then (overlapped with the RMW epilogue) the next GEMM's row setup and first A loads
+template <int MTW, int NT, bool PROF>
+__device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int g, RowSet& rs, double2 (&a)[ABUF][MTW_MAX],
+                                          double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase, int warp,
+                                          int lane, long long* prof)
+{
+    const GemmDesc& gd = ctl->gemm[g];
+    double acc[MTW][NT][2];
+    long long t0 = 0, t1 = 0;
+    if (PROF) t0 = clock64();
+    gemm_kloop<MTW, NT>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane);
+    if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
+    const RowSet rs_cur = rs;
+    if (g + 1 < ctl->ngemm) {
+        rows_setup(P, ctl->gemm[g + 1], warp, lane, rs);
+        a_prologue<MTW_MAX>(P, rs, a);
+    }
+    consumer_bar();   // every warp has finished the previous GEMM's RMW (and the zeroing)
+    gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane);
+    if (PROF) prof[3] += clock64() - t1;
+}
+
+#define FPT_DISPATCH_NT(MTWc, NTv, CALL)                                   \
+    switch (NTv) {                                                         \
+    case 1: { constexpr int MTW = MTWc, NT = 1; CALL; } break;             \
+    case 2: { constexpr int MTW = MTWc, NT = 2; CALL; } break;             \
+    case 3: { constexpr int MTW = MTWc, NT = 3; CALL; } break;             \
+    default: { constexpr int MTW = MTWc, NT = 4; CALL; } break;            \
+    }
+#define FPT_DISPATCH(MTWv, NTv, CALL)                                      \
+    do {                                                                   \
+        switch (MTWv) {                                                    \
+        case 1: FPT_DISPATCH_NT(1, NTv, CALL) break;                       \
+        case 2: FPT_DISPATCH_NT(2, NTv, CALL) break;                       \
+        case 3: FPT_DISPATCH_NT(3, NTv, CALL) break;                       \
+        default: FPT_DISPATCH_NT(4, NTv, CALL) break;                      \
+        }                                                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// The kernel.  PROF: record a phase breakdown (cycles, warp 0's view) into prof_out[blockIdx*6 + 0..5] =
+// {wait-for-item, zero, k-loops, RMW (+barriers), energy, total}.
+// ---------------------------------------------------------------------------------------------------
+template <bool PROF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* counter, double* partials, long long* prof_out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Wsm = reinterpret_cast<double*>(smem_raw);
+    double* Qsm = Wsm + WSLOT_DOUBLES;
+    SmemTail* tail = reinterpret_cast<SmemTail*>(Qsm + QSTAGES * QSTAGE_DOUBLES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < QSTAGES; s++) { mbar_init((uint64_t*)&tail->full[s], 1); mbar_init((uint64_t*)&tail->empty[s], NCWARPS); }
+        for (int s = 0; s < 2; s++) { mbar_init((uint64_t*)&tail->item_full[s], 1); mbar_init((uint64_t*)&tail->item_empty[s], NCWARPS); }
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == NCWARPS) {
+        if (lane == 0) producer_loop(P, item_begin, item_end, counter, Qsm, tail);
+        return;
+    }
+
+    // ------------------------------- consumers -------------------------------
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    long long t_start = 0;
+    if (PROF) t_start = clock64();
+    double esum = 0.0;
+    int stage = 0;
+    uint32_t sphase = 0;
+    double2 a[ABUF][MTW_MAX];
+
+    for (uint32_t n = 0;; n++) {
+        const int slot = n & 1;
+        const Ctl* ctl = &tail->ctl[slot];
+        long long t0 = 0, t1 = 0;
+        if (PROF) t0 = clock64();
+        mbar_wait((uint64_t*)&tail->item_full[slot], (n >> 1) & 1);
+        if (ctl->cur_item < 0) break;
+        if (PROF) { t1 = clock64(); prof[0] += t1 - t0; }
+
+        const int ngemm = ctl->ngemm;
+        RowSet rs;
+        rows_setup(P, ctl->gemm[0], warp, lane, rs);
+        a_prologue<MTW_MAX>(P, rs, a);
+        {   // zero the live W slots
+            const int nz2 = (ctl->bd.nslot * ctl->bd.slot_elems) >> 1;
+            double2* w2 = reinterpret_cast<double2*>(Wsm);
+            for (int idx = tid; idx < nz2; idx += NCTHREADS) w2[idx] = make_double2(0.0, 0.0);
+        }
+        consumer_bar();
+        if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
+
+        for (int g = 0; g < ngemm; g++) {
+            const GemmDesc& gd = ctl->gemm[g];
+            const int rt_total = (gd.TX * gd.TY) >> 3;
+            const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
+            const int nt = gd.TZ >> 2;
+            FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, warp, lane, prof)));
+        }
+        consumer_bar();
+        if (PROF) t0 = clock64();
+        {
+            const BlockDesc& bd = ctl->bd;
+            const int i = ctl->item.i, j = ctl->item.j, k = ctl->item.k;
+            const int npts = bd.slot_elems;
+            for (int pt = tid; pt < npts; pt += NCTHREADS) esum += block_point_energy(P, bd, i, j, k, Wsm, pt);
+        }
+        consumer_bar();       // W slots and ctl[slot] may be reused
+        if (lane == 0) mbar_arrive((uint64_t*)&tail->item_empty[slot]);
+        if (PROF) prof[4] += clock64() - t0;
+    }
+
+    // CTA reduction (warp shuffle, then one thread sums the warp partials in fixed order)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, off);
+    if (lane == 0) tail->red[warp] = esum;
+    consumer_bar();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < NCWARPS; w++) s += tail->red[w];
+        partials[blockIdx.x] = s;
+        if (PROF) {
+            prof[5] = clock64() - t_start;
+            for (int t = 0; t < 6; t++) prof_out[blockIdx.x * 6 + t] = prof[t];
+        }
+    }
+}
+
+}  // namespace fpt

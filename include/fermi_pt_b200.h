@@ -77,8 +77,10 @@ int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double*
  * Returns sustained TFLOP/s over `ms_target` milliseconds of back-to-back launches. */
 int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
 
-/* Diagnostics (not part of the drop-in path): phase breakdown of the last fpt_compute in SM cycles summed over
- * CTAs -- out6 = {setup, zero+prologue, k-loops, RMW epilogues, energy stage, total}; and a DMMA issue study. */
+/* Diagnostics (not part of the drop-in path): with profiling on, fpt_compute runs the instrumented kernel variant and
+ * fpt_last_profile returns its phase breakdown in SM cycles summed over CTAs (warp 0's view) --
+ * out6 = {wait-for-item, zero, k-loops, RMW epilogues + barriers, energy stage, total}; and a DMMA issue study. */
+int fpt_set_profiling(fpt_handle* h, int on);
 int fpt_last_profile(fpt_handle* h, double* out6);
 int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops);
 

@@ -86,6 +86,13 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                         for (int kappa = 0; kappa < P.Kp; kappa++)
                             d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa >> 3, G.z0 + zl) + (kappa & 7)];
                         const int off = gemm_dest(G, s, xl, yl, zl);
+                        {   // the kernel's fast RMW addressing must agree with the reference form
+                            DestIter di;
+                            if (dest_iter_init(G, s, xl, yl, zl & 3, di) && dest_iter_off(di, zl >> 2) != off) {
+                                fprintf(stderr, "dest_iter mismatch\n");
+                                return 5;
+                            }
+                        }
                         if (off < 0 || off >= bd.nslot * bd.slot_elems) { fprintf(stderr, "dest out of range\n"); return 3; }
                         W[off] += d;
                         hits[off]++;
