@@ -27,7 +27,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df",
-           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_set_profiling", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
+           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
 def library_path() -> str:
@@ -53,11 +53,12 @@ def load_library():
     L.fpt_compute.argtypes = [vp, ctypes.c_longlong, ctypes.c_longlong, _dp, ctypes.POINTER(Stats)]
     L.fpt_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_double, _dp]
     L.fpt_set_profiling.argtypes = [vp, ctypes.c_int]
+    L.fpt_set_debug_flags.argtypes = [vp, ctypes.c_int]
     L.fpt_last_profile.argtypes = [vp, _dp]
     L.fpt_dmma_sweep.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp]
     L.fpt_last_error.restype = ctypes.c_char_p
     L.fpt_version.restype = ctypes.c_char_p
-    for f in EXPORTS[:12]:
+    for f in EXPORTS[:13]:
         getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
@@ -130,6 +131,9 @@ class Engine:
         t = ctypes.c_double()
         self._check(self._L.fpt_fp64_peak(self._h, variant, ms_target, ctypes.byref(t)))
         return t.value
+
+    def set_debug_flags(self, flags: int):
+        self._check(self._L.fpt_set_debug_flags(self._h, flags))
 
     def set_profiling(self, on: bool):
         self._check(self._L.fpt_set_profiling(self._h, 1 if on else 0))

@@ -66,6 +66,7 @@ struct fpt_handle {
     int launches = 0;
     int last_grid = 0;
     bool profiling = false;
+    int dbg_flags = 0;
     bool last_profiled = false;
 };
 
@@ -144,6 +145,7 @@ static int setup_problem(fpt_handle* h, int o, int v)
     P.G = P.Kp / KGROUP;
     P.npair = o * (o + 1) / 2;
     P.nb = num_blocks(P.nt);
+    P.dbg_flags = h->dbg_flags;
     std::vector<i64> prefix(P.npair + 1);
     i64 acc = 0;
     for (int pr = 0; pr < P.npair; pr++) {
@@ -406,6 +408,14 @@ extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, doubl
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     *tflops = fl * reps / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+extern "C" int fpt_set_debug_flags(fpt_handle* h, int flags)
+{
+    if (!h) return fail("fpt_set_debug_flags: NULL handle");
+    h->prob.dbg_flags = flags;
+    h->dbg_flags = flags;
     return 0;
 }
 

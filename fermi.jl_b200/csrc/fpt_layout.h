@@ -38,7 +38,7 @@ namespace fpt {
 
 constexpr int TMAX = 16;       // largest tile edge
 constexpr int KGROUP = 8;      // kappa per group: one 16-byte load per lane feeds two DMMA.8x8x4
-constexpr int CHUNK_GROUPS = 4;  // kappa groups per shared-memory Q stage (32 kappa)
+constexpr int CHUNK_GROUPS = 3;  // kappa groups per shared-memory Q stage (24 kappa)
 constexpr int MAX_SLOTS = 6;
 constexpr int MAX_GEMMS = 18;
 
@@ -237,6 +237,7 @@ struct Problem {
     const double* fo;
     const double* fv;
     const i64* pair_prefix;   // npair+1 entries: first item of pair (i,j), pair index = i(i+1)/2+j
+    int dbg_flags;            // diagnostics only (results become wrong): 1 = skip RMW epilogues, 2 = skip energy stage
 };
 
 FPT_HD i64 pt_row(const Problem& P, int p, int y, int x) { return (((i64)p * P.vp + y) * P.vp + x) * P.Kp; }
@@ -310,6 +311,62 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     }
     const double Dd = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[a] - P.fv[b] - P.fv[c];
     return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));
+}
+
+// Energy of the column (bl, cl) of the block (all al): same arithmetic as block_point_energy, organised so that one
+// thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each either
+// contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
+FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl)
+{
+    const int TA = bd.ts[0];
+    const int v = P.v, o = P.o;
+    const int b = bd.t0[1] + bl, c = bd.t0[2] + cl;
+    if (b >= v || c >= v || b < c) return 0.0;
+    const i64 vv2 = (i64)v * v;
+    const double* t1i = P.T1d + (i64)i * v;
+    const double* t1j = P.T1d + (i64)j * v;
+    const double* t1k = P.T1d + (i64)k * v;
+    const double* ovjk = P.OV2 + ((i64)j * o + k) * vv2;   // [y][z] = (jy|kz)
+    const double* ovkj = P.OV2 + ((i64)k * o + j) * vv2;   // [y][z] = (ky|jz) = (jz|ky)
+    const double* ovik = P.OV2 + ((i64)i * o + k) * vv2;
+    const double* ovki = P.OV2 + ((i64)k * o + i) * vv2;
+    const double* ovij = P.OV2 + ((i64)i * o + j) * vv2;
+    const double* ovji = P.OV2 + ((i64)j * o + i) * vv2;
+    const i64 bc = (i64)b * v + c;
+    const double jk_bc = ovjk[bc], jk_cb = ovkj[bc];       // (jb|kc), (jc|kb)
+    const double ik_bc = ovik[bc], ik_cb = ovki[bc];       // (ib|kc), (ic|kb)
+    const double ij_bc = ovij[bc], ij_cb = ovji[bc];       // (ib|jc), (ic|jb)
+    const double t1i_b = t1i[b], t1j_b = t1j[b], t1k_b = t1k[b];
+    const double t1i_c = t1i[c], t1j_c = t1j[c], t1k_c = t1k[c];
+    const double Dbc = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[b] - P.fv[c];
+    const double wijk = (double)(2 - (i == j) - (j == k));
+    const int se = bd.slot_elems;
+    const int TB = bd.ts[1], TC = bd.ts[2];
+    double e = 0.0;
+    for (int al = 0; al < TA; al++) {
+        const int a = bd.t0[0] + al;
+        if (a >= v) break;
+        if (a < b) continue;
+        const i64 ab = (i64)a * v + b, ac = (i64)a * v + c;
+        const double jk_ab = ovjk[ab], jk_ba = ovkj[ab], ik_ab = ovik[ab], ik_ba = ovki[ab], ij_ab = ovij[ab], ij_ba = ovji[ab];
+        const double jk_ac = ovjk[ac], jk_ca = ovkj[ac], ik_ac = ovik[ac], ik_ca = ovki[ac], ij_ac = ovij[ac], ij_ca = ovji[ac];
+        const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];
+        double w[6], vv[6];
+        w[0] = Wsm[bd.slot_of_perm[0] * se + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
+        w[1] = Wsm[bd.slot_of_perm[1] * se + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
+        w[2] = Wsm[bd.slot_of_perm[2] * se + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
+        w[3] = Wsm[bd.slot_of_perm[3] * se + slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
+        w[4] = Wsm[bd.slot_of_perm[4] * se + slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
+        w[5] = Wsm[bd.slot_of_perm[5] * se + slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
+        vv[0] = w[0] + t1i_a * jk_bc + ik_ac * t1j_b + ij_ab * t1k_c;
+        vv[1] = w[1] + t1i_a * jk_cb + ik_ab * t1j_c + ij_ac * t1k_b;
+        vv[2] = w[2] + t1i_b * jk_ac + ik_bc * t1j_a + ij_ba * t1k_c;
+        vv[3] = w[3] + t1i_b * jk_ca + ik_ba * t1j_c + ij_bc * t1k_a;
+        vv[4] = w[4] + t1i_c * jk_ab + ik_cb * t1j_a + ij_ca * t1k_b;
+        vv[5] = w[5] + t1i_c * jk_ba + ik_ca * t1j_b + ij_cb * t1k_a;
+        e += point_energy(w, vv, Dbc - P.fv[a], a, b, c, wijk);
+    }
+    return e;
 }
 
 }  // namespace fpt

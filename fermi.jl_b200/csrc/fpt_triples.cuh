@@ -6,14 +6,15 @@
 //                                                  W and V never go to HBM
 //   accumulation                                   ijk.jl:133,145: per-thread FP64 partial, warp-shuffle, per-CTA partial
 //
-// CTA = 8 consumer warps + 1 producer warp (288 threads, 168 registers each), 1 CTA / SM, grid = #SMs.
-//   producer (warp 16, lane 0): pulls items off the global counter, decodes them into a double-buffered control
+// CTA = 2 consumer warpgroups (8 warps, 232 registers/thread after setmaxnreg) + 1 producer warpgroup (40 registers),
+// 384 threads, 1 CTA / SM, grid = #SMs.
+//   producer (warp 8, lane 0): pulls items off the global counter, decodes them into a double-buffered control
 //       block (item / block / GEMM descriptors) and streams the Q operand chunks of all GEMMs of the item through a
-//       3-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
+//       4-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
 //       through `empty` mbarriers, so it runs ahead of the consumers across GEMM and item boundaries.
 //   consumers: for each P-stationary GEMM  D[TX*TY x 2*TZ] = P_p . [Q_qr | Q_rq]  every warp owns <= 4 row tiles
 //       (8 rows) x all column tiles; A fragments come straight from global memory (each P row is used by exactly one
-//       warp, kappa-contiguous, 16 B per lane, prefetched one kappa-group ahead), B fragments from the ring.  The
+//       warp, kappa-contiguous, 16 B per lane, prefetched two kappa-groups ahead), B fragments from the ring.  The
 //       accumulators are then added into the W slots (swizzled, see fpt_layout.h), and after the last GEMM the
 //       energy of the block's a>=b>=c points is evaluated from the slots.
 #pragma once
@@ -23,16 +24,17 @@
 
 namespace fpt {
 
-constexpr int NCWARPS = 8;                         // consumer warps (9 warps -> 168 registers/thread)
+constexpr int NCWARPS = 8;                         // consumer warps = 2 warpgroups
 constexpr int NCTHREADS = NCWARPS * 32;            // 256
-constexpr int NTHREADS = NCTHREADS + 32;           // + producer warp
-constexpr int QSTAGES = 3;
+constexpr int NTHREADS = NCTHREADS + 128;          // + producer warpgroup (only its first lane works)
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // setmaxnreg: 256*232 + 128*40 = 64512 <= 65536
+constexpr int QSTAGES = 4;
 constexpr int QBLK = (TMAX + 1) * KGROUP;          // doubles per (group, s) block: TZ rows of 8 kappa + 64 B bank skew
-constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 1088 doubles = 8704 B
+constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 816 doubles = 6528 B
 constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
 constexpr int MTW_MAX = 4;
-constexpr int APREF = 1;                           // A-fragment prefetch distance in kappa groups
-constexpr int ABUF = 2;                            // group gg lives in buffer gg % ABUF = gl % ABUF (CHUNK_GROUPS is even)
+constexpr int APREF = 2;                           // A-fragment prefetch distance in kappa groups
+constexpr int ABUF = 3;                            // group gg lives in buffer gg % ABUF = gl % ABUF
 static_assert(CHUNK_GROUPS % ABUF == 0 && APREF < ABUF, "A-fragment ring is indexed by the group's position in its chunk");
 
 struct Ctl {
@@ -53,10 +55,22 @@ constexpr size_t TRIPLES_SMEM_BYTES = (size_t)(WSLOT_DOUBLES + QSTAGES * QSTAGE_
 
 __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 
+// The consumer warps form two groups (warps 0-3 / 4-7) that take turns in the RMW epilogues: a token (named barriers
+// 2 and 3, bar.arrive / bar.sync producer-consumer form) serialises all RMW phases in the order G0(g), G1(g), G0(g+1)...
+// so while one group adds its accumulators into the W slots the other one is still issuing DMMAs -- the tensor pipe
+// never drains at a GEMM boundary -- and no two warps of different groups ever touch a W element concurrently.
+constexpr int GROUP_THREADS = NCTHREADS / 2;
+__device__ __forceinline__ void token_wait(int grp) { named_bar_sync(2 + grp, NCTHREADS); }
+__device__ __forceinline__ void token_pass(int grp)
+{
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(3 - grp), "r"(NCTHREADS) : "memory");
+}
+__device__ __forceinline__ void group_bar(int grp) { named_bar_sync(4 + grp, GROUP_THREADS); }
+
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
+__device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
                                            double* Qsm, SmemTail* tail)
 {
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
@@ -157,11 +171,23 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
 #pragma unroll
         for (int ct = 0; ct < NT; ct++) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
 
+    // B fragments are prefetched one group ahead into a 3-deep register ring indexed by the group's position in its
+    // chunk (static indices: CHUNK_GROUPS == 3), also across the chunk (= ring stage) boundary.
+    static_assert(CHUNK_GROUPS == 3, "B-fragment ring assumes 3 groups per chunk");
+    double2 b[3][NT];
+    mbar_wait((uint64_t*)&tail->full[stage], sphase);
+    {
+        const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
+#pragma unroll
+        for (int ct = 0; ct < NT; ct++) b[0][ct] = *reinterpret_cast<const double2*>(st + ct * 4 * KGROUP);
+    }
     for (int c = 0; c < nchunks; c++) {
         const int g0 = c * CHUNK_GROUPS;
         const int ng = min(CHUNK_GROUPS, P.G - g0);
-        mbar_wait((uint64_t*)&tail->full[stage], sphase);
         const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
+        int nstage = stage + 1;
+        uint32_t nphase = sphase;
+        if (nstage == QSTAGES) { nstage = 0; nphase ^= 1; }
 #pragma unroll
         for (int gl = 0; gl < CHUNK_GROUPS; gl++) {
             if (gl < ng) {
@@ -171,30 +197,40 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
                     for (int mt = 0; mt < MTW; mt++)
                         a[(gl + APREF) % ABUF][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + (gg + APREF) * KGROUP);
                 }
-                double2 b[NT];
+                // next group's B fragments
+                if (gl + 1 < CHUNK_GROUPS) {
+                    if (gl + 1 < ng) {
 #pragma unroll
-                for (int ct = 0; ct < NT; ct++)
-                    b[ct] = *reinterpret_cast<const double2*>(st + gl * 2 * QBLK + ct * 4 * KGROUP);
+                        for (int ct = 0; ct < NT; ct++)
+                            b[(gl + 1) % 3][ct] = *reinterpret_cast<const double2*>(st + (gl + 1) * 2 * QBLK + ct * 4 * KGROUP);
+                    }
+                } else if (c + 1 < nchunks) {
+                    mbar_wait((uint64_t*)&tail->full[nstage], nphase);
+                    const double* nst = Qsm + nstage * QSTAGE_DOUBLES + boff;
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) b[0][ct] = *reinterpret_cast<const double2*>(nst + ct * 4 * KGROUP);
+                }
 #pragma unroll
                 for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[ct].x);
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[gl][ct].x);
 #pragma unroll
                 for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[ct].y);
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[gl][ct].y);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive((uint64_t*)&tail->empty[stage]);
-        if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
+        stage = nstage;
+        sphase = nphase;
     }
 }
 
 // RMW of the accumulators into the W slots
 template <int MTW, int NT>
 __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, const double (&acc)[MTW][NT][2], double* Wsm,
-                                         int lane)
+                                         int lane, int grp)
 {
     const int kk = lane & 3, r = lane >> 2;
     int xl[MTW], yl[MTW];
@@ -207,7 +243,8 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
-        if (e == 1 && gd.diag_xz) consumer_bar();
+        // (the other group is excluded by the token)
+        if (e == 1 && gd.diag_xz) group_bar(grp);
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) {
             if (mt < rs.nvalid) {
@@ -241,8 +278,11 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
         rows_setup(P, ctl->gemm[g + 1], warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
     }
-    consumer_bar();   // every warp has finished the previous GEMM's RMW (and the zeroing)
-    gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane);
+    const int grp = warp >> 2;
+    token_wait(grp);   // all earlier RMW phases (either group) are complete
+    if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane, grp);
+    else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
+    token_pass(grp);
     if (PROF) prof[3] += clock64() - t1;
 }
 
@@ -285,12 +325,15 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     }
     __syncthreads();
 
-    if (warp == NCWARPS) {
-        if (lane == 0) producer_loop(P, item_begin, item_end, counter, Qsm, tail);
+    if (warp >= NCWARPS) {   // producer warpgroup
+        setmaxnreg_dec<PRODUCER_REGS>();
+        if (warp == NCWARPS && lane == 0) producer_loop(P, item_begin, item_end, counter, Qsm, tail);
         return;
     }
+    setmaxnreg_inc<CONSUMER_REGS>();
 
     // ------------------------------- consumers -------------------------------
+    if (warp >= NCWARPS / 2) token_pass(1);   // the first RMW token goes to group 0
     long long prof[6] = {0, 0, 0, 0, 0, 0};
     long long t_start = 0;
     if (PROF) t_start = clock64();
@@ -331,9 +374,9 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (PROF) t0 = clock64();
         {
             const BlockDesc& bd = ctl->bd;
-            const int i = ctl->item.i, j = ctl->item.j, k = ctl->item.k;
-            const int npts = bd.slot_elems;
-            for (int pt = tid; pt < npts; pt += NCTHREADS) esum += block_point_energy(P, bd, i, j, k, Wsm, pt);
+            const int TC = bd.ts[2];
+            if (tid < bd.ts[1] * TC && !(P.dbg_flags & 2))
+                esum += block_column_energy(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tid / TC, tid % TC);
         }
         consumer_bar();       // W slots and ctl[slot] may be reused
         if (lane == 0) mbar_arrive((uint64_t*)&tail->item_empty[slot]);

@@ -7,6 +7,7 @@
 //
 // Exported C function:
 //   fpt_emulate(o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, item_begin, item_end, &Et)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -101,7 +102,15 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         }
         for (size_t t = 0; t < hits.size(); t++)
             if (hits[t] != 6) { fprintf(stderr, "slot element %zu received %d contributions (want 6)\n", t, hits[t]); return 4; }
-        for (int pt = 0; pt < bd.slot_elems; pt++) E += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
+        double e_pt = 0.0, e_col = 0.0;
+        for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
+        for (int bl = 0; bl < bd.ts[1]; bl++)
+            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl);
+        if (std::fabs(e_pt - e_col) > 1e-13 * (1e-30 + std::fabs(e_pt)) + 1e-18) {
+            fprintf(stderr, "column energy %.17g != point energy %.17g\n", e_col, e_pt);
+            return 6;
+        }
+        E += e_col;
     }
     *Et = E;
     return 0;

@@ -20,12 +20,18 @@ for name, (o, v) in shapes.items():
         e_, st = eng.compute(0, -1)
         if best is None or st["kernel_ms"] < best["kernel_ms"]:
             best = st
+    dbg = {}
+    for fl in (1, 2, 3):
+        eng.set_debug_flags(fl)
+        bt = min(eng.compute(0, -1)[1]["kernel_ms"] for _ in range(2))
+        dbg[f"flags{fl}_ms"] = round(bt, 3)
+    eng.set_debug_flags(0)
     eng.set_profiling(True)
     e_, stp = eng.compute(0, -1)
     prof = eng.last_profile()
     tot = prof["total"]
     out["shapes"][name] = {"o": o, "v": v, "E": e_, "kernel_ms": best["kernel_ms"],
-                           "tflops": best["flops"] / best["kernel_ms"] / 1e9, "prof_kernel_ms": stp["kernel_ms"],
+                           "tflops": best["flops"] / best["kernel_ms"] / 1e9, "prof_kernel_ms": stp["kernel_ms"], "dbg": dbg,
                            "phase_frac": {k: round(val / tot, 4) for k, val in prof.items()}}
     print(name, json.dumps(out["shapes"][name]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
