@@ -316,7 +316,8 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
 // Energy of the column (bl, cl) of the block (all al): same arithmetic as block_point_energy, organised so that one
 // thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each either
 // contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
-FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl)
+FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
+                                  int al_begin, int al_end)
 {
     const int TA = bd.ts[0];
     const int v = P.v, o = P.o;
@@ -343,7 +344,8 @@ FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, 
     const int se = bd.slot_elems;
     const int TB = bd.ts[1], TC = bd.ts[2];
     double e = 0.0;
-    for (int al = 0; al < TA; al++) {
+    if (al_end > TA) al_end = TA;
+    for (int al = al_begin; al < al_end; al++) {
         const int a = bd.t0[0] + al;
         if (a >= v) break;
         if (a < b) continue;

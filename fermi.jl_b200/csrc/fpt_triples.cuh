@@ -6,13 +6,13 @@
 //                                                  W and V never go to HBM
 //   accumulation                                   ijk.jl:133,145: per-thread FP64 partial, warp-shuffle, per-CTA partial
 //
-// CTA = 2 consumer warpgroups (8 warps, 232 registers/thread after setmaxnreg) + 1 producer warpgroup (40 registers),
-// 384 threads, 1 CTA / SM, grid = #SMs.
-//   producer (warp 8, lane 0): pulls items off the global counter, decodes them into a double-buffered control
+// CTA = 4 consumer warpgroups (16 warps, 120 registers/thread after setmaxnreg) + 1 producer warpgroup (24 registers),
+// 640 threads, 1 CTA / SM, grid = #SMs.
+//   producer (warp 16, lane 0): pulls items off the global counter, decodes them into a double-buffered control
 //       block (item / block / GEMM descriptors) and streams the Q operand chunks of all GEMMs of the item through a
 //       4-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
 //       through `empty` mbarriers, so it runs ahead of the consumers across GEMM and item boundaries.
-//   consumers: for each P-stationary GEMM  D[TX*TY x 2*TZ] = P_p . [Q_qr | Q_rq]  every warp owns <= 4 row tiles
+//   consumers: for each P-stationary GEMM  D[TX*TY x 2*TZ] = P_p . [Q_qr | Q_rq]  every warp owns <= 2 row tiles
 //       (8 rows) x all column tiles; A fragments come straight from global memory (each P row is used by exactly one
 //       warp, kappa-contiguous, 16 B per lane, prefetched two kappa-groups ahead), B fragments from the ring.  The
 //       accumulators are then added into the W slots (swizzled, see fpt_layout.h), and after the last GEMM the
@@ -24,15 +24,19 @@
 
 namespace fpt {
 
-constexpr int NCWARPS = 8;                         // consumer warps = 2 warpgroups
-constexpr int NCTHREADS = NCWARPS * 32;            // 256
+constexpr int NCWARPS = 16;                        // consumer warps = 4 warpgroups
+constexpr int NGROUPS = 4;
+constexpr int NCTHREADS = NCWARPS * 32;            // 512
 constexpr int NTHREADS = NCTHREADS + 128;          // + producer warpgroup (only its first lane works)
-constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;   // setmaxnreg: 256*232 + 128*40 = 64512 <= 65536
+// setmaxnreg only redistributes the CTA's launch-time allocation: 640 threads x 96 registers (launch bound) = 61440,
+// so 512*R_consumer + 128*R_producer must not exceed that (otherwise the TRY_ALLOC spins forever).
+constexpr int LAUNCH_REGS = 96, CONSUMER_REGS = 112, PRODUCER_REGS = 24;
+static_assert(NCTHREADS * CONSUMER_REGS + 128 * PRODUCER_REGS <= NTHREADS * LAUNCH_REGS, "setmaxnreg budget exceeds the CTA pool");
 constexpr int QSTAGES = 4;
 constexpr int QBLK = (TMAX + 1) * KGROUP;          // doubles per (group, s) block: TZ rows of 8 kappa + 64 B bank skew
 constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 816 doubles = 6528 B
 constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
-constexpr int MTW_MAX = 4;
+constexpr int MTW_MAX = 2;
 constexpr int APREF = 2;                           // A-fragment prefetch distance in kappa groups
 constexpr int ABUF = 3;                            // group gg lives in buffer gg % ABUF = gl % ABUF
 static_assert(CHUNK_GROUPS % ABUF == 0 && APREF < ABUF, "A-fragment ring is indexed by the group's position in its chunk");
@@ -55,17 +59,17 @@ constexpr size_t TRIPLES_SMEM_BYTES = (size_t)(WSLOT_DOUBLES + QSTAGES * QSTAGE_
 
 __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 
-// The consumer warps form two groups (warps 0-3 / 4-7) that take turns in the RMW epilogues: a token (named barriers
-// 2 and 3, bar.arrive / bar.sync producer-consumer form) serialises all RMW phases in the order G0(g), G1(g), G0(g+1)...
-// so while one group adds its accumulators into the W slots the other one is still issuing DMMAs -- the tensor pipe
-// never drains at a GEMM boundary -- and no two warps of different groups ever touch a W element concurrently.
-constexpr int GROUP_THREADS = NCTHREADS / 2;
-__device__ __forceinline__ void token_wait(int grp) { named_bar_sync(2 + grp, NCTHREADS); }
+// The consumer warps form four groups (warpgroups) that take turns in the RMW epilogues: a token (named barriers 2..5,
+// bar.arrive / bar.sync producer-consumer form) serialises all RMW phases in the order G0(g), G1(g), G2(g), G3(g), G0(g+1)...
+// so while one group adds its accumulators into the W slots the other three keep issuing DMMAs -- the tensor pipe does
+// not drain at a GEMM boundary -- and no two warps of different groups ever touch a W element concurrently.
+constexpr int GROUP_THREADS = NCTHREADS / NGROUPS;
+__device__ __forceinline__ void token_wait(int grp) { named_bar_sync(2 + grp, 2 * GROUP_THREADS); }
 __device__ __forceinline__ void token_pass(int grp)
 {
-    asm volatile("bar.arrive %0, %1;\n" ::"r"(3 - grp), "r"(NCTHREADS) : "memory");
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(2 + ((grp + 1) & (NGROUPS - 1))), "r"(2 * GROUP_THREADS) : "memory");
 }
-__device__ __forceinline__ void group_bar(int grp) { named_bar_sync(4 + grp, GROUP_THREADS); }
+__device__ __forceinline__ void group_bar(int grp) { named_bar_sync(2 + NGROUPS + grp, GROUP_THREADS); }
 
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
@@ -171,19 +175,10 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
 #pragma unroll
         for (int ct = 0; ct < NT; ct++) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
 
-    // B fragments are prefetched one group ahead into a 3-deep register ring indexed by the group's position in its
-    // chunk (static indices: CHUNK_GROUPS == 3), also across the chunk (= ring stage) boundary.
-    static_assert(CHUNK_GROUPS == 3, "B-fragment ring assumes 3 groups per chunk");
-    double2 b[3][NT];
-    mbar_wait((uint64_t*)&tail->full[stage], sphase);
-    {
-        const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
-#pragma unroll
-        for (int ct = 0; ct < NT; ct++) b[0][ct] = *reinterpret_cast<const double2*>(st + ct * 4 * KGROUP);
-    }
     for (int c = 0; c < nchunks; c++) {
         const int g0 = c * CHUNK_GROUPS;
         const int ng = min(CHUNK_GROUPS, P.G - g0);
+        mbar_wait((uint64_t*)&tail->full[stage], sphase);
         const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
         int nstage = stage + 1;
         uint32_t nphase = sphase;
@@ -197,27 +192,17 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
                     for (int mt = 0; mt < MTW; mt++)
                         a[(gl + APREF) % ABUF][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + (gg + APREF) * KGROUP);
                 }
-                // next group's B fragments
-                if (gl + 1 < CHUNK_GROUPS) {
-                    if (gl + 1 < ng) {
+                double2 b[NT];
 #pragma unroll
-                        for (int ct = 0; ct < NT; ct++)
-                            b[(gl + 1) % 3][ct] = *reinterpret_cast<const double2*>(st + (gl + 1) * 2 * QBLK + ct * 4 * KGROUP);
-                    }
-                } else if (c + 1 < nchunks) {
-                    mbar_wait((uint64_t*)&tail->full[nstage], nphase);
-                    const double* nst = Qsm + nstage * QSTAGE_DOUBLES + boff;
-#pragma unroll
-                    for (int ct = 0; ct < NT; ct++) b[0][ct] = *reinterpret_cast<const double2*>(nst + ct * 4 * KGROUP);
-                }
+                for (int ct = 0; ct < NT; ct++) b[ct] = *reinterpret_cast<const double2*>(st + gl * 2 * QBLK + ct * 4 * KGROUP);
 #pragma unroll
                 for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[gl][ct].x);
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[ct].x);
 #pragma unroll
                 for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[gl][ct].y);
+                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[ct].y);
             }
         }
         __syncwarp();
@@ -297,9 +282,7 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
     do {                                                                   \
         switch (MTWv) {                                                    \
         case 1: FPT_DISPATCH_NT(1, NTv, CALL) break;                       \
-        case 2: FPT_DISPATCH_NT(2, NTv, CALL) break;                       \
-        case 3: FPT_DISPATCH_NT(3, NTv, CALL) break;                       \
-        default: FPT_DISPATCH_NT(4, NTv, CALL) break;                      \
+        default: FPT_DISPATCH_NT(2, NTv, CALL) break;                      \
         }                                                                  \
     } while (0)
 
@@ -333,7 +316,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     setmaxnreg_inc<CONSUMER_REGS>();
 
     // ------------------------------- consumers -------------------------------
-    if (warp >= NCWARPS / 2) token_pass(1);   // the first RMW token goes to group 0
+    if ((warp >> 2) == NGROUPS - 1) token_pass(NGROUPS - 1);   // the first RMW token goes to group 0
     long long prof[6] = {0, 0, 0, 0, 0, 0};
     long long t_start = 0;
     if (PROF) t_start = clock64();
@@ -375,8 +358,10 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         {
             const BlockDesc& bd = ctl->bd;
             const int TC = bd.ts[2];
-            if (tid < bd.ts[1] * TC && !(P.dbg_flags & 2))
-                esum += block_column_energy(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tid / TC, tid % TC);
+            const int half = tid >> 8, tt = tid & 255;   // two threads per (b,c) column, 8 values of a each
+            if (tt < bd.ts[1] * TC && !(P.dbg_flags & 2))
+                esum += block_column_energy(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt / TC, tt % TC, half * 8,
+                                            half * 8 + 8);
         }
         consumer_bar();       // W slots and ctl[slot] may be reused
         if (lane == 0) mbar_arrive((uint64_t*)&tail->item_empty[slot]);

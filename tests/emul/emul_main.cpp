@@ -105,7 +105,8 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         double e_pt = 0.0, e_col = 0.0;
         for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
         for (int bl = 0; bl < bd.ts[1]; bl++)
-            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl);
+            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl, 0, 8) +
+                         block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl, 8, 16);
         if (std::fabs(e_pt - e_col) > 1e-13 * (1e-30 + std::fabs(e_pt)) + 1e-18) {
             fprintf(stderr, "column energy %.17g != point energy %.17g\n", e_col, e_pt);
             return 6;
