@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- RCCSD(T) perturbative-triples throughput of the B200 path (and the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5|oXvY] [--impl reference]
+
+One "step" = one full (T) correction over the workload (all non-zero-weight triplets i>=j>=k of the configuration).
+  value  : sustained FP64 TFLOP/s (algorithmic flops 12 v^3 (v+o) per triplet) with the operands already
+           resident in HBM -- the fused kernel (+ final reduction), timed with CUDA events / max over ranks.
+  e2e    : the same metric through the public API (RCCSDpT(ccsd, moints, B200()) -> fpt_triples_conv) from HOST
+           buffers: pinned-host -> device copies, layout prep, kernel and the 8-byte result read are all inside the
+           timed region.  At N>1 rank 0 uploads, the raw arrays are broadcast once over NCCL, every rank preps and
+           computes its contiguous shard of the static work list, and E(T) is one scalar all-reduce.
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+With --impl reference the CPU restatement of the reference algorithm (oracle/, OpenMP, all host cores) is timed on a
+bounded triplet sample of the same workload (the reference itself is Julia and cannot run in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c1": ("c1_h2o_dz", 5, 19, 32),
+    "c2": ("c2_h2o_tz", 5, 53, 48),
+    "c3": ("c3_benzene_dz", 15, 93, 64),
+    "c4": ("c4_h2o6_dz", 24, 114, 64),
+    "c5": ("c5_synth_o40_v400", 40, 400, 64),
+}
+METRIC = "RCCSD(T) sustained FP64 throughput (algorithmic flops 12*v^3*(v+o) per triplet / wall time)"
+UNIT = "TFLOP/s"
+
+
+def parse_workload(name):
+    if name in WORKLOADS:
+        return WORKLOADS[name]
+    m = re.fullmatch(r"o(\d+)v(\d+)", name)
+    if not m:
+        raise SystemExit(f"unknown workload {name}")
+    return (name, int(m.group(1)), int(m.group(2)), 64)
+
+
+def algorithmic_flops(o, v, ntrip):
+    return 12.0 * v ** 3 * (v + o) * ntrip
+
+
+def n_triplets(o):
+    return o * (o + 1) * (o + 2) // 6 - o
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/fpt_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_sample(x, o, v, budget_s=15.0):
+    """Time the CPU restatement (oracle.pt_gemm, OpenMP) on a bounded sample of trailing (i,j) pairs."""
+    import oracle
+    import fermi_jl_b200 as fb
+    threads = oracle.num_threads()
+    per_trip = algorithmic_flops(o, v, 1) / (threads * 12e9)      # guess: ~12 GFLOP/s per core
+    want = max(1, int(budget_s / max(per_trip, 1e-9)))
+    npair = o * (o + 1) // 2
+    pr0 = npair
+    while pr0 > 0:
+        (_, _), (tb, te) = fb.host.pair_range_items(o, v, pr0 - 1, npair)
+        pr0 -= 1
+        if te - tb >= want:
+            break
+    (ib, ie), (tb, te) = fb.host.pair_range_items(o, v, pr0, npair)
+    t0 = time.perf_counter()
+    e = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te)
+    dt = time.perf_counter() - t0
+    # zero-weight i=j=k triplets inside the range do no work
+    ntr = 0
+    i = j = k = 0
+    for t in range(te):
+        if t >= tb and not (i == j == k):
+            ntr += 1
+        k += 1
+        if k > j:
+            k = 0; j += 1
+            if j > i:
+                j = 0; i += 1
+    return {"E": e, "seconds": dt, "triplets": ntr, "flops": algorithmic_flops(o, v, ntr), "threads": threads,
+            "items": (ib, ie), "triplet_range": (tb, te)}
+
+
+def run_reference(args, name, o, v, naux):
+    import fermi_jl_b200 as fb
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x = fb.synth.make_inputs(o, v, naux=naux)
+    vals, secs = [], []
+    s = None
+    for it in range(args.warmup + args.steps):
+        s = cpu_reference_sample(x, o, v, budget_s=args.cpu_budget)
+        if it >= args.warmup:
+            vals.append(s["flops"] / s["seconds"] / 1e12)
+            secs.append(s["seconds"])
+    val = statistics.mean(vals)
+    sample = f"triplets [{s['triplet_range'][0]},{s['triplet_range'][1]}) of the i>=j>=k list ({s['triplets']} non-zero-weight) per step"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
+                       "o": o, "v": v},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CPU restatement of Fermi.jl ijk2.jl (oracle/pt_oracle.c, OpenMP); Julia is not available in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    name, o, v, naux = parse_workload(args.workload)
+    if args.impl == "reference":
+        return run_reference(args, name, o, v, naux)
+
+    import torch
+    import fermi_jl_b200 as fb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    eng = fb.Engine(local)
+
+    # ---- synthetic inputs (same seed on every rank; only rank 0's host copy is used for the e2e leg) ----
+    x = fb.synth.make_inputs(o, v, naux=naux)
+    names = ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv")
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(x, k).ravel(order="F"))).pin_memory() for k in names}
+    h2d_bytes = sum(t.numel() * 8 for t in host.values())
+    # column-major numpy views of the pinned buffers: what the reference-facing API (RCCSDpT) is handed
+    harr = {k: host[k].numpy().reshape(getattr(x, k).shape, order="F") for k in names}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(val):
+        if dist is None:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(val):
+        if dist is None:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- leg 1: operands resident in HBM ----
+    eng.upload_conv(o, v, *[host[k] for k in names])
+    n_items = eng.num_items()
+    ib, ie = fb.host.shard_items(n_items, rank, world)
+    ntrip = n_triplets(o)
+    flops = algorithmic_flops(o, v, ntrip)
+    for _ in range(args.warmup):
+        eng.compute(ib, ie)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    kernel_ms, launches, e_part = 0.0, 0, 0.0
+    for _ in range(args.steps):
+        e_part, st = eng.compute(ib, ie)   # synchronous: returns after the result is on the host
+        kernel_ms += st["kernel_ms"]
+        launches += 2                       # triples_kernel + reduce_partials
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = max_over_ranks(wall_ms / args.steps)
+    kern_ms = max_over_ranks(kernel_ms / args.steps)
+    e_gpu = sum_over_ranks(e_part)
+    value = flops / (step_ms * 1e-3) / 1e12
+
+    # ---- leg 2: end to end from pinned host buffers through the public API ----
+    def e2e_step():
+        if world == 1:
+            ccsd = fb.RCCSD(0.0, 0.0, 0.0, harr["T1"], harr["T2"])
+            moints = fb.IntegralHelper({"OVVV": harr["OVVV"], "OOOV": harr["OOOV"], "OVOV": harr["OVOV"],
+                                        "Fii": harr["fo"], "Faa": harr["fv"]})
+            return fb.RCCSDpT(ccsd, moints, fb.B200(), device=local).correction
+        # rank 0: H2D of the raw arrays; NCCL broadcast; every rank: prep + its shard; scalar all-reduce
+        raw = {}
+        for k in names:
+            raw[k] = host[k].to(dev, non_blocking=True) if rank == 0 else torch.empty(host[k].numel(), dtype=torch.float64, device=dev)
+        for k in names:
+            dist.broadcast(raw[k], src=0)
+        torch.cuda.synchronize()
+        eng.upload_conv(o, v, *[raw[k] for k in names])
+        e, st = eng.compute(ib, ie)
+        t = torch.tensor([e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e_e2e = 0.0
+    for _ in range(args.steps):
+        e_e2e = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_value = flops / (e2e_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        # ---- roofline denominator: FP64 tensor-pipe peak measured live (MEASURED_PEAKS.json has no FP64 entry) ----
+        peak = eng.fp64_peak(0, 300.0)
+        achieved = flops / world / (kern_ms * 1e-3) / 1e12   # per GPU: this rank's share of the flops / its kernel time
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tfile):
+            traffic = json.load(open(tfile)).get(name)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": UNIT, "frac": achieved / peak, "traffic": traffic,
+                "kernel": "fpt::triples_kernel (fused W build + permutation + V + denominators + energy)",
+                "peak_source": "live DMMA.8x8x4 register-resident stream on this GPU (fpt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "kernel_ms_per_launch": kern_ms}
+        cpu = None
+        if not args.no_cpu_baseline:
+            s = cpu_reference_sample(x, o, v, budget_s=args.cpu_budget)
+            e_s, _ = eng.compute(*s["items"])
+            cpu = {"value": s["flops"] / s["seconds"] / 1e12, "unit": UNIT, "cores": s["threads"], "kind": "port",
+                   "sample": f"triplets [{s['triplet_range'][0]},{s['triplet_range'][1]}) of the i>=j>=k list "
+                             f"({s['triplets']} non-zero-weight), {s['seconds']:.1f} s of oracle/pt_oracle.c (OpenMP)",
+                   "dE_gpu_minus_cpu_on_sample_Eh": e_s - s["E"]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
+                           "o": o, "v": v, "triplets": ntrip, "work_items": n_items,
+                           "parallelism": f"static contiguous shards of the (pair,block,k) work list over {world} rank(s)",
+                           "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 7) // 8 * 8) * 8 / 1e6)},
+                "triplets_per_s": ntrip / (step_ms * 1e-3), "E_T": e_gpu, "E_T_e2e": e_e2e,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
