@@ -1,0 +1,112 @@
+# FermiB200.jl -- Julia glue that puts libfermi_pt_b200.so behind Fermi.jl's RCCSD(T) entry points.
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no Julia there); it is the binding a Fermi.jl maintainer adds.  The same C ABI
+# (include/fermi_pt_b200.h) is exercised from Python/ctypes by tests/ and bench.py.
+#
+# Usage (inside a Fermi.jl session):
+#     include("FermiB200.jl")                      # defines Fermi.CoupledCluster.B200 <: RpTAlgorithm, pt_alg = 4
+#     @set pt_alg 4
+#     @energy ccsd(t)                              # -> RCCSDpT() -> RCCSDpT(B200()) -> RCCSDpT(ccsd, moints, B200())
+#  or, warm:  @energy cc, moints => ccsd(t)   /   Fermi.CoupledCluster.RCCSDpT(cc, moints, Fermi.CoupledCluster.B200())
+#
+# Mirrors src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:4-20 (the three overloads) and replaces
+# ijk.jl:20-150 by one ccall.
+
+module FermiB200
+
+using Fermi
+using Fermi.Options
+using Fermi.Integrals: IntegralHelper, AbstractERI, AbstractDFERI
+using Fermi.Orbitals: AbstractRestrictedOrbitals
+import Fermi.CoupledCluster: RCCSD, RCCSDpT, RpTAlgorithm, get_rpt_alg, ijk, ijk2, abc
+import Fermi: output, Molecule, FermiException
+
+const LIB = get(ENV, "FERMI_PT_B200_LIB", joinpath(@__DIR__, "..", "libfermi_pt_b200.so"))
+
+struct B200 <: RpTAlgorithm end
+
+# mirror of fpt_stats (include/fermi_pt_b200.h)
+struct FptStats
+    upload_ms::Cdouble; kernel_ms::Cdouble; total_ms::Cdouble; flops::Cdouble; h2d_bytes::Cdouble
+    n_items::Clonglong; n_triplets::Clonglong; n_launches::Cint; n_sm::Cint
+end
+
+const HANDLE = Ref{Ptr{Cvoid}}(C_NULL)
+
+function handle()
+    if HANDLE[] == C_NULL
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:fpt_create, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), 1, C_NULL, h)
+        rc == 0 || throw(FermiException(unsafe_string(ccall((:fpt_last_error, LIB), Cstring, ()))))
+        HANDLE[] = h[]
+        atexit(() -> ccall((:fpt_destroy, LIB), Cint, (Ptr{Cvoid},), HANDLE[]))
+    end
+    return HANDLE[]
+end
+
+check(rc) = rc == 0 || throw(FermiException(unsafe_string(ccall((:fpt_last_error, LIB), Cstring, ()))))
+
+# pt_alg = 4 selects the B200 path (PerturbativeTriples.jl:3-11 holds the list as a local literal, so extend it here)
+function Fermi.CoupledCluster.get_rpt_alg()
+    implemented = [ijk(), ijk2(), abc(), B200()]
+    N = Options.get("pt_alg")
+    try
+        return implemented[N]
+    catch BoundsError
+        throw(FermiException("implementation number $N not available for RCCSD(T)."))
+    end
+end
+
+function RCCSDpT(Alg::B200)                                   # ijk.jl:4-10
+    val = Options.get("return_ints")
+    Options.set("return_ints", true)
+    ccsd, moints = RCCSD()
+    Options.set("return_ints", val)
+    return RCCSDpT(ccsd, moints, Alg)
+end
+
+function RCCSDpT(mol::Molecule, Alg::B200)                    # ijk.jl:12-18
+    val = Options.get("return_ints")
+    Options.set("return_ints", true)
+    ccsd, moints = RCCSD(mol)
+    Options.set("return_ints", val)
+    return RCCSDpT(ccsd, moints, Alg)
+end
+
+dense(A) = A isa Array{Float64} ? A : collect(Float64, A)
+
+function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T<:AbstractFloat,
+                                                                              E<:AbstractERI,O<:AbstractRestrictedOrbitals}
+    T === Float64 || throw(FermiException("the B200 (T) path is Float64 only (got $T)"))
+    output("\n   • Perturbative Triples Started\n")
+    output("   - Contraction Engine: B200 DMMA (libfermi_pt_b200)")
+    T1 = dense(ccsd.T1); T2 = dense(ccsd.T2)
+    o, v = size(T1)
+    fo = dense(moints["Fii"]); fv = dense(moints["Faa"])
+    Et = Ref{Cdouble}(0.0)
+    st = Ref{FptStats}()
+    output("Computing energy contribution from occupied orbitals:")
+    t = @elapsed begin
+        if moints.eri_type isa AbstractDFERI && !haskey(moints.cache, "OVVV")
+            # DF: hand over B factors ([Q,.,.], Q fastest, DFERI.jl:15-69); (ia|bd) etc. are assembled on the GPU
+            BOO = dense(moints["BOO"]); BOV = dense(moints["BOV"]); BVV = dense(moints["BVV"])
+            naux = size(BOV, 1)
+            check(ccall((:fpt_triples_df, LIB), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                         Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
+                        handle(), o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, Et, st))
+        else
+            OVVV = dense(moints["OVVV"]); OOOV = dense(moints["OOOV"]); OVOV = dense(moints["OVOV"])
+            check(ccall((:fpt_triples_conv, LIB), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                         Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
+                        handle(), o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, Et, st))
+        end
+    end
+    output("Finished in {:5.5f} s", t)
+    output("Final (T) contribution: {:15.10f}", Et[])
+    output("CCSD(T) energy:         {:15.10f}", Et[] + ccsd.energy)
+    return RCCSDpT{T}(ccsd, Et[] + ccsd.energy, Et[])        # ijk.jl:149
+end
+
+end # module

@@ -1,0 +1,88 @@
+"""CPU tests of the oracle itself: the C restatement (naive loops and GEMM form) against the numpy transcriptions,
+the spin-orbital brute force and the committed golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fermi_jl_b200 as fb
+import oracle
+from oracle import pt_numpy as P
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pt_golden.json")))
+
+
+def _args(x):
+    return (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+
+
+@pytest.mark.parametrize("rec", GOLD, ids=lambda r: f"o{r['o']}v{r['v']}")
+def test_golden_vectors(rec):
+    x = fb.synth.make_inputs(rec["o"], rec["v"], naux=rec["naux"], seed=rec["seed"])
+    for f in (oracle.pt_naive, oracle.pt_gemm):
+        e = f(*_args(x))
+        assert abs(e - rec["E_ijk"]) < 1e-13, (f.__name__, e, rec["E_ijk"])
+    assert abs(rec["E_ijk"] - rec["E_ijk2"]) < 1e-13
+    if "E_spinorbital" in rec:
+        assert abs(rec["E_ijk"] - rec["E_spinorbital"]) < 1e-13
+
+
+def test_numpy_transcriptions_agree_with_bruteforce():
+    x = fb.synth.make_inputs(2, 4, naux=5, seed=3)
+    a = _args(x)
+    e = P.pt_ijk(*a)
+    assert abs(P.pt_ijk2(*a) - e) < 1e-14
+    assert abs(P.pt_ijk_loops(*a) - e) < 1e-14
+    assert abs(P.pt_spinorbital_bruteforce(*a) - e) < 1e-14
+
+
+def test_unsymmetric_inputs_break_ijk_vs_ijk2():
+    """the two reference algorithms agree only for inputs with the physical symmetries -- the oracle follows
+    ijk.jl index for index, so it must reproduce that disagreement (guards against an accidental symmetrisation)."""
+    rng = np.random.default_rng(0)
+    o, v = 2, 3
+    T1, T2 = rng.standard_normal((o, v)), rng.standard_normal((o, o, v, v))
+    OVVV, OOOV, OVOV = rng.standard_normal((o, v, v, v)), rng.standard_normal((o, o, o, v)), rng.standard_normal((o, v, o, v))
+    fo, fv = -np.sort(rng.uniform(0.5, 2, o))[::-1], np.sort(rng.uniform(0.5, 2, v))
+    e1 = P.pt_ijk(T1, T2, OVVV, OOOV, OVOV, fo, fv)
+    assert abs(oracle.pt_naive(T1, T2, OVVV, OOOV, OVOV, fo, fv) - e1) < 1e-10 * max(1.0, abs(e1))
+    assert abs(P.pt_ijk2(T1, T2, OVVV, OOOV, OVOV, fo, fv) - e1) > 1e-6
+
+
+def test_triplet_ranges_add_up():
+    x = fb.synth.make_inputs(5, 11, naux=6, seed=8)
+    a = _args(x)
+    full = oracle.pt_gemm(*a)
+    ntrip = 5 * 6 * 7 // 6
+    cuts = [0, 4, 9, 20, ntrip]
+    parts = [oracle.pt_gemm(*a, t_begin=cuts[i], t_end=cuts[i + 1]) for i in range(len(cuts) - 1)]
+    assert abs(sum(parts) - full) < 1e-15
+    assert abs(P.pt_ijk(*a) - full) < 1e-14
+    assert abs(oracle.pt_gemm(*a, nthreads=1) - full) < 1e-15
+
+
+def test_degenerate_shapes():
+    for o, v in [(1, 1), (1, 5), (2, 1), (3, 2)]:
+        x = fb.synth.make_inputs(o, v, naux=3, seed=1)
+        a = _args(x)
+        e = oracle.pt_naive(*a)
+        assert np.isfinite(e)
+        assert abs(oracle.pt_gemm(*a) - e) < 1e-15
+        assert abs(P.pt_ijk(*a) - e) < 1e-15
+    # o = 1: the only triplet is i=j=k, weight 0 (ijk.jl:133)
+    x = fb.synth.make_inputs(1, 6, naux=3, seed=2)
+    assert oracle.pt_naive(*_args(x)) == 0.0
+
+
+def test_synth_symmetries_and_dump_roundtrip(tmp_path):
+    x = fb.synth.make_inputs(3, 5, naux=4, seed=4)
+    assert np.allclose(x.T2, x.T2.transpose(1, 0, 3, 2))
+    assert np.allclose(x.OVVV, x.OVVV.transpose(0, 1, 3, 2))
+    assert np.allclose(x.OOOV, x.OOOV.transpose(1, 0, 2, 3))
+    assert np.allclose(x.OVOV, x.OVOV.transpose(2, 3, 0, 1))
+    assert x.T2.flags.f_contiguous and x.OVVV.flags.f_contiguous
+    fb.synth.dump(x, str(tmp_path / "d"))
+    y = fb.synth.load(str(tmp_path / "d"))
+    for k in ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv", "BOO", "BOV", "BVV"):
+        assert np.array_equal(getattr(x, k), getattr(y, k))
