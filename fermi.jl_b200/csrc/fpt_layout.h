@@ -80,16 +80,16 @@ FPT_HD int num_k(int i, int j) { return (i == j) ? j : j + 1; }
 // Element (la,lb,lc) of a slot with dims (Ta,Tb,Tc), lc fastest, with a bank swizzle on lc chosen so that
 //  (1) a 4x4 patch in any two coordinates (lo-2-bits aligned) and (2) a run of 16 in any single coordinate
 // hit 16 distinct 8-byte banks (RMW epilogue of the GEMMs, and the energy stage's permuted reads).
+// For Tc == 16 the swizzle is GF(2)-linear:  lcs = lc ^ SA(la) ^ SB(lb),  SA(x) = swap the two bit pairs of x,
+// SB(x) = (x&3)*5 ^ (x>>2); linearity is what makes the per-column-tile offsets of the RMW epilogue one XOR away
+// from each other (DestIter below).  Other Tc (edge tiles 4/8/12) use an additive skew.
+FPT_HD int swz_a(int x) { return ((x & 3) << 2) | (x >> 2); }
+FPT_HD int swz_b(int x) { return ((x & 3) * 5) ^ (x >> 2); }
 FPT_HD int slot_index(int la, int lb, int lc, int Tb, int Tc)
 {
     int lcs;
-    if (Tc == 16) {
-        int h = ((lb & 3) + (lc & 3) + (lc >> 2) + (la >> 2)) & 3;
-        int l = ((la & 3) + (lc & 3) + (lb >> 2)) & 3;
-        lcs = (h << 2) | l;
-    } else {
-        lcs = (lc + 3 * la + 4 * lb) % Tc;
-    }
+    if (Tc == 16) lcs = lc ^ swz_a(la) ^ swz_b(lb);
+    else lcs = (lc + 3 * la + 4 * lb) % Tc;
     return (la * Tb + lb) * Tc + lcs;
 }
 
@@ -195,9 +195,10 @@ FPT_HD int gemm_dest(const GemmDesc& g, int s, int xl, int yl, int zl)
 
 // Fast form of gemm_dest for the RMW epilogue when the destination slot has Tc == 16: for a fixed thread
 // (xl, yl, kk) the element for column tile ct (zl = 4*ct + kk) is
-//     off(ct) = lin0 + ct*zs + ((((hh + dh*ct) & 3) << 2) | ((ll + dl*ct) & 3))
-// (derived from slot_index; which of la/lb/lc is supplied by z decides zs, dh, dl).
-struct DestIter { int lin0, zs, hh, ll, dh, dl; };
+//     off(ct) = lin0 + ct*zs + (w0 ^ (ct*d1))
+// where (zs, d1) = (0, 4) if z supplies lc, (64, 1) if z supplies lb, (64*Tb, 1) if z supplies la
+// (swz_a(4ct) = swz_b(4ct) = ct and 4ct + kk = 4ct ^ kk).
+struct DestIter { int lin0, zs, w0, d1; };
 
 FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, DestIter& it)
 {
@@ -205,25 +206,14 @@ FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, Des
     const int sel = g.dsel[s];
     const int sa = sel & 3, sb = (sel >> 2) & 3, sc = (sel >> 4) & 3;
     const int Tb = g.dTb[s];
-    // coordinates with zl = kk (ct = 0)
-    const int la = pick3(sa, xl, yl, kk), lb = pick3(sb, xl, yl, kk), lc = pick3(sc, xl, yl, kk);
-    if (sc == 2) {
-        it.lin0 = (la * Tb + lb) * 16; it.zs = 0;
-        it.hh = (lb & 3) + kk + (la >> 2); it.ll = (la & 3) + kk + (lb >> 2); it.dh = 1; it.dl = 0;
-    } else if (sb == 2) {
-        it.lin0 = (la * Tb + kk) * 16; it.zs = 64;
-        it.hh = kk + (lc & 3) + (lc >> 2) + (la >> 2); it.ll = (la & 3) + (lc & 3); it.dh = 0; it.dl = 1;
-    } else {
-        it.lin0 = (kk * Tb + lb) * 16; it.zs = 64 * Tb;
-        it.hh = (lb & 3) + (lc & 3) + (lc >> 2); it.ll = kk + (lc & 3) + (lb >> 2); it.dh = 1; it.dl = 0;
-    }
-    it.lin0 += g.dbase[s];
+    const int la = pick3(sa, xl, yl, kk), lb = pick3(sb, xl, yl, kk), lc = pick3(sc, xl, yl, kk);   // ct = 0
+    it.lin0 = g.dbase[s] + (la * Tb + lb) * 16;
+    it.w0 = lc ^ swz_a(la) ^ swz_b(lb);
+    it.zs = (sc == 2) ? 0 : (sb == 2 ? 64 : 64 * Tb);
+    it.d1 = (sc == 2) ? 4 : 1;
     return true;
 }
-FPT_HD int dest_iter_off(const DestIter& it, int ct)
-{
-    return it.lin0 + ct * it.zs + ((((it.hh + it.dh * ct) & 3) << 2) | ((it.ll + it.dl * ct) & 3));
-}
+FPT_HD int dest_iter_off(const DestIter& it, int ct) { return it.lin0 + ct * it.zs + (it.w0 ^ (ct * it.d1)); }
 
 // ---- problem description --------------------------------------------------------------------------
 struct Problem {

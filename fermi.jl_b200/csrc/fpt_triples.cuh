@@ -74,43 +74,60 @@ __device__ __forceinline__ void group_bar(int grp) { named_bar_sync(2 + NGROUPS 
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
+                                                Ctl* ctl)
+{
+    const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
+    if (it >= item_end) { ctl->cur_item = -1; return; }
+    ctl->cur_item = it;
+    item_decode(P, it, ctl->item);
+    make_block(ctl->item.A, ctl->item.B, ctl->item.C, P.vp, ctl->bd);
+    ctl->ngemm = make_gemms(ctl->bd, ctl->item.i, ctl->item.j, ctl->item.k, ctl->gemm);
+}
+
+// Item n+1 is fetched and decoded while the chunks of item n are still streaming (right after its first GEMM), so the
+// Q ring never runs dry at an item boundary.
 __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
-                                           double* Qsm, SmemTail* tail)
+                                              double* Qsm, SmemTail* tail)
 {
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+    const i64 gstride = (i64)P.vp * KGROUP;   // doubles between consecutive kappa groups of one (q,r) in Qt
     int stage = 0;
     uint32_t sphase = 0;
+    // item 0
+    mbar_wait((uint64_t*)&tail->item_empty[0], 1);
+    producer_decode(P, item_begin, item_end, counter, &tail->ctl[0]);
+    mbar_arrive((uint64_t*)&tail->item_full[0]);
     for (uint32_t n = 0;; n++) {
         const int slot = n & 1;
-        Ctl* ctl = &tail->ctl[slot];
-        mbar_wait((uint64_t*)&tail->item_empty[slot], ((n >> 1) & 1) ^ 1);
-        const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
-        if (it >= item_end) {
-            ctl->cur_item = -1;
-            mbar_arrive((uint64_t*)&tail->item_full[slot]);
-            break;
-        }
-        ctl->cur_item = it;
-        item_decode(P, it, ctl->item);
-        make_block(ctl->item.A, ctl->item.B, ctl->item.C, P.vp, ctl->bd);
-        ctl->ngemm = make_gemms(ctl->bd, ctl->item.i, ctl->item.j, ctl->item.k, ctl->gemm);
-        mbar_arrive((uint64_t*)&tail->item_full[slot]);
+        const Ctl* ctl = &tail->ctl[slot];
+        if (ctl->cur_item < 0) break;
         const int ngemm = ctl->ngemm;
         for (int g = 0; g < ngemm; g++) {
             const GemmDesc& gd = ctl->gemm[g];
             const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
+            const double* src0 = P.Qt + qt_row(P, gd.q, gd.r, 0, gd.z0);
+            const double* src1 = P.Qt + qt_row(P, gd.r, gd.q, 0, gd.z0);
             for (int c = 0; c < nchunks; c++) {
-                const int g0 = c * CHUNK_GROUPS;
-                const int ng = min(CHUNK_GROUPS, P.G - g0);
+                const int ng = min(CHUNK_GROUPS, P.G - c * CHUNK_GROUPS);
                 mbar_wait((uint64_t*)&tail->empty[stage], sphase ^ 1);
                 uint64_t* fb = (uint64_t*)&tail->full[stage];
                 mbar_arrive_expect_tx(fb, (uint32_t)ng * 2u * row_bytes);
                 double* st = Qsm + stage * QSTAGE_DOUBLES;
                 for (int gl = 0; gl < ng; gl++) {
-                    tma_bulk_g2s(st + (gl * 2 + 0) * QBLK, P.Qt + qt_row(P, gd.q, gd.r, g0 + gl, gd.z0), row_bytes, fb);
-                    tma_bulk_g2s(st + (gl * 2 + 1) * QBLK, P.Qt + qt_row(P, gd.r, gd.q, g0 + gl, gd.z0), row_bytes, fb);
+                    tma_bulk_g2s(st, src0, row_bytes, fb);
+                    tma_bulk_g2s(st + QBLK, src1, row_bytes, fb);
+                    st += 2 * QBLK;
+                    src0 += gstride;
+                    src1 += gstride;
                 }
                 if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
+            }
+            if (g == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
+                const uint32_t m = n + 1;
+                mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
+                producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1]);
+                mbar_arrive((uint64_t*)&tail->item_full[m & 1]);
             }
         }
     }
