@@ -139,10 +139,12 @@ class Engine:
         self._check(self._L.fpt_set_profiling(self._h, 1 if on else 0))
 
     def last_profile(self):
-        buf = (ctypes.c_double * 6)()
+        buf = (ctypes.c_double * 16)()
         self._check(self._L.fpt_last_profile(self._h, buf))
-        names = ["wait_item", "zero", "kloops", "rmw", "energy", "total"]
-        return dict(zip(names, list(buf)))
+        names = ["wait_item", "zero", "kloops", "rmw", "energy", "total", "token_wait", "_"]
+        out = dict(zip(names, list(buf)[:8]))
+        out.update({"g3_" + k: v for k, v in zip(names, list(buf)[8:])})
+        return out
 
     def dmma_sweep(self, ilp: int, warps_per_sm: int) -> float:
         t = ctypes.c_double()

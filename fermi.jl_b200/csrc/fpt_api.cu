@@ -57,7 +57,7 @@ struct fpt_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // resident operands
-    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out, prof;
+    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out, prof, blocktab;
     // staging for raw inputs
     DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
     Problem prob{};
@@ -106,7 +106,7 @@ extern "C" int fpt_destroy(fpt_handle* h)
 {
     if (!h) return 0;
     cudaSetDevice(h->dev);
-    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof,
+    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof, &h->blocktab,
                       &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
     for (DevBuf* b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -166,7 +166,18 @@ static int setup_problem(fpt_handle* h, int o, int v)
     if (h->partials.ensure((size_t)h->n_sm * 4 * sizeof(double))) return 1;
     if (h->counter.ensure(sizeof(unsigned long long))) return 1;
     if (h->out.ensure(sizeof(double))) return 1;
-    if (h->prof.ensure((size_t)h->n_sm * 6 * sizeof(long long))) return 1;
+    if (h->prof.ensure((size_t)h->n_sm * NPROF * sizeof(long long))) return 1;
+    // block descriptor table (positions in (i,j,k) instead of orbital numbers)
+    std::vector<BlockTabEntry> tab((size_t)P.nb);
+    for (i64 b = 0; b < P.nb; b++) {
+        int A, B, C;
+        tetra_decode(b, A, B, C);
+        make_block(A, B, C, P.vp, tab[b].bd);
+        tab[b].ngemm = make_gemms(tab[b].bd, 0, 1, 2, tab[b].gemm);
+    }
+    if (h->blocktab.ensure(tab.size() * sizeof(BlockTabEntry))) return 1;
+    CK(cudaMemcpyAsync(h->blocktab.p, tab.data(), tab.size() * sizeof(BlockTabEntry), cudaMemcpyHostToDevice, h->stream));
+    P.blocktab = (const BlockTabEntry*)h->blocktab.p;
     CK(cudaMemcpyAsync(h->prefix.p, prefix.data(), prefix.size() * sizeof(i64), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // `prefix` is a local
     P.Pt = h->Pt.d(); P.Qt = h->Qt.d(); P.OV2 = h->OV2.d(); P.T1d = h->T1d.d();
@@ -433,11 +444,11 @@ extern "C" int fpt_last_profile(fpt_handle* h, double* out6)
     if (!h || !out6) return fail("fpt_last_profile: NULL argument");
     if (h->last_grid <= 0 || !h->last_profiled) return fail("fpt_last_profile: the last compute was not profiled (fpt_set_profiling)");
     CK(cudaSetDevice(h->dev));
-    std::vector<long long> buf((size_t)h->last_grid * 6);
+    std::vector<long long> buf((size_t)h->last_grid * NPROF);
     CK(cudaMemcpy(buf.data(), h->prof.p, buf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int t = 0; t < 6; t++) out6[t] = 0.0;
+    for (int t = 0; t < NPROF; t++) out6[t] = 0.0;
     for (int b = 0; b < h->last_grid; b++)
-        for (int t = 0; t < 6; t++) out6[t] += (double)buf[(size_t)b * 6 + t];
+        for (int t = 0; t < NPROF; t++) out6[t] += (double)buf[(size_t)b * NPROF + t];
     return 0;
 }
 

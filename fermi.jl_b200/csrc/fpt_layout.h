@@ -215,6 +215,16 @@ FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, Des
 }
 FPT_HD int dest_iter_off(const DestIter& it, int ct) { return it.lin0 + ct * it.zs + (it.w0 ^ (ct * it.d1)); }
 
+// Per-block descriptors are independent of (i,j,k) up to which occupied plays p, q, r: the host builds one entry per
+// block with make_gemms(bd, 0, 1, 2), so that GemmDesc.p/q/r hold *positions* in (i,j,k); the kernel's producer copies
+// the entry of an item's block into shared memory with one TMA bulk copy.
+struct BlockTabEntry {
+    BlockDesc bd;
+    int ngemm;
+    GemmDesc gemm[MAX_GEMMS];
+};
+static_assert(sizeof(BlockTabEntry) % 16 == 0, "BlockTabEntry is moved by 16-byte-granular bulk copies");
+
 // ---- problem description --------------------------------------------------------------------------
 struct Problem {
     int o, v, vp, nt, Kp, G;
@@ -227,7 +237,8 @@ struct Problem {
     const double* T1d;
     const double* fo;
     const double* fv;
-    const i64* pair_prefix;   // npair+1 entries: first item of pair (i,j), pair index = i(i+1)/2+j
+    const i64* pair_prefix;   // npair+1 entries: first item of pair (i,j), pair index = i(i+1)/2+j (host / emulator only)
+    const BlockTabEntry* blocktab;   // nb entries (device)
     int dbg_flags;            // diagnostics only (results become wrong): 1 = skip RMW epilogues, 2 = skip energy stage
 };
 
@@ -248,6 +259,25 @@ FPT_HD void item_decode(const Problem& P, i64 item, ItemDesc& it)
     const int nk = num_k(it.i, it.j);
     it.k = (int)(rem % nk);
     tetra_decode(rem / nk, it.A, it.B, it.C);
+}
+
+FPT_HD int occ_pick(const ItemDesc& it, int pos) { return pos == 0 ? it.i : (pos == 1 ? it.j : it.k); }
+
+// Same decode without the prefix table: the number of non-zero-weight triplets before pair (i,j) is
+// T(i,j) = i(i+1)(i+2)/6 - i + j(j+1)/2, and item = nb*T(i,j) + block*nk + k.
+FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block)
+{
+    const i64 u = item / P.nb;
+    int i = 0;
+    while (i + 1 < P.o && (i64)(i + 1) * (i + 2) * (i + 3) / 6 - (i + 1) <= u) i++;
+    const i64 ti = (i64)i * (i + 1) * (i + 2) / 6 - i;
+    int j = 0;
+    while (j + 1 <= i && (i64)(j + 1) * (j + 2) / 2 <= u - ti) j++;
+    const i64 rem = item - P.nb * (ti + (i64)j * (j + 1) / 2);
+    const int nk = num_k(i, j);
+    it.i = i; it.j = j; it.k = (int)(rem % nk);
+    block = rem / nk;
+    tetra_decode(block, it.A, it.B, it.C);
 }
 
 // ---- energy of one (a,b,c) point, ijk.jl:127-133 ---------------------------------------------------------
@@ -304,16 +334,20 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));
 }
 
-// Energy of the column (bl, cl) of the block (all al): same arithmetic as block_point_energy, organised so that one
-// thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each either
-// contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
-FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
-                                  int al_begin, int al_end)
+template <bool ALL16>
+FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
+                                    int al_begin, int al_end)
 {
-    const int TA = bd.ts[0];
+    const int TA = ALL16 ? 16 : bd.ts[0], TB = ALL16 ? 16 : bd.ts[1], TC = ALL16 ? 16 : bd.ts[2];
     const int v = P.v, o = P.o;
+    const int a0 = bd.t0[0];
     const int b = bd.t0[1] + bl, c = bd.t0[2] + cl;
     if (b >= v || c >= v || b < c) return 0.0;
+    // a runs over [max(al_begin, b - a0), min(al_end, TA, v - a0)): a >= b (ijk.jl:123) and a < v (padding)
+    if (al_begin < b - a0) al_begin = b - a0;
+    if (al_end > TA) al_end = TA;
+    if (al_end > v - a0) al_end = v - a0;
+    if (al_begin >= al_end) return 0.0;
     const i64 vv2 = (i64)v * v;
     const double* t1i = P.T1d + (i64)i * v;
     const double* t1j = P.T1d + (i64)j * v;
@@ -333,24 +367,26 @@ FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, 
     const double Dbc = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[b] - P.fv[c];
     const double wijk = (double)(2 - (i == j) - (j == k));
     const int se = bd.slot_elems;
-    const int TB = bd.ts[1], TC = bd.ts[2];
+    const double* W0 = Wsm + bd.slot_of_perm[0] * se;
+    const double* W1 = Wsm + bd.slot_of_perm[1] * se;
+    const double* W2 = Wsm + bd.slot_of_perm[2] * se;
+    const double* W3 = Wsm + bd.slot_of_perm[3] * se;
+    const double* W4 = Wsm + bd.slot_of_perm[4] * se;
+    const double* W5 = Wsm + bd.slot_of_perm[5] * se;
     double e = 0.0;
-    if (al_end > TA) al_end = TA;
     for (int al = al_begin; al < al_end; al++) {
-        const int a = bd.t0[0] + al;
-        if (a >= v) break;
-        if (a < b) continue;
+        const int a = a0 + al;
         const i64 ab = (i64)a * v + b, ac = (i64)a * v + c;
         const double jk_ab = ovjk[ab], jk_ba = ovkj[ab], ik_ab = ovik[ab], ik_ba = ovki[ab], ij_ab = ovij[ab], ij_ba = ovji[ab];
         const double jk_ac = ovjk[ac], jk_ca = ovkj[ac], ik_ac = ovik[ac], ik_ca = ovki[ac], ij_ac = ovij[ac], ij_ca = ovji[ac];
         const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];
         double w[6], vv[6];
-        w[0] = Wsm[bd.slot_of_perm[0] * se + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
-        w[1] = Wsm[bd.slot_of_perm[1] * se + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
-        w[2] = Wsm[bd.slot_of_perm[2] * se + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
-        w[3] = Wsm[bd.slot_of_perm[3] * se + slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
-        w[4] = Wsm[bd.slot_of_perm[4] * se + slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
-        w[5] = Wsm[bd.slot_of_perm[5] * se + slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
+        w[0] = W0[slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
+        w[1] = W1[slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
+        w[2] = W2[slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
+        w[3] = W3[slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
+        w[4] = W4[slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
+        w[5] = W5[slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
         vv[0] = w[0] + t1i_a * jk_bc + ik_ac * t1j_b + ij_ab * t1k_c;
         vv[1] = w[1] + t1i_a * jk_cb + ik_ab * t1j_c + ij_ac * t1k_b;
         vv[2] = w[2] + t1i_b * jk_ac + ik_bc * t1j_a + ij_ba * t1k_c;
@@ -360,6 +396,17 @@ FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, 
         e += point_energy(w, vv, Dbc - P.fv[a], a, b, c, wijk);
     }
     return e;
+}
+
+// Energy of the column (bl, cl) of the block for al in [al_begin, al_end): same arithmetic as block_point_energy, organised
+// so that one thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each
+// either contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
+FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
+                                  int al_begin, int al_end)
+{
+    if (bd.ts[0] == 16 && bd.ts[1] == 16 && bd.ts[2] == 16)
+        return block_column_energy_t<true>(P, bd, i, j, k, Wsm, bl, cl, al_begin, al_end);
+    return block_column_energy_t<false>(P, bd, i, j, k, Wsm, bl, cl, al_begin, al_end);
 }
 
 }  // namespace fpt

@@ -77,6 +77,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// TMA bulk prefetch of a contiguous global range into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");

@@ -19,6 +19,7 @@
 //       energy of the block's a>=b>=c points is evaluated from the slots.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include "fpt_layout.h"
 #include "fpt_ptx.cuh"
 
@@ -44,10 +45,10 @@ static_assert(CHUNK_GROUPS % ABUF == 0 && APREF < ABUF, "A-fragment ring is inde
 struct Ctl {
     i64 cur_item;          // < 0: no more work
     ItemDesc item;
-    BlockDesc bd;
-    int ngemm;
-    GemmDesc gemm[MAX_GEMMS];
+    BlockTabEntry ent;     // bd, ngemm, gemm[] -- copied from the device block table by TMA; gemm[].p/q/r are positions in (i,j,k)
 };
+static_assert(sizeof(Ctl) % 16 == 0 && offsetof(Ctl, ent) % 16 == 0, "Ctl::ent is a TMA bulk-copy destination");
+constexpr int NPROF = 16;
 
 struct SmemTail {
     Ctl ctl[2];
@@ -74,19 +75,27 @@ __device__ __forceinline__ void group_bar(int grp) { named_bar_sync(2 + NGROUPS 
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
 // ---------------------------------------------------------------------------------------------------
+// Fetch the next item, decode it arithmetically and pull its block's descriptor table entry into ctl->ent with one TMA
+// bulk copy that completes on item_full (the scalar fields are ordinary stores released by the same barrier).
 __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
-                                                Ctl* ctl)
+                                                Ctl* ctl, uint64_t* item_full)
 {
     const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
-    if (it >= item_end) { ctl->cur_item = -1; return; }
+    if (it >= item_end) {
+        ctl->cur_item = -1;
+        mbar_arrive(item_full);
+        return;
+    }
+    i64 block;
+    item_decode_cf(P, it, ctl->item, block);
     ctl->cur_item = it;
-    item_decode(P, it, ctl->item);
-    make_block(ctl->item.A, ctl->item.B, ctl->item.C, P.vp, ctl->bd);
-    ctl->ngemm = make_gemms(ctl->bd, ctl->item.i, ctl->item.j, ctl->item.k, ctl->gemm);
+    mbar_arrive_expect_tx(item_full, (uint32_t)sizeof(BlockTabEntry));
+    tma_bulk_g2s(&ctl->ent, P.blocktab + block, (uint32_t)sizeof(BlockTabEntry), item_full);
 }
 
-// Item n+1 is fetched and decoded while the chunks of item n are still streaming (right after its first GEMM), so the
-// Q ring never runs dry at an item boundary.
+// Producer: one thread.  Streams the Q chunks of every GEMM of every item through the ring.  Item n+1 is fetched and
+// decoded while the chunks of item n are still streaming (right after its first GEMM), so the ring never runs dry at an
+// item boundary.
 __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
                                               double* Qsm, SmemTail* tail)
 {
@@ -94,20 +103,20 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
     const i64 gstride = (i64)P.vp * KGROUP;   // doubles between consecutive kappa groups of one (q,r) in Qt
     int stage = 0;
     uint32_t sphase = 0;
-    // item 0
     mbar_wait((uint64_t*)&tail->item_empty[0], 1);
-    producer_decode(P, item_begin, item_end, counter, &tail->ctl[0]);
-    mbar_arrive((uint64_t*)&tail->item_full[0]);
+    producer_decode(P, item_begin, item_end, counter, &tail->ctl[0], (uint64_t*)&tail->item_full[0]);
     for (uint32_t n = 0;; n++) {
         const int slot = n & 1;
         const Ctl* ctl = &tail->ctl[slot];
+        mbar_wait((uint64_t*)&tail->item_full[slot], (n >> 1) & 1);   // own TMA copy of the table entry has landed
         if (ctl->cur_item < 0) break;
-        const int ngemm = ctl->ngemm;
+        const int ngemm = ctl->ent.ngemm;
         for (int g = 0; g < ngemm; g++) {
-            const GemmDesc& gd = ctl->gemm[g];
+            const GemmDesc& gd = ctl->ent.gemm[g];
             const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
-            const double* src0 = P.Qt + qt_row(P, gd.q, gd.r, 0, gd.z0);
-            const double* src1 = P.Qt + qt_row(P, gd.r, gd.q, 0, gd.z0);
+            const int q = occ_pick(ctl->item, gd.q), r = occ_pick(ctl->item, gd.r);
+            const double* src0 = P.Qt + qt_row(P, q, r, 0, gd.z0);
+            const double* src1 = P.Qt + qt_row(P, r, q, 0, gd.z0);
             for (int c = 0; c < nchunks; c++) {
                 const int ng = min(CHUNK_GROUPS, P.G - c * CHUNK_GROUPS);
                 mbar_wait((uint64_t*)&tail->empty[stage], sphase ^ 1);
@@ -126,8 +135,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
             if (g == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
                 const uint32_t m = n + 1;
                 mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
-                producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1]);
-                mbar_arrive((uint64_t*)&tail->item_full[m & 1]);
+                producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
             }
         }
     }
@@ -144,12 +152,12 @@ struct RowSet {
     int rt0;                   // first row tile of this warp
 };
 
-__device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd, int warp, int lane, RowSet& rs)
+__device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
 {
     const int r = lane >> 2, kk = lane & 3;
     const int rt_total = (gd.TX * gd.TY) >> 3;
     const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
-    rs.base = P.Pt + pt_row(P, gd.p, gd.y0, gd.x0) + 2 * kk;
+    rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 2 * kk;
     rs.nvalid = 0;
     rs.rt0 = warp * mtw;
 #pragma unroll
@@ -269,19 +277,23 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
                                           double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase, int warp,
                                           int lane, long long* prof)
 {
-    const GemmDesc& gd = ctl->gemm[g];
+    const GemmDesc& gd = ctl->ent.gemm[g];
     double acc[MTW][NT][2];
     long long t0 = 0, t1 = 0;
     if (PROF) t0 = clock64();
     gemm_kloop<MTW, NT>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane);
     if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
     const RowSet rs_cur = rs;
-    if (g + 1 < ctl->ngemm) {
-        rows_setup(P, ctl->gemm[g + 1], warp, lane, rs);
+    if (g + 1 < ctl->ent.ngemm) {
+        const GemmDesc& gn = ctl->ent.gemm[g + 1];
+        rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
     }
     const int grp = warp >> 2;
-    token_wait(grp);   // all earlier RMW phases (either group) are complete
+    long long tw = 0;
+    if (PROF) tw = clock64();
+    token_wait(grp);   // all earlier RMW phases (any group) are complete
+    if (PROF) prof[6] += clock64() - tw;
     if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane, grp);
     else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
     token_pass(grp);
@@ -305,7 +317,8 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
 
 // ---------------------------------------------------------------------------------------------------
 // The kernel.  PROF: record a phase breakdown (cycles, warp 0's view) into prof_out[blockIdx*6 + 0..5] =
-// {wait-for-item, zero, k-loops, RMW (+barriers), energy, total}.
+// {wait-for-item, zero, k-loops, RMW (+token wait, next prologue), energy, total, token wait, -} for warp 0 (entries 0-7)
+// and for the first warp of the last group (entries 8-15).
 // ---------------------------------------------------------------------------------------------------
 template <bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -334,7 +347,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
 
     // ------------------------------- consumers -------------------------------
     if ((warp >> 2) == NGROUPS - 1) token_pass(NGROUPS - 1);   // the first RMW token goes to group 0
-    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_start = 0;
     if (PROF) t_start = clock64();
     double esum = 0.0;
@@ -351,12 +364,12 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (ctl->cur_item < 0) break;
         if (PROF) { t1 = clock64(); prof[0] += t1 - t0; }
 
-        const int ngemm = ctl->ngemm;
+        const int ngemm = ctl->ent.ngemm;
         RowSet rs;
-        rows_setup(P, ctl->gemm[0], warp, lane, rs);
+        rows_setup(P, ctl->ent.gemm[0], occ_pick(ctl->item, ctl->ent.gemm[0].p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
         {   // zero the live W slots
-            const int nz2 = (ctl->bd.nslot * ctl->bd.slot_elems) >> 1;
+            const int nz2 = (ctl->ent.bd.nslot * ctl->ent.bd.slot_elems) >> 1;
             double2* w2 = reinterpret_cast<double2*>(Wsm);
             for (int idx = tid; idx < nz2; idx += NCTHREADS) w2[idx] = make_double2(0.0, 0.0);
         }
@@ -364,7 +377,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 
         for (int g = 0; g < ngemm; g++) {
-            const GemmDesc& gd = ctl->gemm[g];
+            const GemmDesc& gd = ctl->ent.gemm[g];
             const int rt_total = (gd.TX * gd.TY) >> 3;
             const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
             const int nt = gd.TZ >> 2;
@@ -373,12 +386,17 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         consumer_bar();
         if (PROF) t0 = clock64();
         {
-            const BlockDesc& bd = ctl->bd;
+            const BlockDesc& bd = ctl->ent.bd;
             const int TC = bd.ts[2];
             const int half = tid >> 8, tt = tid & 255;   // two threads per (b,c) column, 8 values of a each
-            if (tt < bd.ts[1] * TC && !(P.dbg_flags & 2))
-                esum += block_column_energy(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt / TC, tt % TC, half * 8,
-                                            half * 8 + 8);
+            if (!(P.dbg_flags & 2)) {
+                if (bd.slot_elems == 4096)
+                    esum += block_column_energy_t<true>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt >> 4, tt & 15,
+                                                        half * 8, half * 8 + 8);
+                else if (tt < bd.ts[1] * TC)
+                    esum += block_column_energy_t<false>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt / TC, tt % TC,
+                                                         half * 8, half * 8 + 8);
+            }
         }
         consumer_bar();       // W slots and ctl[slot] may be reused
         if (lane == 0) mbar_arrive((uint64_t*)&tail->item_empty[slot]);
@@ -394,10 +412,10 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         double s = 0.0;
         for (int w = 0; w < NCWARPS; w++) s += tail->red[w];
         partials[blockIdx.x] = s;
-        if (PROF) {
-            prof[5] = clock64() - t_start;
-            for (int t = 0; t < 6; t++) prof_out[blockIdx.x * 6 + t] = prof[t];
-        }
+    }
+    if (PROF && lane == 0 && (warp == 0 || warp == NCWARPS - 4)) {   // group 0's and group 3's view
+        prof[5] = clock64() - t_start;
+        for (int t = 0; t < 8; t++) prof_out[blockIdx.x * NPROF + (warp ? 8 : 0) + t] = prof[t];
     }
 }
 

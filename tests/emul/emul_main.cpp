@@ -64,8 +64,14 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
     std::vector<double> W((size_t)MAX_SLOTS * TMAX * TMAX * TMAX);
     double E = 0.0;
     for (i64 item = item_begin; item < item_end; item++) {
-        ItemDesc it;
+        ItemDesc it, it2;
         item_decode(P, item, it);
+        i64 blk2;
+        item_decode_cf(P, item, it2, blk2);
+        if (it.i != it2.i || it.j != it2.j || it.k != it2.k || it.A != it2.A || it.B != it2.B || it.C != it2.C) {
+            fprintf(stderr, "closed-form item decode disagrees at %lld\n", item);
+            return 7;
+        }
         if (!(it.i >= it.j && it.j >= it.k) || (it.i == it.j && it.j == it.k) || !(it.A >= it.B && it.B >= it.C) || it.A >= P.nt) {
             fprintf(stderr, "bad item decode %lld -> %d %d %d / %d %d %d\n", item, it.i, it.j, it.k, it.A, it.B, it.C);
             return 2;
@@ -73,7 +79,8 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         BlockDesc bd;
         make_block(it.A, it.B, it.C, P.vp, bd);
         GemmDesc gd[MAX_GEMMS];
-        const int ng = make_gemms(bd, it.i, it.j, it.k, gd);
+        const int ng = make_gemms(bd, 0, 1, 2, gd);   // positions, as in the device block table
+        for (int g = 0; g < ng; g++) { gd[g].p = occ_pick(it, gd[g].p); gd[g].q = occ_pick(it, gd[g].q); gd[g].r = occ_pick(it, gd[g].r); }
         std::fill(W.begin(), W.begin() + (size_t)bd.nslot * bd.slot_elems, 0.0);
         std::vector<int> hits((size_t)bd.nslot * bd.slot_elems, 0);
         for (int g = 0; g < ng; g++) {
