@@ -192,7 +192,7 @@ __device__ __forceinline__ void df_store(const Problem& P, double* out, int m, i
     } else if (MODE == 1) {
         const int l = m % o, q = m / o, r = n % o, z = n / o;
         const int kappa = v + l;
-        out[qt_row(P, q, r, kappa >> 3, z) + (kappa & 7)] = val;
+        out[qt_row(P, q, r, kappa / KGROUP, z) + (kappa % KGROUP)] = val;
     } else {
         const int q = m % o, y = m / o, r = n % o, z = n / o;
         out[(((i64)q * o + r) * v + y) * v + z] = val;

@@ -15,8 +15,8 @@
 // i.e. X(p;q,r)[x,y,z] lands on the W element whose i/j/k-paired virtual is  x<->q, y<->p, z<->r.
 //
 // Device-resident operand layouts (built once per call by the prep kernels):
-//     Pt [p][y][x][kappa]          kappa contiguous, Kp = roundup8(v+o) doubles per row, x,y < vp (zero padded)
-//     Qt [q*o+r][g][z][8]          kappa = 8g + (0..7), z < vp (zero padded)
+//     Pt [p][y][x][kappa]          kappa contiguous, Kp = roundup16(v+o) doubles per row, x,y < vp (zero padded)
+//     Qt [q*o+r][g][z][16]         kappa = 16g + (0..15), z < vp (zero padded)
 //     OV2[q*o+r][y][z] = OVOV[q,y,r,z]     T1d[p][x] = T1[p,x]
 //
 // Work decomposition: virtual range [0,vp) is cut into tiles (edge 16, last tile 4/8/12); a *block* is a
@@ -37,8 +37,8 @@
 namespace fpt {
 
 constexpr int TMAX = 16;       // largest tile edge
-constexpr int KGROUP = 8;      // kappa per group: one 16-byte load per lane feeds two DMMA.8x8x4
-constexpr int CHUNK_GROUPS = 3;  // kappa groups per shared-memory Q stage (24 kappa)
+constexpr int KGROUP = 16;     // kappa per group: one 32-byte (256-bit) load per lane feeds four DMMA.8x8x4
+constexpr int CHUNK_GROUPS = 2;  // kappa groups per shared-memory Q stage (32 kappa)
 constexpr int MAX_SLOTS = 6;
 constexpr int MAX_GEMMS = 18;
 

@@ -20,6 +20,14 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+struct __align__(32) double4x { double x, y, z, w; };
+// 256-bit streaming load (sm_100: LDG.E.256): one full 128-byte line per row for the 4 lanes that share it
+__device__ __forceinline__ double4x ldg_stream_f64x4(const double* p)
+{
+    double4x v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)

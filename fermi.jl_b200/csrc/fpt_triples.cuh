@@ -10,11 +10,11 @@
 // 640 threads, 1 CTA / SM, grid = #SMs.
 //   producer (warp 16, lane 0): pulls items off the global counter, decodes them into a double-buffered control
 //       block (item / block / GEMM descriptors) and streams the Q operand chunks of all GEMMs of the item through a
-//       4-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
+//       3-stage shared-memory ring with TMA bulk copies that complete on `full` mbarriers; stages are recycled
 //       through `empty` mbarriers, so it runs ahead of the consumers across GEMM and item boundaries.
 //   consumers: for each P-stationary GEMM  D[TX*TY x 2*TZ] = P_p . [Q_qr | Q_rq]  every warp owns <= 2 row tiles
 //       (8 rows) x all column tiles; A fragments come straight from global memory (each P row is used by exactly one
-//       warp, kappa-contiguous, 16 B per lane, prefetched two kappa-groups ahead), B fragments from the ring.  The
+//       warp, kappa-contiguous, 32 B per lane, 256-bit loads prefetched one 16-kappa group ahead), B fragments from the ring.  The
 //       accumulators are then added into the W slots (swizzled, see fpt_layout.h), and after the last GEMM the
 //       energy of the block's a>=b>=c points is evaluated from the slots.
 #pragma once
@@ -33,13 +33,14 @@ constexpr int NTHREADS = NCTHREADS + 128;          // + producer warpgroup (only
 // so 512*R_consumer + 128*R_producer must not exceed that (otherwise the TRY_ALLOC spins forever).
 constexpr int LAUNCH_REGS = 96, CONSUMER_REGS = 112, PRODUCER_REGS = 24;
 static_assert(NCTHREADS * CONSUMER_REGS + 128 * PRODUCER_REGS <= NTHREADS * LAUNCH_REGS, "setmaxnreg budget exceeds the CTA pool");
-constexpr int QSTAGES = 4;
-constexpr int QBLK = (TMAX + 1) * KGROUP;          // doubles per (group, s) block: TZ rows of 8 kappa + 64 B bank skew
-constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 816 doubles = 6528 B
+constexpr int QSTAGES = 3;
+constexpr int QBLK = (TMAX + 1) * KGROUP + 2;      // doubles per (group, s) block: TZ rows of 16 kappa, skewed by 16 B mod 128 B
+                                                   // so that the s=0 / s=1 halves of a quarter-warp hit disjoint banks
+constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 1096 doubles = 8768 B
 constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
 constexpr int MTW_MAX = 2;
-constexpr int APREF = 2;                           // A-fragment prefetch distance in kappa groups
-constexpr int ABUF = 3;                            // group gg lives in buffer gg % ABUF = gl % ABUF
+constexpr int APREF = 1;                           // A-fragment prefetch distance in kappa groups (of 16)
+constexpr int ABUF = 2;                            // group gg lives in buffer gg % ABUF = gl % ABUF
 static_assert(CHUNK_GROUPS % ABUF == 0 && APREF < ABUF, "A-fragment ring is indexed by the group's position in its chunk");
 
 struct Ctl {
@@ -157,7 +158,7 @@ __device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd,
     const int r = lane >> 2, kk = lane & 3;
     const int rt_total = (gd.TX * gd.TY) >> 3;
     const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
-    rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 2 * kk;
+    rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 4 * kk;
     rs.nvalid = 0;
     rs.rt0 = warp * mtw;
 #pragma unroll
@@ -173,13 +174,13 @@ __device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd,
 }
 
 template <int MTW>
-__device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, double2 (&a)[ABUF][MTW_MAX])
+__device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX])
 {
 #pragma unroll
     for (int d = 0; d < APREF; d++)
         if (d < P.G) {
 #pragma unroll
-            for (int mt = 0; mt < MTW; mt++) a[d][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + d * KGROUP);
+            for (int mt = 0; mt < MTW; mt++) a[d][mt] = ldg_stream_f64x4(rs.base + rs.off[mt] + d * KGROUP);
         }
 }
 
@@ -188,12 +189,12 @@ __device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, d
 // Column n of tile ct is (zl = 4ct + (n>>1), s = n&1), so a lane's two D elements are (zl = 4ct + kk, s = e).
 // ---------------------------------------------------------------------------------------------------
 template <int MTW, int NT>
-__device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double2 (&a)[ABUF][MTW_MAX],
+__device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
                                            double (&acc)[MTW][NT][2], const double* Qsm, SmemTail* tail, int& stage,
                                            uint32_t& sphase, int lane)
 {
     const int kk = lane & 3, n = lane >> 2;
-    const int boff = ((n & 1) * QBLK) + (n >> 1) * KGROUP + 2 * kk;   // s block + row zl(ct=0) + kappa pair
+    const int boff = ((n & 1) * QBLK) + (n >> 1) * KGROUP + 4 * kk;   // s block + row zl(ct=0) + this lane's 4 kappa
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
 #pragma unroll
     for (int mt = 0; mt < MTW; mt++)
@@ -215,19 +216,26 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
                 if (gg + APREF < P.G) {
 #pragma unroll
                     for (int mt = 0; mt < MTW; mt++)
-                        a[(gl + APREF) % ABUF][mt] = ldg_stream_f64x2(rs.base + rs.off[mt] + (gg + APREF) * KGROUP);
+                        a[(gl + APREF) % ABUF][mt] = ldg_stream_f64x4(rs.base + rs.off[mt] + (gg + APREF) * KGROUP);
                 }
-                double2 b[NT];
+                // kappa = 16*gg + 4*kk + h, h = 0..3: two halves of B fragments (h = 0,1 then h = 2,3)
 #pragma unroll
-                for (int ct = 0; ct < NT; ct++) b[ct] = *reinterpret_cast<const double2*>(st + gl * 2 * QBLK + ct * 4 * KGROUP);
+                for (int hh = 0; hh < 2; hh++) {
+                    double2 b[NT];
 #pragma unroll
-                for (int mt = 0; mt < MTW; mt++)
+                    for (int ct = 0; ct < NT; ct++)
+                        b[ct] = *reinterpret_cast<const double2*>(st + gl * 2 * QBLK + ct * 4 * KGROUP + 2 * hh);
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].x, b[ct].x);
+                    for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-                for (int mt = 0; mt < MTW; mt++)
+                        for (int ct = 0; ct < NT; ct++)
+                            dmma884(acc[mt][ct][0], acc[mt][ct][1], hh ? a[gl % ABUF][mt].z : a[gl % ABUF][mt].x, b[ct].x);
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) dmma884(acc[mt][ct][0], acc[mt][ct][1], a[gl % ABUF][mt].y, b[ct].y);
+                    for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+                        for (int ct = 0; ct < NT; ct++)
+                            dmma884(acc[mt][ct][0], acc[mt][ct][1], hh ? a[gl % ABUF][mt].w : a[gl % ABUF][mt].y, b[ct].y);
+                }
             }
         }
         __syncwarp();
@@ -273,7 +281,7 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 
 // one GEMM of an item: k-loop, then (overlapped with the RMW epilogue) the next GEMM's row setup and first A loads
 template <int MTW, int NT, bool PROF>
-__device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int g, RowSet& rs, double2 (&a)[ABUF][MTW_MAX],
+__device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int g, RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
                                           double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase, int warp,
                                           int lane, long long* prof)
 {
@@ -353,7 +361,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     double esum = 0.0;
     int stage = 0;
     uint32_t sphase = 0;
-    double2 a[ABUF][MTW_MAX];
+    double4x a[ABUF][MTW_MAX];
 
     for (uint32_t n = 0;; n++) {
         const int slot = n & 1;

@@ -49,7 +49,7 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                 for (int kappa = 0; kappa < v + o; kappa++) {
                     double val = kappa < v ? T2[r + (i64)o * (q + (i64)o * (z + (i64)v * kappa))]
                                            : OOOV[(kappa - v) + (i64)o * (q + (i64)o * (r + (i64)o * z))];
-                    Qt[qt_row(P, q, r, kappa >> 3, z) + (kappa & 7)] = val;
+                    Qt[qt_row(P, q, r, kappa / KGROUP, z) + (kappa % KGROUP)] = val;
                 }
     for (int q = 0; q < o; q++)
         for (int r = 0; r < o; r++)
@@ -92,7 +92,7 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                     for (int zl = 0; zl < G.TZ; zl++) {
                         double d = 0.0;
                         for (int kappa = 0; kappa < P.Kp; kappa++)
-                            d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa >> 3, G.z0 + zl) + (kappa & 7)];
+                            d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa / KGROUP, G.z0 + zl) + (kappa % KGROUP)];
                         const int off = gemm_dest(G, s, xl, yl, zl);
                         {   // the kernel's fast RMW addressing must agree with the reference form
                             DestIter di;
