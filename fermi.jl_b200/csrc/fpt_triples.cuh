@@ -26,7 +26,6 @@
 namespace fpt {
 
 constexpr int NCWARPS = 16;                        // consumer warps = 4 warpgroups
-constexpr int NGROUPS = 4;
 constexpr int NCTHREADS = NCWARPS * 32;            // 512
 constexpr int NTHREADS = NCTHREADS + 128;          // + producer warpgroup (only its first lane works)
 // setmaxnreg only redistributes the CTA's launch-time allocation: 640 threads x 96 registers (launch bound) = 61440,
@@ -53,7 +52,7 @@ constexpr int NPROF = 16;
 
 struct SmemTail {
     Ctl ctl[2];
-    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2];
+    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2], rmw_done;
     double red[NCWARPS];
 };
 
@@ -61,17 +60,10 @@ constexpr size_t TRIPLES_SMEM_BYTES = (size_t)(WSLOT_DOUBLES + QSTAGES * QSTAGE_
 
 __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 
-// The consumer warps form four groups (warpgroups) that take turns in the RMW epilogues: a token (named barriers 2..5,
-// bar.arrive / bar.sync producer-consumer form) serialises all RMW phases in the order G0(g), G1(g), G2(g), G3(g), G0(g+1)...
-// so while one group adds its accumulators into the W slots the other three keep issuing DMMAs -- the tensor pipe does
-// not drain at a GEMM boundary -- and no two warps of different groups ever touch a W element concurrently.
-constexpr int GROUP_THREADS = NCTHREADS / NGROUPS;
-__device__ __forceinline__ void token_wait(int grp) { named_bar_sync(2 + grp, 2 * GROUP_THREADS); }
-__device__ __forceinline__ void token_pass(int grp)
-{
-    asm volatile("bar.arrive %0, %1;\n" ::"r"(2 + ((grp + 1) & (NGROUPS - 1))), "r"(2 * GROUP_THREADS) : "memory");
-}
-__device__ __forceinline__ void group_bar(int grp) { named_bar_sync(2 + NGROUPS + grp, GROUP_THREADS); }
+// RMW phases of *different* GEMMs may touch the same W elements (through different thread->element maps), RMW phases of
+// the same GEMM never do (except the diag_xz aliasing handled inside gemm_rmw).  So all warps add their accumulators
+// concurrently, and a split mbarrier orders consecutive GEMMs: every warp arrives on `rmw_done` after its RMW(g) and waits
+// for that phase to complete before its RMW(g+1) -- a whole k-loop later, so the wait practically never blocks.
 
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
@@ -248,7 +240,7 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
 // RMW of the accumulators into the W slots
 template <int MTW, int NT>
 __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, const double (&acc)[MTW][NT][2], double* Wsm,
-                                         int lane, int grp)
+                                         int lane)
 {
     const int kk = lane & 3, r = lane >> 2;
     int xl[MTW], yl[MTW];
@@ -261,8 +253,7 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
-        // (the other group is excluded by the token)
-        if (e == 1 && gd.diag_xz) group_bar(grp);
+        if (e == 1 && gd.diag_xz) consumer_bar();
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) {
             if (mt < rs.nvalid) {
@@ -282,8 +273,8 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 // one GEMM of an item: k-loop, then (overlapped with the RMW epilogue) the next GEMM's row setup and first A loads
 template <int MTW, int NT, bool PROF>
 __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int g, RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
-                                          double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase, int warp,
-                                          int lane, long long* prof)
+                                          double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase,
+                                          uint32_t& gcount, int warp, int lane, long long* prof)
 {
     const GemmDesc& gd = ctl->ent.gemm[g];
     double acc[MTW][NT][2];
@@ -297,14 +288,15 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
         rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
     }
-    const int grp = warp >> 2;
     long long tw = 0;
     if (PROF) tw = clock64();
-    token_wait(grp);   // all earlier RMW phases (any group) are complete
+    if (gcount > 0) mbar_wait((uint64_t*)&tail->rmw_done, (gcount - 1) & 1);   // every warp has finished RMW(previous GEMM)
     if (PROF) prof[6] += clock64() - tw;
-    if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane, grp);
+    if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane);
     else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
-    token_pass(grp);
+    __syncwarp();
+    if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done);
+    gcount++;
     if (PROF) prof[3] += clock64() - t1;
 }
 
@@ -341,6 +333,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     if (tid == 0) {
         for (int s = 0; s < QSTAGES; s++) { mbar_init((uint64_t*)&tail->full[s], 1); mbar_init((uint64_t*)&tail->empty[s], NCWARPS); }
         for (int s = 0; s < 2; s++) { mbar_init((uint64_t*)&tail->item_full[s], 1); mbar_init((uint64_t*)&tail->item_empty[s], NCWARPS); }
+        mbar_init((uint64_t*)&tail->rmw_done, NCWARPS);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -354,13 +347,12 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     setmaxnreg_inc<CONSUMER_REGS>();
 
     // ------------------------------- consumers -------------------------------
-    if ((warp >> 2) == NGROUPS - 1) token_pass(NGROUPS - 1);   // the first RMW token goes to group 0
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_start = 0;
     if (PROF) t_start = clock64();
     double esum = 0.0;
     int stage = 0;
-    uint32_t sphase = 0;
+    uint32_t sphase = 0, gcount = 0;
     double4x a[ABUF][MTW_MAX];
 
     for (uint32_t n = 0;; n++) {
@@ -389,7 +381,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
             const int rt_total = (gd.TX * gd.TY) >> 3;
             const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
             const int nt = gd.TZ >> 2;
-            FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, warp, lane, prof)));
+            FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
         }
         consumer_bar();
         if (PROF) t0 = clock64();
