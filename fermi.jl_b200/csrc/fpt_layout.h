@@ -213,6 +213,21 @@ FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, Des
     it.d1 = (sc == 2) ? 4 : 1;
     return true;
 }
+// Same, with the role permutation `sel` hoisted into a (warp-uniform) switch so that no per-element selects remain.
+FPT_HD void dest_iter_init_fast(int dbase, int sel, int Tb, int xl, int yl, int kk, DestIter& it)
+{
+    int la, lb, lc;
+    switch (sel) {
+    case (0 | (1 << 2) | (2 << 4)): la = xl; lb = yl; lc = kk; it.zs = 0; it.d1 = 4; break;        // (x,y,z)
+    case (0 | (2 << 2) | (1 << 4)): la = xl; lb = kk; lc = yl; it.zs = 64; it.d1 = 1; break;       // (x,z,y)
+    case (1 | (0 << 2) | (2 << 4)): la = yl; lb = xl; lc = kk; it.zs = 0; it.d1 = 4; break;        // (y,x,z)
+    case (1 | (2 << 2) | (0 << 4)): la = yl; lb = kk; lc = xl; it.zs = 64; it.d1 = 1; break;       // (y,z,x)
+    case (2 | (0 << 2) | (1 << 4)): la = kk; lb = xl; lc = yl; it.zs = 64 * Tb; it.d1 = 1; break;  // (z,x,y)
+    default:                         la = kk; lb = yl; lc = xl; it.zs = 64 * Tb; it.d1 = 1; break;  // (z,y,x)
+    }
+    it.lin0 = dbase + (la * Tb + lb) * 16;
+    it.w0 = lc ^ swz_a(la) ^ swz_b(lb);
+}
 FPT_HD int dest_iter_off(const DestIter& it, int ct) { return it.lin0 + ct * it.zs + (it.w0 ^ (ct * it.d1)); }
 
 // Per-block descriptors are independent of (i,j,k) up to which occupied plays p, q, r: the host builds one entry per
@@ -374,6 +389,9 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     const double* W4 = Wsm + bd.slot_of_perm[4] * se;
     const double* W5 = Wsm + bd.slot_of_perm[5] * se;
     double e = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
     for (int al = al_begin; al < al_end; al++) {
         const int a = a0 + al;
         const i64 ab = (i64)a * v + b, ac = (i64)a * v + c;

@@ -100,6 +100,11 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                                 fprintf(stderr, "dest_iter mismatch\n");
                                 return 5;
                             }
+                            if (G.dTc[s] == 16) {
+                                DestIter df;
+                                dest_iter_init_fast(G.dbase[s], G.dsel[s], G.dTb[s], xl, yl, zl & 3, df);
+                                if (dest_iter_off(df, zl >> 2) != off) { fprintf(stderr, "dest_iter_fast mismatch\n"); return 8; }
+                            }
                         }
                         if (off < 0 || off >= bd.nslot * bd.slot_elems) { fprintf(stderr, "dest out of range\n"); return 3; }
                         W[off] += d;
