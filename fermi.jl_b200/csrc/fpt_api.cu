@@ -158,7 +158,7 @@ static int setup_problem(fpt_handle* h, int o, int v)
     P.nitems = acc;
     if (h->Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
     if (h->Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
-    if (h->OV2.ensure((size_t)o * o * v * v * sizeof(double))) return 1;
+    if (h->OV2.ensure((size_t)ov2_elems(P) * sizeof(double))) return 1;
     if (h->T1d.ensure((size_t)o * v * sizeof(double))) return 1;
     if (h->fo.ensure((size_t)o * sizeof(double))) return 1;
     if (h->fv.ensure((size_t)v * sizeof(double))) return 1;
@@ -225,7 +225,7 @@ extern "C" int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, co
     if (stage_in(h, h->sOOOV, OOOV, (size_t)o * o * o * v, &dOOOV, &h2d)) return 1;
     if (stage_in(h, h->sOVOV, OVOV, (size_t)o * v * o * v, &dOVOV, &h2d)) return 1;
     prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, h->stream>>>(P, h->Qt.d(), dT2, dOOOV);
-    prep_ov2<<<grid1d((i64)o * o * v * v), 256, 0, h->stream>>>(P, h->OV2.d(), dOVOV);
+    prep_ov2<<<grid1d(ov2_elems(P)), 256, 0, h->stream>>>(P, h->OV2.d(), dOVOV);
     h->launches += 2;
     CK(cudaGetLastError());
     // OVVV -> Pt particle part, in chunks over the slowest index d
@@ -290,6 +290,7 @@ extern "C" int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double
         dim3 grid((M + 63) / 64, (N + 63) / 64);
         df_gemm_kernel<1><<<grid, 128, 0, h->stream>>>(P, h->Qt.d(), dBOO, dBOV, M, N, naux);
     }
+    CK(cudaMemsetAsync(h->OV2.p, 0, (size_t)ov2_elems(P) * sizeof(double), h->stream));
     {   // OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z]  -> OV2                 (DFERI.jl:139-154)
         const int M = o * v, N = o * v;
         dim3 grid((M + 63) / 64, (N + 63) / 64);

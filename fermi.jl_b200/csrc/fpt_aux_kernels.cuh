@@ -85,18 +85,20 @@ __global__ void prep_qt(Problem P, double* Qt, const double* __restrict__ T2, co
     }
 }
 
-// OV2[(q,r)][y][z] = OVOV[q,y,r,z]
+// OV2[(q,r)][Y][Z][16][16] = OVOV[q,y,r,z] (zero padded to 16-multiples)
 __global__ void prep_ov2(Problem P, double* OV2, const double* __restrict__ OVOV)
 {
-    const int o = P.o, v = P.v;
-    const i64 n = (i64)o * o * v * v;
+    const int o = P.o, v = P.v, nt = P.nt;
+    const i64 n = ov2_elems(P);
     for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
-        const int z = (int)(idx % v);
-        i64 t = idx / v;
-        const int y = (int)(t % v); t /= v;
+        const int zl = (int)(idx & 15), yl = (int)((idx >> 4) & 15);
+        i64 t = idx >> 8;
+        const int Z = (int)(t % nt); t /= nt;
+        const int Y = (int)(t % nt); t /= nt;
         const int r = (int)(t % o);
         const int q = (int)(t / o);
-        OV2[idx] = OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))];
+        const int y = Y * 16 + yl, z = Z * 16 + zl;
+        OV2[idx] = (y < v && z < v) ? OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))] : 0.0;
     }
 }
 
@@ -195,7 +197,7 @@ __device__ __forceinline__ void df_store(const Problem& P, double* out, int m, i
         out[qt_row(P, q, r, kappa / KGROUP, z) + (kappa % KGROUP)] = val;
     } else {
         const int q = m % o, y = m / o, r = n % o, z = n / o;
-        out[(((i64)q * o + r) * v + y) * v + z] = val;
+        out[ov2_idx(P, q, r, y, z)] = val;
     }
 }
 

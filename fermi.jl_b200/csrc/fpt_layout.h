@@ -17,7 +17,7 @@
 // Device-resident operand layouts (built once per call by the prep kernels):
 //     Pt [p][y][x][kappa]          kappa contiguous, Kp = roundup16(v+o) doubles per row, x,y < vp (zero padded)
 //     Qt [q*o+r][g][z][16]         kappa = 16g + (0..15), z < vp (zero padded)
-//     OV2[q*o+r][y][z] = OVOV[q,y,r,z]     T1d[p][x] = T1[p,x]
+//     OV2[q*o+r][Y][Z][16][16] = OVOV[q,y,r,z] in 16x16 tiles (Y = y>>4, ...), zero padded;   T1d[p][x] = T1[p,x]
 //
 // Work decomposition: virtual range [0,vp) is cut into tiles (edge 16, last tile 4/8/12); a *block* is a
 // tile triple A>=B>=C; an *item* is (i>=j, block, k<=j) ordered pair-major / block / k-fastest so that
@@ -276,6 +276,16 @@ FPT_HD void item_decode(const Problem& P, i64 item, ItemDesc& it)
     tetra_decode(rem / nk, it.A, it.B, it.C);
 }
 
+// OV2 is stored in 16x16 tiles so that the 18 tiles an item's energy stage reads are 2 KB contiguous blocks (one TMA L2
+// prefetch each) and the in-tile offsets are shift/adds.
+FPT_HD i64 ov2_pair_base(const Problem& P, int q, int r) { return ((i64)q * P.o + r) * P.nt * P.nt * 256; }
+FPT_HD int ov2_tile_off(const Problem& P, int Y, int Z) { return (Y * P.nt + Z) * 256; }
+FPT_HD i64 ov2_idx(const Problem& P, int q, int r, int y, int z)
+{
+    return ov2_pair_base(P, q, r) + ov2_tile_off(P, y >> 4, z >> 4) + ((y & 15) << 4) + (z & 15);
+}
+FPT_HD i64 ov2_elems(const Problem& P) { return (i64)P.o * P.o * P.nt * P.nt * 256; }
+
 FPT_HD int occ_pick(const ItemDesc& it, int pos) { return pos == 0 ? it.i : (pos == 1 ? it.j : it.k); }
 
 // Same decode without the prefix table: the number of non-zero-weight triplets before pair (i,j) is
@@ -312,7 +322,7 @@ FPT_HD double point_energy(const double* w, const double* vv, double Dd, int a, 
 FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int pt)
 {
     const int TB = bd.ts[1], TC = bd.ts[2];
-    const int v = P.v, o = P.o;
+    const int v = P.v;
     const int cl = pt % TC;
     const int t2 = pt / TC;
     const int bl = t2 % TB, al = t2 / TB;
@@ -323,13 +333,6 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     const double* t1k = P.T1d + (i64)k * v;
     // OV2[(q,r)][y][z] = (qy|rz) = OV2[(r,q)][z][y]: always index so that the virtual that comes later in (a,b,c)
     // is the contiguous one -- lanes run over c, so every load is either coalesced or a broadcast.
-    const i64 vv2 = (i64)v * v;
-    const double* ovjk = P.OV2 + ((i64)j * o + k) * vv2;
-    const double* ovkj = P.OV2 + ((i64)k * o + j) * vv2;
-    const double* ovik = P.OV2 + ((i64)i * o + k) * vv2;
-    const double* ovki = P.OV2 + ((i64)k * o + i) * vv2;
-    const double* ovij = P.OV2 + ((i64)i * o + j) * vv2;
-    const double* ovji = P.OV2 + ((i64)j * o + i) * vv2;
     double w[6], vv[6];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -340,9 +343,9 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
         const int lx = pick3(c0, al, bl, cl), ly = pick3(c1, al, bl, cl), lz = pick3(c2, al, bl, cl);
         const int off = bd.slot_of_perm[m] * bd.slot_elems + slot_index(lx, ly, lz, bd.ts[c1], bd.ts[c2]);
         w[m] = Wsm[off];
-        const double g_jk = (c2 > c1) ? ovjk[(i64)y * v + z] : ovkj[(i64)z * v + y];   // (jy|kz)
-        const double g_ik = (c2 > c0) ? ovik[(i64)x * v + z] : ovki[(i64)z * v + x];   // (ix|kz)
-        const double g_ij = (c1 > c0) ? ovij[(i64)x * v + y] : ovji[(i64)y * v + x];   // (ix|jy)
+        const double g_jk = (c2 > c1) ? P.OV2[ov2_idx(P, j, k, y, z)] : P.OV2[ov2_idx(P, k, j, z, y)];   // (jy|kz)
+        const double g_ik = (c2 > c0) ? P.OV2[ov2_idx(P, i, k, x, z)] : P.OV2[ov2_idx(P, k, i, z, x)];   // (ix|kz)
+        const double g_ij = (c1 > c0) ? P.OV2[ov2_idx(P, i, j, x, y)] : P.OV2[ov2_idx(P, j, i, y, x)];   // (ix|jy)
         vv[m] = w[m] + t1i[x] * g_jk + g_ik * t1j[y] + g_ij * t1k[z];
     }
     const double Dd = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[a] - P.fv[b] - P.fv[c];
@@ -354,7 +357,7 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
                                     int al_begin, int al_end)
 {
     const int TA = ALL16 ? 16 : bd.ts[0], TB = ALL16 ? 16 : bd.ts[1], TC = ALL16 ? 16 : bd.ts[2];
-    const int v = P.v, o = P.o;
+    const int v = P.v;
     const int a0 = bd.t0[0];
     const int b = bd.t0[1] + bl, c = bd.t0[2] + cl;
     if (b >= v || c >= v || b < c) return 0.0;
@@ -363,17 +366,19 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     if (al_end > TA) al_end = TA;
     if (al_end > v - a0) al_end = v - a0;
     if (al_begin >= al_end) return 0.0;
-    const i64 vv2 = (i64)v * v;
     const double* t1i = P.T1d + (i64)i * v;
     const double* t1j = P.T1d + (i64)j * v;
     const double* t1k = P.T1d + (i64)k * v;
-    const double* ovjk = P.OV2 + ((i64)j * o + k) * vv2;   // [y][z] = (jy|kz)
-    const double* ovkj = P.OV2 + ((i64)k * o + j) * vv2;   // [y][z] = (ky|jz) = (jz|ky)
-    const double* ovik = P.OV2 + ((i64)i * o + k) * vv2;
-    const double* ovki = P.OV2 + ((i64)k * o + i) * vv2;
-    const double* ovij = P.OV2 + ((i64)i * o + j) * vv2;
-    const double* ovji = P.OV2 + ((i64)j * o + i) * vv2;
-    const i64 bc = (i64)b * v + c;
+    const double* ovjk = P.OV2 + ov2_pair_base(P, j, k);   // [y][z] = (jy|kz)
+    const double* ovkj = P.OV2 + ov2_pair_base(P, k, j);   // [y][z] = (ky|jz) = (jz|ky)
+    const double* ovik = P.OV2 + ov2_pair_base(P, i, k);
+    const double* ovki = P.OV2 + ov2_pair_base(P, k, i);
+    const double* ovij = P.OV2 + ov2_pair_base(P, i, j);
+    const double* ovji = P.OV2 + ov2_pair_base(P, j, i);
+    // tile-local offsets: the block's tiles are 16-aligned, so (y,z) in tile (Y,Z) sits at tile_off + yl*16 + zl
+    const int bc = ov2_tile_off(P, bd.tile[1], bd.tile[2]) + (bl << 4) + cl;
+    const int ab0 = ov2_tile_off(P, bd.tile[0], bd.tile[1]) + bl;
+    const int ac0 = ov2_tile_off(P, bd.tile[0], bd.tile[2]) + cl;
     const double jk_bc = ovjk[bc], jk_cb = ovkj[bc];       // (jb|kc), (jc|kb)
     const double ik_bc = ovik[bc], ik_cb = ovki[bc];       // (ib|kc), (ic|kb)
     const double ij_bc = ovij[bc], ij_cb = ovji[bc];       // (ib|jc), (ic|jb)
@@ -394,7 +399,7 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
 #endif
     for (int al = al_begin; al < al_end; al++) {
         const int a = a0 + al;
-        const i64 ab = (i64)a * v + b, ac = (i64)a * v + c;
+        const int ab = ab0 + (al << 4), ac = ac0 + (al << 4);
         const double jk_ab = ovjk[ab], jk_ba = ovkj[ab], ik_ab = ovik[ab], ik_ba = ovki[ab], ij_ab = ovij[ab], ij_ba = ovji[ab];
         const double jk_ac = ovjk[ac], jk_ca = ovkj[ac], ik_ac = ovik[ac], ik_ca = ovki[ac], ij_ac = ovij[ac], ij_ca = ovji[ac];
         const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];

@@ -84,6 +84,19 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
     ctl->cur_item = it;
     mbar_arrive_expect_tx(item_full, (uint32_t)sizeof(BlockTabEntry));
     tma_bulk_g2s(&ctl->ent, P.blocktab + block, (uint32_t)sizeof(BlockTabEntry), item_full);
+    // the energy stage of this item (one item ahead of the consumers) reads 18 OV2 tiles of 2 KB: pull them into L2 now
+    const int A = ctl->item.A, B = ctl->item.B, C = ctl->item.C;
+    const int toff[3] = {ov2_tile_off(P, B, C), ov2_tile_off(P, A, B), ov2_tile_off(P, A, C)};
+    const int occ[3] = {ctl->item.i, ctl->item.j, ctl->item.k};
+#pragma unroll
+    for (int x = 0; x < 3; x++)
+#pragma unroll
+        for (int y = 0; y < 3; y++)
+            if (x != y) {
+                const double* pb = P.OV2 + ov2_pair_base(P, occ[x], occ[y]);
+#pragma unroll
+                for (int t = 0; t < 3; t++) tma_prefetch_l2(pb + toff[t], 2048);
+            }
 }
 
 // Producer: one thread.  Streams the Q chunks of every GEMM of every item through the ring.  Item n+1 is fetched and

@@ -35,7 +35,7 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
 
     // ---- layout prep (same formulas as prep_* kernels) ----
     std::vector<double> Pt((size_t)o * P.vp * P.vp * P.Kp, 0.0), Qt((size_t)o * o * P.G * P.vp * KGROUP, 0.0),
-        OV2((size_t)o * o * v * v), T1d((size_t)o * v);
+        OV2((size_t)ov2_elems(P), 0.0), T1d((size_t)o * v);
     for (int p = 0; p < o; p++)
         for (int y = 0; y < v; y++)
             for (int x = 0; x < v; x++) {
@@ -55,7 +55,7 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         for (int r = 0; r < o; r++)
             for (int y = 0; y < v; y++)
                 for (int z = 0; z < v; z++)
-                    OV2[(((i64)q * o + r) * v + y) * v + z] = OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))];
+                    OV2[ov2_idx(P, q, r, y, z)] = OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))];
     for (int p = 0; p < o; p++)
         for (int x = 0; x < v; x++) T1d[(i64)p * v + x] = T1[p + (i64)o * x];
     P.Pt = Pt.data(); P.Qt = Qt.data(); P.OV2 = OV2.data(); P.T1d = T1d.data(); P.fo = fo; P.fv = fv;
