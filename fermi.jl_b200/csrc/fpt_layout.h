@@ -288,6 +288,15 @@ FPT_HD i64 ov2_elems(const Problem& P) { return (i64)P.o * P.o * P.nt * P.nt * 2
 
 FPT_HD int occ_pick(const ItemDesc& it, int pos) { return pos == 0 ? it.i : (pos == 1 ? it.j : it.k); }
 
+// The GEMMs of an item come in triples (same operand tiles, p = i, j, k).  For i == j the p = j GEMM has exactly the
+// operands of the p = i one (P_i = P_j, Q_jk = Q_ik, Q_kj = Q_ki), for j == k the p = k GEMM repeats the p = j one: such
+// a GEMM is not recomputed, the accumulators of its twin are added a second time at the twin's destinations.
+FPT_HD bool gemm_is_dup(const ItemDesc& it, int g)
+{
+    const int pi = g % 3;
+    return (pi == 1 && it.i == it.j) || (pi == 2 && it.j == it.k);
+}
+
 // Same decode without the prefix table: the number of non-zero-weight triplets before pair (i,j) is
 // T(i,j) = i(i+1)(i+2)/6 - i + j(j+1)/2, and item = nb*T(i,j) + block*nk + k.
 FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block)
@@ -387,36 +396,50 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     const double Dbc = P.fo[i] + P.fo[j] + P.fo[k] - P.fv[b] - P.fv[c];
     const double wijk = (double)(2 - (i == j) - (j == k));
     const int se = bd.slot_elems;
-    const double* W0 = Wsm + bd.slot_of_perm[0] * se;
-    const double* W1 = Wsm + bd.slot_of_perm[1] * se;
-    const double* W2 = Wsm + bd.slot_of_perm[2] * se;
-    const double* W3 = Wsm + bd.slot_of_perm[3] * se;
-    const double* W4 = Wsm + bd.slot_of_perm[4] * se;
-    const double* W5 = Wsm + bd.slot_of_perm[5] * se;
+    const int s0 = bd.slot_of_perm[0] * se, s1 = bd.slot_of_perm[1] * se, s2 = bd.slot_of_perm[2] * se;
+    const int s3 = bd.slot_of_perm[3] * se, s4 = bd.slot_of_perm[4] * se, s5 = bd.slot_of_perm[5] * se;
     double e = 0.0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
     for (int al = al_begin; al < al_end; al++) {
         const int a = a0 + al;
         const int ab = ab0 + (al << 4), ac = ac0 + (al << 4);
-        const double jk_ab = ovjk[ab], jk_ba = ovkj[ab], ik_ab = ovik[ab], ik_ba = ovki[ab], ij_ab = ovij[ab], ij_ba = ovji[ab];
-        const double jk_ac = ovjk[ac], jk_ca = ovkj[ac], ik_ac = ovik[ac], ik_ca = ovki[ac], ij_ac = ovij[ac], ij_ca = ovji[ac];
+        const double w0 = Wsm[s0 + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
+        const double w1 = Wsm[s1 + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
+        const double w2 = Wsm[s2 + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
+        const double w3 = Wsm[s3 + slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
+        const double w4 = Wsm[s4 + slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
+        const double w5 = Wsm[s5 + slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
+        // V = W + D with D the disconnected term (ijk.jl:116); every product t1*g is consumed as soon as it is formed:
+        //   X = sum_m W_m V_m = Xw + Xd,  Y = V0+V3+V4 = Ye + Yd,  Z = V1+V2+V5 = Zo + Zd
+        const double Ye = w0 + w3 + w4, Zo = w1 + w2 + w5;
+        double X = w0 * w0 + w1 * w1 + w2 * w2 + w3 * w3 + w4 * w4 + w5 * w5;
+        double Yd, Zd, p;
         const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];
-        double w[6], vv[6];
-        w[0] = W0[slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
-        w[1] = W1[slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
-        w[2] = W2[slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
-        w[3] = W3[slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
-        w[4] = W4[slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
-        w[5] = W5[slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
-        vv[0] = w[0] + t1i_a * jk_bc + ik_ac * t1j_b + ij_ab * t1k_c;
-        vv[1] = w[1] + t1i_a * jk_cb + ik_ab * t1j_c + ij_ac * t1k_b;
-        vv[2] = w[2] + t1i_b * jk_ac + ik_bc * t1j_a + ij_ba * t1k_c;
-        vv[3] = w[3] + t1i_b * jk_ca + ik_ba * t1j_c + ij_bc * t1k_a;
-        vv[4] = w[4] + t1i_c * jk_ab + ik_cb * t1j_a + ij_ca * t1k_b;
-        vv[5] = w[5] + t1i_c * jk_ba + ik_ca * t1j_b + ij_cb * t1k_a;
-        e += point_energy(w, vv, Dbc - P.fv[a], a, b, c, wijk);
+        // D0 = t1i_a jk_bc + ik_ac t1j_b + ij_ab t1k_c
+#if defined(__CUDA_ARCH__)
+        if (P.dbg_flags & 4) {   // timing experiment: no per-a OV2 loads
+            p = t1i_a * jk_bc + ik_bc * t1j_b + ij_bc * t1k_c; Yd = p; Zd = p; X += (w0 + w1 + w2 + w3 + w4 + w5) * p;
+            const double Y = Ye + Yd, Z = Zo + Zd;
+            const double Ef = (Y - 2.0 * Z) * Ye + (Z - 2.0 * Y) * Zo + 3.0 * X;
+            const double den = (Dbc - P.fv[a]) * (double)(1 + (a == b) + (b == c));
+            e += (P.dbg_flags & 8) ? Ef * wijk * den : Ef * wijk / den;
+            continue;
+        }
+#endif
+        p = t1i_a * jk_bc + ovik[ac] * t1j_b + ovij[ab] * t1k_c;  Yd = p;  X += w0 * p;
+        // D1 = t1i_a jk_cb + ik_ab t1j_c + ij_ac t1k_b
+        p = t1i_a * jk_cb + ovik[ab] * t1j_c + ovij[ac] * t1k_b;  Zd = p;  X += w1 * p;
+        // D2 = t1i_b jk_ac + ik_bc t1j_a + ij_ba t1k_c
+        p = t1i_b * ovjk[ac] + ik_bc * t1j_a + ovji[ab] * t1k_c;  Zd += p; X += w2 * p;
+        // D3 = t1i_b jk_ca + ik_ba t1j_c + ij_bc t1k_a
+        p = t1i_b * ovkj[ac] + ovki[ab] * t1j_c + ij_bc * t1k_a;  Yd += p; X += w3 * p;
+        // D4 = t1i_c jk_ab + ik_cb t1j_a + ij_ca t1k_b
+        p = t1i_c * ovjk[ab] + ik_cb * t1j_a + ovji[ac] * t1k_b;  Yd += p; X += w4 * p;
+        // D5 = t1i_c jk_ba + ik_ca t1j_b + ij_cb t1k_a
+        p = t1i_c * ovkj[ab] + ovki[ac] * t1j_b + ij_cb * t1k_a;  Zd += p; X += w5 * p;
+        const double Y = Ye + Yd, Z = Zo + Zd;
+        const double Ef = (Y - 2.0 * Z) * Ye + (Z - 2.0 * Y) * Zo + 3.0 * X;                       // ijk.jl:132
+        const double den = (Dbc - P.fv[a]) * (double)(1 + (a == b) + (b == c));                   // ijk.jl:133
+        e += Ef * wijk / den;
     }
     return e;
 }

@@ -118,6 +118,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
         if (ctl->cur_item < 0) break;
         const int ngemm = ctl->ent.ngemm;
         for (int g = 0; g < ngemm; g++) {
+            if (gemm_is_dup(ctl->item, g)) continue;   // no k-loop for twin GEMMs (i == j or j == k)
             const GemmDesc& gd = ctl->ent.gemm[g];
             const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
             const int q = occ_pick(ctl->item, gd.q), r = occ_pick(ctl->item, gd.r);
@@ -303,20 +304,24 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
     gemm_kloop<MTW, NT>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane);
     if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
     const RowSet rs_cur = rs;
-    if (g + 1 < ctl->ent.ngemm) {
-        const GemmDesc& gn = ctl->ent.gemm[g + 1];
+    const bool dup_next = (g + 1 < ctl->ent.ngemm) && gemm_is_dup(ctl->item, g + 1);   // twin GEMM: same D, other destinations
+    const int gnext = g + (dup_next ? 2 : 1);
+    if (gnext < ctl->ent.ngemm) {
+        const GemmDesc& gn = ctl->ent.gemm[gnext];
         rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
     }
-    long long tw = 0;
-    if (PROF) tw = clock64();
-    if (gcount > 0) mbar_wait((uint64_t*)&tail->rmw_done, (gcount - 1) & 1);   // every warp has finished RMW(previous GEMM)
-    if (PROF) prof[6] += clock64() - tw;
-    if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(gd, rs_cur, acc, Wsm, lane);
-    else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
-    __syncwarp();
-    if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done);
-    gcount++;
+    for (int rep = 0; rep <= (dup_next ? 1 : 0); rep++) {
+        long long tw = 0;
+        if (PROF) tw = clock64();
+        if (gcount > 0) mbar_wait((uint64_t*)&tail->rmw_done, (gcount - 1) & 1);   // every warp has finished the previous RMW phase
+        if (PROF) prof[6] += clock64() - tw;
+        if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane);
+        else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
+        __syncwarp();
+        if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done);
+        gcount++;
+    }
     if (PROF) prof[3] += clock64() - t1;
 }
 
@@ -397,6 +402,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 
         for (int g = 0; g < ngemm; g++) {
+            if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
             const GemmDesc& gd = ctl->ent.gemm[g];
             const int rt_total = (gd.TX * gd.TY) >> 3;
             const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;

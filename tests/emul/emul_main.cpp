@@ -83,16 +83,22 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         for (int g = 0; g < ng; g++) { gd[g].p = occ_pick(it, gd[g].p); gd[g].q = occ_pick(it, gd[g].q); gd[g].r = occ_pick(it, gd[g].r); }
         std::fill(W.begin(), W.begin() + (size_t)bd.nslot * bd.slot_elems, 0.0);
         std::vector<int> hits((size_t)bd.nslot * bd.slot_elems, 0);
+        std::vector<double> Dbuf;   // D of the last computed GEMM, [m][s][zl]
         for (int g = 0; g < ng; g++) {
             const GemmDesc& G = gd[g];
+            const bool dup = gemm_is_dup(it, g);   // twin GEMM: the kernel reuses the accumulators instead of recomputing
+            if (!dup) Dbuf.assign((size_t)G.TX * G.TY * 2 * G.TZ, 0.0);
             for (int m = 0; m < G.TX * G.TY; m++) {
                 const int yl = m / G.TX, xl = m % G.TX;
                 const double* prow = P.Pt + pt_row(P, G.p, G.y0 + yl, G.x0 + xl);
                 for (int s = 0; s < 2; s++)
                     for (int zl = 0; zl < G.TZ; zl++) {
-                        double d = 0.0;
-                        for (int kappa = 0; kappa < P.Kp; kappa++)
-                            d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa / KGROUP, G.z0 + zl) + (kappa % KGROUP)];
+                        double& d = Dbuf[((size_t)m * 2 + s) * G.TZ + zl];
+                        if (!dup) {
+                            d = 0.0;
+                            for (int kappa = 0; kappa < P.Kp; kappa++)
+                                d += prow[kappa] * P.Qt[qt_row(P, s ? G.r : G.q, s ? G.q : G.r, kappa / KGROUP, G.z0 + zl) + (kappa % KGROUP)];
+                        }
                         const int off = gemm_dest(G, s, xl, yl, zl);
                         {   // the kernel's fast RMW addressing must agree with the reference form
                             DestIter di;
