@@ -1,0 +1,369 @@
+"""CPU ORACLE SUPPORT (test infrastructure, NOT product code) -- a minimal RHF + CCSD for water/STO-3G.
+
+Purpose: pin the (T) oracle on a known answer the reference itself printed.  examples/Juliacon2022.ipynb:461-476 runs
+`@energy ccsd(t)` for water / STO-3G / `df false` and prints (lines 497-615)
+    Nuclear repulsion 8.8880641743, CCSD correlation -0.0537066985, CCSD energy -75.0187095932,
+    Final (T) contribution -0.0000738086, CCSD(T) energy -75.0187834019.
+This script rebuilds the inputs of `RCCSDpT(ccsd, moints, alg)` for that molecule from scratch -- McMurchie-Davidson
+integrals over the STO-3G s/p Gaussians, RHF, spin-orbital CCSD (Stanton, Gauss, Watts, Bartlett, JCP 94, 4334 (1991)) --
+and writes them, in the reference's array layouts, to tests/golden/water_sto3g.npz together with the energies it found.
+tests/test_oracle_kat.py then feeds the stored T1/T2/integrals to the oracle and compares E(T) with the reference's print.
+
+Run from the repo root (about a minute of pure-Python integrals):  python oracle/mini_ccsd.py
+"""
+from __future__ import annotations
+
+import itertools
+import math
+import os
+import sys
+
+import numpy as np
+from scipy.special import hyp1f1
+
+BOHR_TO_ANGSTROM = 0.529177210903  # src/Backend/PhysicalConstants.jl:38
+
+# geometry of examples/Juliacon2022.ipynb:467-471 (Angstrom)
+GEOM = [("O", (1.2091536548, 1.7664118189, -0.0171613972)),
+        ("H", (2.1984800075, 1.7977100627, 0.0121161719)),
+        ("H", (0.9197881882, 2.4580185570, 0.6297938830))]
+Z = {"H": 1, "O": 8}
+
+# STO-3G (Basis Set Exchange), shells as (l, exponents, coefficients)
+STO3G = {
+    "H": [(0, [0.3425250914e+01, 0.6239137298e+00, 0.1688554040e+00], [0.1543289673e+00, 0.5353281423e+00, 0.4446345422e+00])],
+    "O": [(0, [0.1307093214e+03, 0.2380886605e+02, 0.6443608313e+01], [0.1543289673e+00, 0.5353281423e+00, 0.4446345422e+00]),
+          (0, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [-0.9996722919e-01, 0.3995128261e+00, 0.7001154689e+00]),
+          (1, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [0.1559162750e+00, 0.6076837186e+00, 0.3919573931e+00])],
+}
+
+
+def dfact(n):
+    return 1 if n <= 0 else n * dfact(n - 2)
+
+
+class BF:
+    """contracted cartesian Gaussian"""
+
+    def __init__(self, origin, lmn, exps, coefs):
+        self.o = np.array(origin, float)
+        self.lmn = lmn
+        self.exps = list(exps)
+        l, m, n = lmn
+        self.norm = [(2 * a / math.pi) ** 0.75 * (4 * a) ** ((l + m + n) / 2) / math.sqrt(dfact(2 * l - 1) * dfact(2 * m - 1) * dfact(2 * n - 1))
+                     for a in exps]
+        self.coefs = list(coefs)
+        # normalise the contraction
+        s = 0.0
+        for a, ca, na in zip(exps, coefs, self.norm):
+            for b, cb, nb in zip(exps, coefs, self.norm):
+                s += ca * cb * na * nb * overlap_prim(a, lmn, self.o, b, lmn, self.o)
+        self.coefs = [c / math.sqrt(s) for c in coefs]
+
+
+def E(i, j, t, Qx, a, b):
+    p = a + b
+    q = a * b / p
+    if t < 0 or t > i + j:
+        return 0.0
+    if i == j == t == 0:
+        return math.exp(-q * Qx * Qx)
+    if j == 0:
+        return (1 / (2 * p)) * E(i - 1, j, t - 1, Qx, a, b) - (q * Qx / a) * E(i - 1, j, t, Qx, a, b) + (t + 1) * E(i - 1, j, t + 1, Qx, a, b)
+    return (1 / (2 * p)) * E(i, j - 1, t - 1, Qx, a, b) + (q * Qx / b) * E(i, j - 1, t, Qx, a, b) + (t + 1) * E(i, j - 1, t + 1, Qx, a, b)
+
+
+def overlap_prim(a, lmn1, A, b, lmn2, B):
+    S = 1.0
+    for x in range(3):
+        S *= E(lmn1[x], lmn2[x], 0, A[x] - B[x], a, b)
+    return S * (math.pi / (a + b)) ** 1.5
+
+
+def kinetic_prim(a, lmn1, A, b, lmn2, B):
+    l2, m2, n2 = lmn2
+    t0 = b * (2 * (l2 + m2 + n2) + 3) * overlap_prim(a, lmn1, A, b, lmn2, B)
+    t1 = -2 * b * b * (overlap_prim(a, lmn1, A, b, (l2 + 2, m2, n2), B) + overlap_prim(a, lmn1, A, b, (l2, m2 + 2, n2), B)
+                       + overlap_prim(a, lmn1, A, b, (l2, m2, n2 + 2), B))
+    t2 = -0.5 * (l2 * (l2 - 1) * overlap_prim(a, lmn1, A, b, (l2 - 2, m2, n2), B) + m2 * (m2 - 1) * overlap_prim(a, lmn1, A, b, (l2, m2 - 2, n2), B)
+                 + n2 * (n2 - 1) * overlap_prim(a, lmn1, A, b, (l2, m2, n2 - 2), B))
+    return t0 + t1 + t2
+
+
+def boys(n, x):
+    return hyp1f1(n + 0.5, n + 1.5, -x) / (2 * n + 1)
+
+
+def R(t, u, v, n, p, PC, RPC2):
+    if t < 0 or u < 0 or v < 0:
+        return 0.0
+    if t == u == v == 0:
+        return (-2 * p) ** n * boys(n, p * RPC2)
+    if t == u == 0:
+        val = PC[2] * R(t, u, v - 1, n + 1, p, PC, RPC2)
+        if v > 1:
+            val += (v - 1) * R(t, u, v - 2, n + 1, p, PC, RPC2)
+        return val
+    if t == 0:
+        val = PC[1] * R(t, u - 1, v, n + 1, p, PC, RPC2)
+        if u > 1:
+            val += (u - 1) * R(t, u - 2, v, n + 1, p, PC, RPC2)
+        return val
+    val = PC[0] * R(t - 1, u, v, n + 1, p, PC, RPC2)
+    if t > 1:
+        val += (t - 1) * R(t - 2, u, v, n + 1, p, PC, RPC2)
+    return val
+
+
+def nuclear_prim(a, lmn1, A, b, lmn2, B, C):
+    p = a + b
+    P = (a * A + b * B) / p
+    PC = P - C
+    RPC2 = float(PC @ PC)
+    val = 0.0
+    for t in range(lmn1[0] + lmn2[0] + 1):
+        for u in range(lmn1[1] + lmn2[1] + 1):
+            for v in range(lmn1[2] + lmn2[2] + 1):
+                val += (E(lmn1[0], lmn2[0], t, A[0] - B[0], a, b) * E(lmn1[1], lmn2[1], u, A[1] - B[1], a, b)
+                        * E(lmn1[2], lmn2[2], v, A[2] - B[2], a, b) * R(t, u, v, 0, p, PC, RPC2))
+    return 2 * math.pi / p * val
+
+
+def eri_prim(a, lmn1, A, b, lmn2, B, c, lmn3, C, d, lmn4, D):
+    p, q = a + b, c + d
+    alpha = p * q / (p + q)
+    P = (a * A + b * B) / p
+    Q = (c * C + d * D) / q
+    PQ = P - Q
+    RPQ2 = float(PQ @ PQ)
+    Eab = [[E(lmn1[x], lmn2[x], t, A[x] - B[x], a, b) for t in range(lmn1[x] + lmn2[x] + 1)] for x in range(3)]
+    Ecd = [[E(lmn3[x], lmn4[x], t, C[x] - D[x], c, d) for t in range(lmn3[x] + lmn4[x] + 1)] for x in range(3)]
+    val = 0.0
+    for t, et in enumerate(Eab[0]):
+        for u, eu in enumerate(Eab[1]):
+            for v, ev in enumerate(Eab[2]):
+                for tau, ft in enumerate(Ecd[0]):
+                    for nu, fu in enumerate(Ecd[1]):
+                        for phi, fv in enumerate(Ecd[2]):
+                            val += et * eu * ev * ft * fu * fv * (-1) ** (tau + nu + phi) * R(t + tau, u + nu, v + phi, 0, alpha, PQ, RPQ2)
+    return val * 2 * math.pi ** 2.5 / (p * q * math.sqrt(p + q))
+
+
+def contracted(fn, *bfs, extra=()):
+    val = 0.0
+    for idx in itertools.product(*[range(len(b.exps)) for b in bfs]):
+        c = 1.0
+        args = []
+        for b, i in zip(bfs, idx):
+            c *= b.coefs[i] * b.norm[i]
+            args += [b.exps[i], b.lmn, b.o]
+        val += c * fn(*args, *extra)
+    return val
+
+
+def build_basis():
+    bfs, atoms = [], []
+    for sym, xyz in GEOM:
+        pos = np.array(xyz) / BOHR_TO_ANGSTROM
+        atoms.append((Z[sym], pos))
+        for l, exps, coefs in STO3G[sym]:
+            for lmn in ([(0, 0, 0)] if l == 0 else [(1, 0, 0), (0, 1, 0), (0, 0, 1)]):
+                bfs.append(BF(pos, lmn, exps, coefs))
+    return bfs, atoms
+
+
+def integrals(bfs, atoms):
+    n = len(bfs)
+    S, T, V = np.zeros((n, n)), np.zeros((n, n)), np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1):
+            S[i, j] = S[j, i] = contracted(overlap_prim, bfs[i], bfs[j])
+            T[i, j] = T[j, i] = contracted(kinetic_prim, bfs[i], bfs[j])
+            v = 0.0
+            for z, pos in atoms:
+                v -= z * contracted(nuclear_prim, bfs[i], bfs[j], extra=(pos,))
+            V[i, j] = V[j, i] = v
+    ERI = np.zeros((n, n, n, n))
+    for i in range(n):
+        for j in range(i + 1):
+            for k in range(n):
+                for l in range(k + 1):
+                    if i * (i + 1) // 2 + j < k * (k + 1) // 2 + l:
+                        continue
+                    x = contracted(eri_prim, bfs[i], bfs[j], bfs[k], bfs[l])
+                    for (a, b, c, d) in ((i, j, k, l), (j, i, k, l), (i, j, l, k), (j, i, l, k), (k, l, i, j), (l, k, i, j), (k, l, j, i), (l, k, j, i)):
+                        ERI[a, b, c, d] = x
+    enuc = sum(atoms[a][0] * atoms[b][0] / np.linalg.norm(atoms[a][1] - atoms[b][1]) for a in range(len(atoms)) for b in range(a))
+    return S, T, V, ERI, enuc
+
+
+def rhf(S, H, ERI, ndocc, tol=1e-13, maxit=500):
+    w, U = np.linalg.eigh(S)
+    X = U @ np.diag(w ** -0.5) @ U.T
+    F = H.copy()
+    D = np.zeros_like(H)
+    e_old = 0.0
+    fs, es = [], []
+    for it in range(maxit):
+        Fp = X @ F @ X
+        eps, C2 = np.linalg.eigh(Fp)
+        C = X @ C2
+        Cocc = C[:, :ndocc]
+        D = Cocc @ Cocc.T
+        J = np.einsum("pqrs,rs->pq", ERI, D)
+        K = np.einsum("prqs,rs->pq", ERI, D)
+        F = H + 2 * J - K
+        e = float(np.sum(D * (H + F)))
+        # DIIS
+        err = X @ (F @ D @ S - S @ D @ F) @ X
+        fs.append(F.copy()); es.append(err)
+        fs, es = fs[-8:], es[-8:]
+        if len(fs) > 1:
+            nB = len(fs)
+            B = -np.ones((nB + 1, nB + 1)); B[-1, -1] = 0
+            for a in range(nB):
+                for b in range(nB):
+                    B[a, b] = np.sum(es[a] * es[b])
+            rhs = np.zeros(nB + 1); rhs[-1] = -1
+            try:
+                c = np.linalg.solve(B, rhs)[:-1]
+                F = sum(ci * fi for ci, fi in zip(c, fs))
+            except np.linalg.LinAlgError:
+                pass
+        if abs(e - e_old) < tol and np.max(np.abs(err)) < 1e-11:
+            break
+        e_old = e
+    Fp = X @ (H + 2 * np.einsum("pqrs,rs->pq", ERI, D) - np.einsum("prqs,rs->pq", ERI, D)) @ X
+    eps, C2 = np.linalg.eigh(Fp)
+    C = X @ C2
+    Cocc = C[:, :ndocc]
+    D = Cocc @ Cocc.T
+    Ffin = H + 2 * np.einsum("pqrs,rs->pq", ERI, D) - np.einsum("prqs,rs->pq", ERI, D)
+    return float(np.sum(D * (H + Ffin))), eps, C
+
+
+def ccsd_spinorbital(eps, MO, ndocc, tol=1e-13, maxit=200):
+    """MO: (pq|rs) chemist, spatial.  Returns correlation energy, t1, t2 (spin orbital, interleaved alpha/beta)."""
+    n = len(eps)
+    ns = 2 * n
+    sp = np.arange(ns) // 2
+    spin = np.arange(ns) % 2
+    g = MO[np.ix_(sp, sp, sp, sp)] * (spin[:, None, None, None] == spin[None, :, None, None]) * (spin[None, None, :, None] == spin[None, None, None, :])
+    phys = g.transpose(0, 2, 1, 3)          # <pq|rs> = (pr|qs)
+    A = phys - phys.transpose(0, 1, 3, 2)   # <pq||rs>
+    fs = np.repeat(eps, 2)
+    no = 2 * ndocc
+    o, v = slice(0, no), slice(no, ns)
+    fo, fv = fs[o], fs[v]
+    Dia = fo[:, None] - fv[None, :]
+    Dijab = fo[:, None, None, None] + fo[None, :, None, None] - fv[None, None, :, None] - fv[None, None, None, :]
+    t1 = np.zeros((no, ns - no))
+    t2 = A[o, o, v, v] / Dijab
+    es = np.einsum
+    e_old = 0.0
+    hist_t, hist_e = [], []
+    for it in range(maxit):
+        tau_t = t2 + 0.5 * (es("ia,jb->ijab", t1, t1) - es("ib,ja->ijab", t1, t1))
+        tau = t2 + es("ia,jb->ijab", t1, t1) - es("ib,ja->ijab", t1, t1)
+        Fae = es("mf,mafe->ae", t1, A[o, v, v, v]) - 0.5 * es("mnaf,mnef->ae", tau_t, A[o, o, v, v])
+        Fmi = es("ne,mnie->mi", t1, A[o, o, o, v]) + 0.5 * es("inef,mnef->mi", tau_t, A[o, o, v, v])
+        Fme = es("nf,mnef->me", t1, A[o, o, v, v])
+        Wmnij = A[o, o, o, o] + es("je,mnie->mnij", t1, A[o, o, o, v]) - es("ie,mnje->mnij", t1, A[o, o, o, v]) + 0.25 * es("ijef,mnef->mnij", tau, A[o, o, v, v])
+        Wabef = A[v, v, v, v] - es("mb,amef->abef", t1, A[v, o, v, v]) + es("ma,bmef->abef", t1, A[v, o, v, v]) + 0.25 * es("mnab,mnef->abef", tau, A[o, o, v, v])
+        Wmbej = (A[o, v, v, o] + es("jf,mbef->mbej", t1, A[o, v, v, v]) - es("nb,mnej->mbej", t1, A[o, o, v, o])
+                 - es("jnfb,mnef->mbej", 0.5 * t2 + es("jf,nb->jnfb", t1, t1), A[o, o, v, v]))
+        r1 = (es("ie,ae->ia", t1, Fae) - es("ma,mi->ia", t1, Fmi) + es("imae,me->ia", t2, Fme) - es("nf,naif->ia", t1, A[o, v, o, v])
+              - 0.5 * es("imef,maef->ia", t2, A[o, v, v, v]) - 0.5 * es("mnae,nmei->ia", t2, A[o, o, v, o]))
+        r2 = A[o, o, v, v].copy()
+        tmp = es("ijae,be->ijab", t2, Fae - 0.5 * es("mb,me->be", t1, Fme))
+        r2 += tmp - tmp.transpose(0, 1, 3, 2)
+        tmp = es("imab,mj->ijab", t2, Fmi + 0.5 * es("je,me->mj", t1, Fme))
+        r2 -= tmp - tmp.transpose(1, 0, 2, 3)
+        r2 += 0.5 * es("mnab,mnij->ijab", tau, Wmnij) + 0.5 * es("ijef,abef->ijab", tau, Wabef)
+        tmp = es("imae,mbej->ijab", t2, Wmbej) - es("ie,ma,mbej->ijab", t1, t1, A[o, v, v, o])
+        r2 += tmp - tmp.transpose(1, 0, 2, 3) - tmp.transpose(0, 1, 3, 2) + tmp.transpose(1, 0, 3, 2)
+        tmp = es("ie,abej->ijab", t1, A[v, v, v, o])
+        r2 += tmp - tmp.transpose(1, 0, 2, 3)
+        tmp = es("ma,mbij->ijab", t1, A[o, v, o, o])
+        r2 -= tmp - tmp.transpose(0, 1, 3, 2)
+        t1n, t2n = r1 / Dia, r2 / Dijab
+        # DIIS on the amplitudes
+        vec = np.concatenate([t1n.ravel(), t2n.ravel()])
+        err = vec - np.concatenate([t1.ravel(), t2.ravel()])
+        hist_t.append(vec); hist_e.append(err)
+        hist_t, hist_e = hist_t[-8:], hist_e[-8:]
+        if len(hist_t) > 2:
+            nB = len(hist_t)
+            B = -np.ones((nB + 1, nB + 1)); B[-1, -1] = 0
+            for a in range(nB):
+                for b in range(nB):
+                    B[a, b] = hist_e[a] @ hist_e[b]
+            rhs = np.zeros(nB + 1); rhs[-1] = -1
+            try:
+                c = np.linalg.solve(B, rhs)[:-1]
+                vec = sum(ci * ti for ci, ti in zip(c, hist_t))
+            except np.linalg.LinAlgError:
+                pass
+        t1 = vec[:t1.size].reshape(t1.shape)
+        t2 = vec[t1.size:].reshape(t2.shape)
+        e = 0.25 * es("ijab,ijab->", A[o, o, v, v], t2) + 0.5 * es("ijab,ia,jb->", A[o, o, v, v], t1, t1)
+        if abs(e - e_old) < tol and np.max(np.abs(err)) < 1e-12:
+            break
+        e_old = e
+    return float(e), t1, t2, A, fs, no
+
+
+def pt_spinorbital(t1, t2, A, fs, no):
+    """Textbook spin-orbital (T) -- an independent check of the closed-shell oracle on the molecular amplitudes."""
+    ns = len(fs)
+    o, v = slice(0, no), slice(no, ns)
+    es = np.einsum
+    fo, fv = fs[o], fs[v]
+    D = (fo[:, None, None, None, None, None] + fo[None, :, None, None, None, None] + fo[None, None, :, None, None, None]
+         - fv[None, None, None, :, None, None] - fv[None, None, None, None, :, None] - fv[None, None, None, None, None, :])
+
+    def perm(x):
+        y = x - x.transpose(1, 0, 2, 3, 4, 5) - x.transpose(2, 1, 0, 3, 4, 5)
+        return y - y.transpose(0, 1, 2, 4, 3, 5) - y.transpose(0, 1, 2, 5, 4, 3)
+
+    conn = perm(es("jkae,eibc->ijkabc", t2, A[v, o, v, v]) - es("imbc,majk->ijkabc", t2, A[o, v, o, o]))
+    disc = perm(es("ia,jkbc->ijkabc", t1, A[o, o, v, v]))
+    return float(np.sum(conn * (conn + disc) / D) / 36.0)
+
+
+def main():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bfs, atoms = build_basis()
+    S, T, V, ERI, enuc = integrals(bfs, atoms)
+    ndocc = 5
+    e_el, eps, C = rhf(S, T + V, ERI, ndocc)
+    e_rhf = e_el + enuc
+    MO = np.einsum("pqrs,pi,qj,rk,sl->ijkl", ERI, C, C, C, C, optimize=True)
+    e_cc, t1, t2, A, fs, no = ccsd_spinorbital(eps, MO, ndocc)
+    e_t_so = pt_spinorbital(t1, t2, A, fs, no)
+    o, n = ndocc, len(eps)
+    v = n - o
+    T1 = np.asfortranarray(t1[0::2, 0::2])
+    T2 = np.asfortranarray(t2[0::2, 1::2, 0::2, 1::2])
+    oc, vi = slice(0, o), slice(o, n)
+    OVVV = np.asfortranarray(MO[oc, vi, vi, vi])
+    OOOV = np.asfortranarray(MO[oc, oc, oc, vi])
+    OVOV = np.asfortranarray(MO[oc, vi, oc, vi])
+    fo, fv = eps[:o].copy(), eps[o:].copy()
+    from oracle import pt_numpy as P
+    e_t = P.pt_ijk(T1, T2, OVVV, OOOV, OVOV, fo, fv)
+    print(f"E_nuc   {enuc:.10f}   (reference print  8.8880641743)")
+    print(f"E_RHF   {e_rhf:.10f}")
+    print(f"E_corr  {e_cc:.10f}   (reference print -0.0537066985)")
+    print(f"E_CCSD  {e_rhf + e_cc:.10f}   (reference print -75.0187095932)")
+    print(f"E(T)    {e_t:.10f}   (reference print -0.0000738086)   spin-orbital formula: {e_t_so:.10f}")
+    print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}   (reference print -75.0187834019)")
+    out = os.path.join(root, "tests", "golden", "water_sto3g.npz")
+    np.savez(out, T1=T1, T2=T2, OVVV=OVVV, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t,
+             e_t_spinorbital=e_t_so)
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()
