@@ -97,8 +97,9 @@ __global__ void prep_ov2(Problem P, double* OV2, const double* __restrict__ OVOV
         const int Y = (int)(t % nt); t /= nt;
         const int r = (int)(t % o);
         const int q = (int)(t / o);
-        const int y = Y * 16 + yl, z = Z * 16 + zl;
-        OV2[idx] = (y < v && z < v) ? OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))] : 0.0;
+        const int y = tile_start(Y, P.vp) + yl, z = tile_start(Z, P.vp) + zl;
+        const bool ok = yl < tile_size(Y, P.vp) && zl < tile_size(Z, P.vp) && y < v && z < v;
+        OV2[idx] = ok ? OVOV[q + (i64)o * (y + (i64)v * (r + (i64)o * z))] : 0.0;
     }
 }
 

@@ -47,12 +47,31 @@ typedef long long i64;
 FPT_HD int roundup(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- tiles ---------------------------------------------------------------------------------------
-// vp = roundup4(v); tiles of 16 then one remainder tile (4, 8 or 12).  (A balanced split such as 116 = 5x16 + 3x12
-// was measured slower: it turns most blocks into mixed-size blocks, which take the generic addressing paths.)
+// vp = roundup4(v) is cut into nt = ceil(vp/16) tiles: 16, 16, ..., then a remainder tile of 8 or 12; a remainder of 4
+// is merged with the last full tile and re-split as 12 + 8 (a 4-wide tile makes N = 8 GEMMs that are bound by the A
+// stream).  All tile sizes are multiples of 4.
 FPT_HD int padded_v(int v) { return roundup(v, 4); }
 FPT_HD int num_tiles(int v) { return (padded_v(v) + TMAX - 1) / TMAX; }
-FPT_HD int tile_start(int t, int vp) { (void)vp; return t * TMAX; }
-FPT_HD int tile_size(int t, int vp) { int s = vp - t * TMAX; return s > TMAX ? TMAX : s; }
+FPT_HD bool split_12_8(int vp) { return (vp & 15) == 4 && vp > 16; }
+FPT_HD int tile_start(int t, int vp)
+{
+    const int nt = (vp + TMAX - 1) / TMAX;
+    if (split_12_8(vp) && t == nt - 1) return 16 * (nt - 2) + 12;
+    return t * TMAX;
+}
+FPT_HD int tile_size(int t, int vp)
+{
+    const int nt = (vp + TMAX - 1) / TMAX;
+    if (split_12_8(vp)) return t < nt - 2 ? 16 : (t == nt - 2 ? 12 : 8);
+    const int s = vp - t * TMAX;
+    return s > TMAX ? TMAX : s;
+}
+FPT_HD int tile_of(int y, int vp)
+{
+    const int nt = (vp + TMAX - 1) / TMAX;
+    if (split_12_8(vp) && y >= 16 * (nt - 2) + 12) return nt - 1;
+    return y >> 4;
+}
 
 // ---- tetrahedral / triangular decodes ----------------------------------------------------------------
 // n -> (A,B,C), A>=B>=C>=0, n = A(A+1)(A+2)/6 + B(B+1)/2 + C
@@ -82,15 +101,14 @@ FPT_HD int num_k(int i, int j) { return (i == j) ? j : j + 1; }
 // hit 16 distinct 8-byte banks (RMW epilogue of the GEMMs, and the energy stage's permuted reads).
 // For Tc == 16 the swizzle is GF(2)-linear:  lcs = lc ^ SA(la) ^ SB(lb),  SA(x) = swap the two bit pairs of x,
 // SB(x) = (x&3)*5 ^ (x>>2); linearity is what makes the per-column-tile offsets of the RMW epilogue one XOR away
-// from each other (DestIter below).  Other Tc (edge tiles 4/8/12) use an additive skew.
+// from each other (DestIter below).  Edge tiles (Tc = 4/8/12) swizzle only the low two bits of lc.
 FPT_HD int swz_a(int x) { return ((x & 3) << 2) | (x >> 2); }
 FPT_HD int swz_b(int x) { return ((x & 3) * 5) ^ (x >> 2); }
 FPT_HD int slot_index(int la, int lb, int lc, int Tb, int Tc)
 {
-    int lcs;
-    if (Tc == 16) lcs = lc ^ swz_a(la) ^ swz_b(lb);
-    else lcs = (lc + 3 * la + 4 * lb) % Tc;
-    return (la * Tb + lb) * Tc + lcs;
+    // Tc == 16: full 4-bit XOR swizzle; edge tiles (4/8/12): only the low two bits are swizzled (stays inside the tile)
+    const int mask = (Tc == 16) ? 15 : 3;
+    return (la * Tb + lb) * Tc + (lc ^ ((swz_a(la) ^ swz_b(lb)) & mask));
 }
 
 // perm m of three things, m = 0..5: (0,1,2),(0,2,1),(1,0,2),(1,2,0),(2,0,1),(2,1,0); perm3(m,c) = c-th entry
@@ -193,40 +211,28 @@ FPT_HD int gemm_dest(const GemmDesc& g, int s, int xl, int yl, int zl)
     return g.dbase[s] + slot_index(la, lb, lc, g.dTb[s], g.dTc[s]);
 }
 
-// Fast form of gemm_dest for the RMW epilogue when the destination slot has Tc == 16: for a fixed thread
-// (xl, yl, kk) the element for column tile ct (zl = 4*ct + kk) is
+// Fast form of gemm_dest for the RMW epilogue: for a fixed thread (xl, yl, kk) the element for column tile ct
+// (zl = 4*ct + kk) is
 //     off(ct) = lin0 + ct*zs + (w0 ^ (ct*d1))
-// where (zs, d1) = (0, 4) if z supplies lc, (64, 1) if z supplies lb, (64*Tb, 1) if z supplies la
-// (swz_a(4ct) = swz_b(4ct) = ct and 4ct + kk = 4ct ^ kk).
+// where (zs, d1) = (0, 4) if z supplies lc, (4*Tc, 1) if z supplies lb, (4*Tb*Tc, 1) if z supplies la
+// (swz_a(4ct) = swz_b(4ct) = ct, 4ct + kk = 4ct ^ kk, and ct < 4 only touches the low two bits).
 struct DestIter { int lin0, zs, w0, d1; };
 
-FPT_HD bool dest_iter_init(const GemmDesc& g, int s, int xl, int yl, int kk, DestIter& it)
-{
-    if (g.dTc[s] != 16) return false;
-    const int sel = g.dsel[s];
-    const int sa = sel & 3, sb = (sel >> 2) & 3, sc = (sel >> 4) & 3;
-    const int Tb = g.dTb[s];
-    const int la = pick3(sa, xl, yl, kk), lb = pick3(sb, xl, yl, kk), lc = pick3(sc, xl, yl, kk);   // ct = 0
-    it.lin0 = g.dbase[s] + (la * Tb + lb) * 16;
-    it.w0 = lc ^ swz_a(la) ^ swz_b(lb);
-    it.zs = (sc == 2) ? 0 : (sb == 2 ? 64 : 64 * Tb);
-    it.d1 = (sc == 2) ? 4 : 1;
-    return true;
-}
-// Same, with the role permutation `sel` hoisted into a (warp-uniform) switch so that no per-element selects remain.
-FPT_HD void dest_iter_init_fast(int dbase, int sel, int Tb, int xl, int yl, int kk, DestIter& it)
+// `sel` (which of x,y,z supplies la,lb,lc) is uniform per (GEMM, s): switch on it once, no per-element selects remain.
+FPT_HD void dest_iter_init_fast(int dbase, int sel, int Tb, int Tc, int xl, int yl, int kk, DestIter& it)
 {
     int la, lb, lc;
     switch (sel) {
-    case (0 | (1 << 2) | (2 << 4)): la = xl; lb = yl; lc = kk; it.zs = 0; it.d1 = 4; break;        // (x,y,z)
-    case (0 | (2 << 2) | (1 << 4)): la = xl; lb = kk; lc = yl; it.zs = 64; it.d1 = 1; break;       // (x,z,y)
-    case (1 | (0 << 2) | (2 << 4)): la = yl; lb = xl; lc = kk; it.zs = 0; it.d1 = 4; break;        // (y,x,z)
-    case (1 | (2 << 2) | (0 << 4)): la = yl; lb = kk; lc = xl; it.zs = 64; it.d1 = 1; break;       // (y,z,x)
-    case (2 | (0 << 2) | (1 << 4)): la = kk; lb = xl; lc = yl; it.zs = 64 * Tb; it.d1 = 1; break;  // (z,x,y)
-    default:                         la = kk; lb = yl; lc = xl; it.zs = 64 * Tb; it.d1 = 1; break;  // (z,y,x)
+    case (0 | (1 << 2) | (2 << 4)): la = xl; lb = yl; lc = kk; it.zs = 0; it.d1 = 4; break;            // (x,y,z)
+    case (0 | (2 << 2) | (1 << 4)): la = xl; lb = kk; lc = yl; it.zs = 4 * Tc; it.d1 = 1; break;       // (x,z,y)
+    case (1 | (0 << 2) | (2 << 4)): la = yl; lb = xl; lc = kk; it.zs = 0; it.d1 = 4; break;            // (y,x,z)
+    case (1 | (2 << 2) | (0 << 4)): la = yl; lb = kk; lc = xl; it.zs = 4 * Tc; it.d1 = 1; break;       // (y,z,x)
+    case (2 | (0 << 2) | (1 << 4)): la = kk; lb = xl; lc = yl; it.zs = 4 * Tb * Tc; it.d1 = 1; break;  // (z,x,y)
+    default:                         la = kk; lb = yl; lc = xl; it.zs = 4 * Tb * Tc; it.d1 = 1; break;  // (z,y,x)
     }
-    it.lin0 = dbase + (la * Tb + lb) * 16;
-    it.w0 = lc ^ swz_a(la) ^ swz_b(lb);
+    const int mask = (Tc == 16) ? 15 : 3;
+    it.lin0 = dbase + (la * Tb + lb) * Tc;
+    it.w0 = lc ^ ((swz_a(la) ^ swz_b(lb)) & mask);
 }
 FPT_HD int dest_iter_off(const DestIter& it, int ct) { return it.lin0 + ct * it.zs + (it.w0 ^ (ct * it.d1)); }
 
@@ -282,7 +288,8 @@ FPT_HD i64 ov2_pair_base(const Problem& P, int q, int r) { return ((i64)q * P.o 
 FPT_HD int ov2_tile_off(const Problem& P, int Y, int Z) { return (Y * P.nt + Z) * 256; }
 FPT_HD i64 ov2_idx(const Problem& P, int q, int r, int y, int z)
 {
-    return ov2_pair_base(P, q, r) + ov2_tile_off(P, y >> 4, z >> 4) + ((y & 15) << 4) + (z & 15);
+    const int Y = tile_of(y, P.vp), Z = tile_of(z, P.vp);
+    return ov2_pair_base(P, q, r) + ov2_tile_off(P, Y, Z) + ((y - tile_start(Y, P.vp)) << 4) + (z - tile_start(Z, P.vp));
 }
 FPT_HD i64 ov2_elems(const Problem& P) { return (i64)P.o * P.o * P.nt * P.nt * 256; }
 
@@ -384,7 +391,7 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     const double* ovki = P.OV2 + ov2_pair_base(P, k, i);
     const double* ovij = P.OV2 + ov2_pair_base(P, i, j);
     const double* ovji = P.OV2 + ov2_pair_base(P, j, i);
-    // tile-local offsets: the block's tiles are 16-aligned, so (y,z) in tile (Y,Z) sits at tile_off + yl*16 + zl
+    // tile-local offsets: (y,z) in tile (Y,Z) sits at tile_off + yl*16 + zl
     const int bc = ov2_tile_off(P, bd.tile[1], bd.tile[2]) + (bl << 4) + cl;
     const int ab0 = ov2_tile_off(P, bd.tile[0], bd.tile[1]) + bl;
     const int ac0 = ov2_tile_off(P, bd.tile[0], bd.tile[2]) + cl;

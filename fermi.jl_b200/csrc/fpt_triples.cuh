@@ -268,24 +268,14 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
     for (int e = 0; e < 2; e++) {
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
         if (e == 1 && gd.diag_xz) consumer_bar();
-        const int dbase = gd.dbase[e], sel = gd.dsel[e], Tb = gd.dTb[e];
-        if (gd.dTc[e] == 16) {
+        const int dbase = gd.dbase[e], sel = gd.dsel[e], Tb = gd.dTb[e], Tc = gd.dTc[e];
 #pragma unroll
-            for (int mt = 0; mt < MTW; mt++) {
-                if (mt < rs.nvalid) {
-                    DestIter it;
-                    dest_iter_init_fast(dbase, sel, Tb, xl[mt], yl[mt], kk, it);
+        for (int mt = 0; mt < MTW; mt++) {
+            if (mt < rs.nvalid) {
+                DestIter it;
+                dest_iter_init_fast(dbase, sel, Tb, Tc, xl[mt], yl[mt], kk, it);
 #pragma unroll
-                    for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int mt = 0; mt < MTW; mt++) {
-                if (mt < rs.nvalid) {
-#pragma unroll
-                    for (int ct = 0; ct < NT; ct++) Wsm[gemm_dest(gd, e, xl[mt], yl[mt], 4 * ct + kk)] += acc[mt][ct][e];
-                }
+                for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
             }
         }
     }

@@ -101,16 +101,9 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                         }
                         const int off = gemm_dest(G, s, xl, yl, zl);
                         {   // the kernel's fast RMW addressing must agree with the reference form
-                            DestIter di;
-                            if (dest_iter_init(G, s, xl, yl, zl & 3, di) && dest_iter_off(di, zl >> 2) != off) {
-                                fprintf(stderr, "dest_iter mismatch\n");
-                                return 5;
-                            }
-                            if (G.dTc[s] == 16) {
-                                DestIter df;
-                                dest_iter_init_fast(G.dbase[s], G.dsel[s], G.dTb[s], xl, yl, zl & 3, df);
-                                if (dest_iter_off(df, zl >> 2) != off) { fprintf(stderr, "dest_iter_fast mismatch\n"); return 8; }
-                            }
+                            DestIter df;
+                            dest_iter_init_fast(G.dbase[s], G.dsel[s], G.dTb[s], G.dTc[s], xl, yl, zl & 3, df);
+                            if (dest_iter_off(df, zl >> 2) != off) { fprintf(stderr, "dest_iter_fast mismatch\n"); return 8; }
                         }
                         if (off < 0 || off >= bd.nslot * bd.slot_elems) { fprintf(stderr, "dest out of range\n"); return 3; }
                         W[off] += d;
