@@ -368,9 +368,11 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));
 }
 
+// `ovs` holds the 12 OV2 tiles whose row index is a -- [(pair: jk,kj,ik,ki,ij,ji) x (column tile: B, C)][16][16] -- staged in
+// shared memory by the producer (TMA) so that the a-loop has no global loads; see ov2_stage_src.
 template <bool ALL16>
-FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
-                                    int al_begin, int al_end)
+FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm,
+                                    const double* ovs, int bl, int cl, int al_begin, int al_end)
 {
     const int TA = ALL16 ? 16 : bd.ts[0], TB = ALL16 ? 16 : bd.ts[1], TC = ALL16 ? 16 : bd.ts[2];
     const int v = P.v;
@@ -393,8 +395,8 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     const double* ovji = P.OV2 + ov2_pair_base(P, j, i);
     // tile-local offsets: (y,z) in tile (Y,Z) sits at tile_off + yl*16 + zl
     const int bc = ov2_tile_off(P, bd.tile[1], bd.tile[2]) + (bl << 4) + cl;
-    const int ab0 = ov2_tile_off(P, bd.tile[0], bd.tile[1]) + bl;
-    const int ac0 = ov2_tile_off(P, bd.tile[0], bd.tile[2]) + cl;
+    const double* sab = ovs + bl;          // tile (pair, B): [al][bl]
+    const double* sac = ovs + 256 + cl;    // tile (pair, C): [al][cl]
     const double jk_bc = ovjk[bc], jk_cb = ovkj[bc];       // (jb|kc), (jc|kb)
     const double ik_bc = ovik[bc], ik_cb = ovki[bc];       // (ib|kc), (ic|kb)
     const double ij_bc = ovij[bc], ij_cb = ovji[bc];       // (ib|jc), (ic|jb)
@@ -408,7 +410,7 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     double e = 0.0;
     for (int al = al_begin; al < al_end; al++) {
         const int a = a0 + al;
-        const int ab = ab0 + (al << 4), ac = ac0 + (al << 4);
+        const int ab = al << 4, ac = al << 4;
         const double w0 = Wsm[s0 + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
         const double w1 = Wsm[s1 + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
         const double w2 = Wsm[s2 + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
@@ -432,17 +434,17 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
             continue;
         }
 #endif
-        p = t1i_a * jk_bc + ovik[ac] * t1j_b + ovij[ab] * t1k_c;  Yd = p;  X += w0 * p;
+        p = t1i_a * jk_bc + sac[2 * 512 + ac] * t1j_b + sab[4 * 512 + ab] * t1k_c;  Yd = p;  X += w0 * p;
         // D1 = t1i_a jk_cb + ik_ab t1j_c + ij_ac t1k_b
-        p = t1i_a * jk_cb + ovik[ab] * t1j_c + ovij[ac] * t1k_b;  Zd = p;  X += w1 * p;
+        p = t1i_a * jk_cb + sab[2 * 512 + ab] * t1j_c + sac[4 * 512 + ac] * t1k_b;  Zd = p;  X += w1 * p;
         // D2 = t1i_b jk_ac + ik_bc t1j_a + ij_ba t1k_c
-        p = t1i_b * ovjk[ac] + ik_bc * t1j_a + ovji[ab] * t1k_c;  Zd += p; X += w2 * p;
+        p = t1i_b * sac[0 * 512 + ac] + ik_bc * t1j_a + sab[5 * 512 + ab] * t1k_c;  Zd += p; X += w2 * p;
         // D3 = t1i_b jk_ca + ik_ba t1j_c + ij_bc t1k_a
-        p = t1i_b * ovkj[ac] + ovki[ab] * t1j_c + ij_bc * t1k_a;  Yd += p; X += w3 * p;
+        p = t1i_b * sac[1 * 512 + ac] + sab[3 * 512 + ab] * t1j_c + ij_bc * t1k_a;  Yd += p; X += w3 * p;
         // D4 = t1i_c jk_ab + ik_cb t1j_a + ij_ca t1k_b
-        p = t1i_c * ovjk[ab] + ik_cb * t1j_a + ovji[ac] * t1k_b;  Yd += p; X += w4 * p;
+        p = t1i_c * sab[0 * 512 + ab] + ik_cb * t1j_a + sac[5 * 512 + ac] * t1k_b;  Yd += p; X += w4 * p;
         // D5 = t1i_c jk_ba + ik_ca t1j_b + ij_cb t1k_a
-        p = t1i_c * ovkj[ab] + ovki[ac] * t1j_b + ij_cb * t1k_a;  Zd += p; X += w5 * p;
+        p = t1i_c * sab[1 * 512 + ab] + sac[3 * 512 + ac] * t1j_b + ij_cb * t1k_a;  Zd += p; X += w5 * p;
         const double Y = Ye + Yd, Z = Zo + Zd;
         const double Ef = (Y - 2.0 * Z) * Ye + (Z - 2.0 * Y) * Zo + 3.0 * X;                       // ijk.jl:132
         const double den = (Dbc - P.fv[a]) * (double)(1 + (a == b) + (b == c));                   // ijk.jl:133
@@ -454,12 +456,23 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
 // Energy of the column (bl, cl) of the block for al in [al_begin, al_end): same arithmetic as block_point_energy, organised
 // so that one thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each
 // either contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
-FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int bl, int cl,
-                                  int al_begin, int al_end)
+FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm,
+                                  const double* ovs, int bl, int cl, int al_begin, int al_end)
 {
     if (bd.ts[0] == 16 && bd.ts[1] == 16 && bd.ts[2] == 16)
-        return block_column_energy_t<true>(P, bd, i, j, k, Wsm, bl, cl, al_begin, al_end);
-    return block_column_energy_t<false>(P, bd, i, j, k, Wsm, bl, cl, al_begin, al_end);
+        return block_column_energy_t<true>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end);
+    return block_column_energy_t<false>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end);
 }
+
+// Source (offset into OV2) of staged tile t = 2*pair + col, pair in (jk,kj,ik,ki,ij,ji), col 0 = tile B, 1 = tile C,
+// rows = tile A, for item (i,j,k) and block (A,B,C).
+FPT_HD i64 ov2_stage_src(const Problem& P, const ItemDesc& it, int t)
+{
+    const int pair = t >> 1, col = t & 1;
+    const int q = (pair == 0 || pair == 5) ? it.j : ((pair == 1 || pair == 3) ? it.k : it.i);
+    const int r = (pair == 0 || pair == 2) ? it.k : ((pair == 1 || pair == 4) ? it.j : it.i);
+    return ov2_pair_base(P, q, r) + ov2_tile_off(P, it.A, col ? it.C : it.B);
+}
+constexpr int OV_STAGE_TILES = 12;
 
 }  // namespace fpt

@@ -35,6 +35,7 @@ static_assert(NCTHREADS * CONSUMER_REGS + 128 * PRODUCER_REGS <= NTHREADS * LAUN
 constexpr int QSTAGES = 3;
 constexpr int QBLK = (TMAX + 1) * KGROUP + 2;      // doubles per (group, s) block: TZ rows of 16 kappa, skewed by 16 B mod 128 B
                                                    // so that the s=0 / s=1 halves of a quarter-warp hit disjoint banks
+static_assert(OV_STAGE_TILES * 256 <= QSTAGES * CHUNK_GROUPS * 2 * QBLK, "the energy stage's OV2 tiles are staged in the Q ring area");
 constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 1096 doubles = 8768 B
 constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
 constexpr int MTW_MAX = 2;
@@ -52,7 +53,7 @@ constexpr int NPROF = 16;
 
 struct SmemTail {
     Ctl ctl[2];
-    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2], rmw_done;
+    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2], rmw_done, ov_full, ov_empty;
     double red[NCWARPS];
 };
 
@@ -144,6 +145,22 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
                 mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
                 producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
             }
+        }
+        // Energy stage of this item: once the consumers have drained the ring (all stages released), its area is reused
+        // for the 12 OV2 tiles whose row index is a, so that the a-loop of the energy stage reads shared memory only.
+        {
+            int st = stage;
+            uint32_t ph = sphase;
+            for (int t = 0; t < QSTAGES; t++) {
+                mbar_wait((uint64_t*)&tail->empty[st], ph ^ 1);
+                if (++st == QSTAGES) { st = 0; ph ^= 1; }
+            }
+            uint64_t* ob = (uint64_t*)&tail->ov_full;
+            mbar_arrive_expect_tx(ob, (uint32_t)(OV_STAGE_TILES * 256 * sizeof(double)));
+#pragma unroll 1
+            for (int t = 0; t < OV_STAGE_TILES; t++)
+                tma_bulk_g2s(Qsm + t * 256, P.OV2 + ov2_stage_src(P, ctl->item, t), 256 * sizeof(double), ob);
+            mbar_wait((uint64_t*)&tail->ov_empty, n & 1);   // energy stage done: the ring may be refilled
         }
     }
 }
@@ -349,6 +366,8 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         for (int s = 0; s < QSTAGES; s++) { mbar_init((uint64_t*)&tail->full[s], 1); mbar_init((uint64_t*)&tail->empty[s], NCWARPS); }
         for (int s = 0; s < 2; s++) { mbar_init((uint64_t*)&tail->item_full[s], 1); mbar_init((uint64_t*)&tail->item_empty[s], NCWARPS); }
         mbar_init((uint64_t*)&tail->rmw_done, NCWARPS);
+        mbar_init((uint64_t*)&tail->ov_full, 1);
+        mbar_init((uint64_t*)&tail->ov_empty, NCWARPS);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -405,17 +424,21 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
             const BlockDesc& bd = ctl->ent.bd;
             const int TC = bd.ts[2];
             const int half = tid >> 8, tt = tid & 255;   // two threads per (b,c) column, 8 values of a each
+            mbar_wait((uint64_t*)&tail->ov_full, n & 1);      // the 12 a-row OV2 tiles are in the ring area
             if (!(P.dbg_flags & 2)) {
                 if (bd.slot_elems == 4096)
-                    esum += block_column_energy_t<true>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt >> 4, tt & 15,
+                    esum += block_column_energy_t<true>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, Qsm, tt >> 4, tt & 15,
                                                         half * 8, half * 8 + 8);
                 else if (tt < bd.ts[1] * TC)
-                    esum += block_column_energy_t<false>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, tt / TC, tt % TC,
+                    esum += block_column_energy_t<false>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, Qsm, tt / TC, tt % TC,
                                                          half * 8, half * 8 + 8);
             }
         }
-        consumer_bar();       // W slots and ctl[slot] may be reused
-        if (lane == 0) mbar_arrive((uint64_t*)&tail->item_empty[slot]);
+        consumer_bar();       // W slots, the staged tiles and ctl[slot] may be reused
+        if (lane == 0) {
+            mbar_arrive((uint64_t*)&tail->ov_empty);
+            mbar_arrive((uint64_t*)&tail->item_empty[slot]);
+        }
         if (PROF) prof[4] += clock64() - t0;
     }
 

@@ -113,11 +113,14 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         }
         for (size_t t = 0; t < hits.size(); t++)
             if (hits[t] != 6) { fprintf(stderr, "slot element %zu received %d contributions (want 6)\n", t, hits[t]); return 4; }
+        std::vector<double> ovs((size_t)OV_STAGE_TILES * 256);
+        for (int t = 0; t < OV_STAGE_TILES; t++)
+            for (int e = 0; e < 256; e++) ovs[(size_t)t * 256 + e] = P.OV2[ov2_stage_src(P, it, t) + e];
         double e_pt = 0.0, e_col = 0.0;
         for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
         for (int bl = 0; bl < bd.ts[1]; bl++)
-            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl, 0, 8) +
-                         block_column_energy(P, bd, it.i, it.j, it.k, W.data(), bl, cl, 8, 16);
+            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 0, 8) +
+                         block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 8, 16);
         if (std::fabs(e_pt - e_col) > 1e-13 * (1e-30 + std::fabs(e_pt)) + 1e-18) {
             fprintf(stderr, "column energy %.17g != point energy %.17g\n", e_col, e_pt);
             return 6;
