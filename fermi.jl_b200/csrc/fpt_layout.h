@@ -424,16 +424,6 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
         double Yd, Zd, p;
         const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];
         // D0 = t1i_a jk_bc + ik_ac t1j_b + ij_ab t1k_c
-#if defined(__CUDA_ARCH__)
-        if (P.dbg_flags & 4) {   // timing experiment: no per-a OV2 loads
-            p = t1i_a * jk_bc + ik_bc * t1j_b + ij_bc * t1k_c; Yd = p; Zd = p; X += (w0 + w1 + w2 + w3 + w4 + w5) * p;
-            const double Y = Ye + Yd, Z = Zo + Zd;
-            const double Ef = (Y - 2.0 * Z) * Ye + (Z - 2.0 * Y) * Zo + 3.0 * X;
-            const double den = (Dbc - P.fv[a]) * (double)(1 + (a == b) + (b == c));
-            e += (P.dbg_flags & 8) ? Ef * wijk * den : Ef * wijk / den;
-            continue;
-        }
-#endif
         p = t1i_a * jk_bc + sac[2 * 512 + ac] * t1j_b + sab[4 * 512 + ab] * t1k_c;  Yd = p;  X += w0 * p;
         // D1 = t1i_a jk_cb + ik_ab t1j_c + ij_ac t1k_b
         p = t1i_a * jk_cb + sab[2 * 512 + ab] * t1j_c + sac[4 * 512 + ac] * t1k_b;  Zd = p;  X += w1 * p;

@@ -21,7 +21,7 @@ for name, (o, v) in shapes.items():
         if best is None or st["kernel_ms"] < best["kernel_ms"]:
             best = st
     dbg = {}
-    for fl in (1, 2, 3, 4, 12):
+    for fl in (1, 2, 3):
         eng.set_debug_flags(fl)
         bt = min(eng.compute(0, -1)[1]["kernel_ms"] for _ in range(2))
         dbg[f"flags{fl}_ms"] = round(bt, 3)
