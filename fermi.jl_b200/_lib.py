@@ -76,11 +76,17 @@ def _ptr(a):
 class Engine:
     """Owns one fpt_handle (one GPU).  Thin, 1:1 over the C ABI."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device=None):
+        """device: None (current device), an int, or a list of ints (single-process multi-GPU handle)."""
         self._L = load_library()
         self._h = ctypes.c_void_p()
-        devs = (ctypes.c_int * 1)(device) if device is not None else None
-        self._check(self._L.fpt_create(1, devs, ctypes.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            devs = (ctypes.c_int * len(device))(*device)
+            n = len(device)
+        else:
+            devs = (ctypes.c_int * 1)(device) if device is not None else None
+            n = 1
+        self._check(self._L.fpt_create(n, devs, ctypes.byref(self._h)))
 
     def _check(self, rc):
         if rc != 0:

@@ -4,6 +4,8 @@
 //   src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:20-150 (reference, Julia threads)
 // No CPU fallback: every entry point fails loudly without a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -68,23 +70,62 @@ struct fpt_handle {
     bool profiling = false;
     int dbg_flags = 0;
     bool last_profiled = false;
+    // multi-GPU (single process): this handle drives devices[0]; peers[] drive the others; one NCCL clique
+    std::vector<fpt_handle*> peers;
+    std::vector<ncclComm_t> comms;   // comms[0] = this device, comms[1+k] = peers[k]
 };
 
-extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
-extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.1 (sm_100a)"; }
-
-extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
+// ---- NCCL, resolved at run time (only handles with ngpu > 1 need it) ---------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
 {
-    if (!out) return fail("fpt_create: out is NULL");
-    *out = nullptr;
-    if (ngpu != 1) return fail("fpt_create: this build drives one GPU per handle (got ngpu=%d); use one process per GPU", ngpu);
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail("multi-GPU handle: cannot load libnccl.so.2 (%s)", dlerror());
+#define FPT_SYM(field, name)                                                            \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));          \
+    if (!g_nccl.field) return fail("multi-GPU handle: libnccl lacks %s", name)
+    FPT_SYM(CommInitAll, "ncclCommInitAll");
+    FPT_SYM(CommDestroy, "ncclCommDestroy");
+    FPT_SYM(GroupStart, "ncclGroupStart");
+    FPT_SYM(GroupEnd, "ncclGroupEnd");
+    FPT_SYM(Broadcast, "ncclBroadcast");
+    FPT_SYM(AllReduce, "ncclAllReduce");
+    FPT_SYM(GetErrorString, "ncclGetErrorString");
+#undef FPT_SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NCK(call)                                                                                              \
+    do {                                                                                                       \
+        ncclResult_t r_ = (call);                                                                              \
+        if (r_ != ncclSuccess) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+static int broadcast_operands(fpt_handle* h);
+
+extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
+extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.2 (sm_100a)"; }
+
+static int create_one(int dev, fpt_handle** out)
+{
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return fail("fpt_create: no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString(e));
-    int dev = 0;
-    if (devices) dev = devices[0]; else CK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= ndev) return fail("fpt_create: device %d out of range (have %d)", dev, ndev);
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail("fpt_create: device %d out of range (have %d)", dev, ndev);
     CK(cudaSetDevice(dev));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
@@ -102,9 +143,43 @@ extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
     return 0;
 }
 
+extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
+{
+    if (!out) return fail("fpt_create: out is NULL");
+    *out = nullptr;
+    if (ngpu < 1 || ngpu > 16) return fail("fpt_create: ngpu=%d out of range", ngpu);
+    if (ngpu > 1 && !devices) return fail("fpt_create: a device list is required for ngpu > 1");
+    fpt_handle* h = nullptr;
+    if (create_one(devices ? devices[0] : -1, &h)) return 1;
+    if (ngpu > 1) {
+        // single-process multi-GPU: one NCCL clique over NVLink, operands broadcast once per upload, one scalar all-reduce
+        if (nccl_load()) { fpt_destroy(h); return 1; }
+        for (int k = 1; k < ngpu; k++) {
+            fpt_handle* p = nullptr;
+            if (create_one(devices[k], &p)) { fpt_destroy(h); return 1; }
+            h->peers.push_back(p);
+        }
+        h->comms.resize(ngpu);
+        ncclResult_t r = g_nccl.CommInitAll(h->comms.data(), ngpu, devices);
+        if (r != ncclSuccess) {
+            h->comms.clear();
+            fail("ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+            fpt_destroy(h);
+            return 1;
+        }
+        CK(cudaSetDevice(h->dev));
+    }
+    *out = h;
+    return 0;
+}
+
 extern "C" int fpt_destroy(fpt_handle* h)
 {
     if (!h) return 0;
+    for (ncclComm_t c : h->comms) g_nccl.CommDestroy(c);
+    h->comms.clear();
+    for (fpt_handle* p : h->peers) fpt_destroy(p);
+    h->peers.clear();
     cudaSetDevice(h->dev);
     DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof, &h->blocktab,
                       &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
@@ -254,6 +329,7 @@ extern "C" int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, co
     }
     CK(cudaStreamSynchronize(h->stream));
     h->loaded = true;
+    if (!h->peers.empty() && broadcast_operands(h)) return 1;
     h->last = fpt_stats{};
     h->last.h2d_bytes = h2d;
     h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -305,6 +381,7 @@ extern "C" int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     h->loaded = true;
+    if (!h->peers.empty() && broadcast_operands(h)) return 1;
     h->last = fpt_stats{};
     h->last.h2d_bytes = h2d;
     h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -319,15 +396,11 @@ extern "C" int fpt_num_items(fpt_handle* h, long long* n)
     return 0;
 }
 
-extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et, fpt_stats* st)
+// launch the fused kernel + reduction for [item_begin, item_end) on h's device (asynchronous; result in h->out)
+static int compute_launch(fpt_handle* h, i64 item_begin, i64 item_end)
 {
-    if (!h || !Et) return fail("fpt_compute: NULL argument");
-    if (!h->loaded) return fail("fpt_compute: no problem uploaded");
     CK(cudaSetDevice(h->dev));
     const Problem& P = h->prob;
-    if (item_end < 0 || item_end > P.nitems) item_end = P.nitems;
-    if (item_begin < 0) item_begin = 0;
-    if (item_begin > item_end) item_begin = item_end;
     const i64 n = item_end - item_begin;
     int grid = h->n_sm;
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
@@ -345,20 +418,84 @@ extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_e
     CK(cudaEventRecord(h->ev1, h->stream));
     reduce_partials<<<1, 32, 0, h->stream>>>(h->partials.d(), grid, h->out.d());
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et, fpt_stats* st)
+{
+    if (!h || !Et) return fail("fpt_compute: NULL argument");
+    if (!h->loaded) return fail("fpt_compute: no problem uploaded");
+    const Problem& P = h->prob;
+    if (item_end < 0 || item_end > P.nitems) item_end = P.nitems;
+    if (item_begin < 0) item_begin = 0;
+    if (item_begin > item_end) item_begin = item_end;
+    const i64 n = item_end - item_begin;
+    const int ng = 1 + (int)h->peers.size();
+    std::vector<fpt_handle*> hs(1, h);
+    for (fpt_handle* p : h->peers) hs.push_back(p);
+    // static contiguous shards of the range, one per GPU (equal item counts)
+    for (int d = 0; d < ng; d++) {
+        hs[d]->profiling = h->profiling;
+        if (compute_launch(hs[d], item_begin + n * d / ng, item_begin + n * (d + 1) / ng)) return 1;
+    }
+    if (ng > 1) {   // the single scalar all-reduce of E(T)
+        NCK(g_nccl.GroupStart());
+        for (int d = 0; d < ng; d++)
+            NCK(g_nccl.AllReduce(hs[d]->out.p, hs[d]->out.p, 1, ncclDouble, ncclSum, h->comms[d], hs[d]->stream));
+        NCK(g_nccl.GroupEnd());
+    }
     double e = 0.0;
+    float ms_max = 0.f;
+    CK(cudaSetDevice(h->dev));
     CK(cudaMemcpyAsync(&e, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    for (int d = 0; d < ng; d++) {
+        CK(cudaSetDevice(hs[d]->dev));
+        CK(cudaStreamSynchronize(hs[d]->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, hs[d]->ev0, hs[d]->ev1));
+        if (ms > ms_max) ms_max = ms;
+    }
+    CK(cudaSetDevice(h->dev));
     *Et = e;
     const double ntrip = (double)P.o * (P.o + 1) * (P.o + 2) / 6.0 - P.o;
-    h->last.kernel_ms = ms;
+    h->last.kernel_ms = ms_max;
     h->last.n_items = n;
     h->last.n_triplets = (long long)ntrip;
     h->last.flops = 12.0 * P.v * (double)P.v * P.v * (P.v + P.o) * ntrip * (P.nitems ? (double)n / (double)P.nitems : 0.0);
-    h->last.n_launches = h->launches + 2;
+    h->last.n_launches = h->launches + 2 * ng;
     h->last.n_sm = h->n_sm;
     if (st) *st = h->last;
+    return 0;
+}
+
+// multi-GPU handle: make the prepared operands resident on every peer (one NCCL broadcast per buffer, root = device 0)
+static int broadcast_operands(fpt_handle* h)
+{
+    const Problem& P = h->prob;
+    const int ng = 1 + (int)h->peers.size();
+    for (fpt_handle* p : h->peers) {
+        CK(cudaSetDevice(p->dev));
+        p->dbg_flags = h->dbg_flags;
+        p->loaded = false;
+        if (setup_problem(p, P.o, P.v)) return 1;
+    }
+    const size_t counts[6] = {(size_t)P.o * P.vp * P.vp * P.Kp, (size_t)P.o * P.o * P.G * P.vp * KGROUP, (size_t)ov2_elems(P),
+                              (size_t)P.o * P.v, (size_t)P.o, (size_t)P.v};
+    NCK(g_nccl.GroupStart());
+    for (int d = 0; d < ng; d++) {
+        fpt_handle* hd = d ? h->peers[d - 1] : h;
+        void* bufs[6] = {hd->Pt.p, hd->Qt.p, hd->OV2.p, hd->T1d.p, hd->fo.p, hd->fv.p};
+        for (int b = 0; b < 6; b++)
+            NCK(g_nccl.Broadcast(bufs[b], bufs[b], counts[b], ncclDouble, 0, h->comms[d], hd->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    for (int d = 0; d < ng; d++) {
+        fpt_handle* hd = d ? h->peers[d - 1] : h;
+        CK(cudaSetDevice(hd->dev));
+        CK(cudaStreamSynchronize(hd->stream));
+        hd->loaded = true;
+    }
+    CK(cudaSetDevice(h->dev));
     return 0;
 }
 

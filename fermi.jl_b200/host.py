@@ -101,7 +101,7 @@ _ENGINES: dict = {}
 
 
 def _engine(device=None) -> Engine:
-    key = device
+    key = tuple(device) if isinstance(device, (list, tuple)) else device
     if key not in _ENGINES:
         _ENGINES[key] = Engine(device)
     return _ENGINES[key]

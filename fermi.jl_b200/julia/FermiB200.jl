@@ -36,7 +36,10 @@ const HANDLE = Ref{Ptr{Cvoid}}(C_NULL)
 function handle()
     if HANDLE[] == C_NULL
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:fpt_create, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), 1, C_NULL, h)
+        # FERMI_PT_B200_NGPU=8 -> one handle driving GPUs 0..7 (NCCL broadcast of the operands, one scalar all-reduce)
+        ngpu = parse(Int, get(ENV, "FERMI_PT_B200_NGPU", "1"))
+        devs = Cint.(collect(0:ngpu-1))
+        rc = ccall((:fpt_create, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), ngpu, devs, h)
         rc == 0 || throw(FermiException(unsafe_string(ccall((:fpt_last_error, LIB), Cstring, ()))))
         HANDLE[] = h[]
         atexit(() -> ccall((:fpt_destroy, LIB), Cint, (Ptr{Cvoid},), HANDLE[]))

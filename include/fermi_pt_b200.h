@@ -47,8 +47,11 @@ typedef struct fpt_stats {
     int n_sm;              /* SMs of the device */
 } fpt_stats;
 
-/* ngpu must be 1 in this build (multi-GPU runs use one process per GPU, see fpt_compute's item ranges).
- * devices[0] = CUDA device ordinal (NULL -> current device). */
+/* ngpu = 1: devices[0] = CUDA device ordinal (devices == NULL -> current device).
+ * ngpu > 1 (single-process multi-GPU, what a Julia caller uses): devices[0..ngpu) form one NCCL clique (libnccl.so.2 is
+ * loaded at run time); every upload prepares the operands on devices[0] and broadcasts them once over NVLink, every
+ * compute splits its item range into ngpu contiguous shards and ends with one scalar all-reduce of E(T).
+ * Multi-process runs (one process per GPU, torchrun) use ngpu = 1 handles and fpt_compute's item ranges instead. */
 int fpt_create(int ngpu, const int* devices, fpt_handle** out);
 int fpt_destroy(fpt_handle* h);
 
