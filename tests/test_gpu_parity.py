@@ -104,3 +104,65 @@ def test_single_process_multi_gpu_handle(built):
     e2, _ = eng.triples_df(6, 37, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
     assert abs(e2 - ref) < TOL, (e2, ref)
     eng.close()
+
+
+@pytest.mark.parametrize("o,v", [(7, 5), (6, 6), (12, 20), (9, 31), (4, 44), (3, 68)])
+def test_more_shapes(engine, o, v):
+    """occupied > virtual, square, many (i,j) pairs, 12+8 edge split (v=44 -> vp=44: 16,16,12; v=68 -> vp=68: 16x3,12,8)."""
+    x = fb.synth.make_inputs(o, v, naux=11, seed=1000 + o * v)
+    ref = oracle.pt_gemm(*_args(x))
+    e, _ = engine.triples_conv(o, v, *_args(x))
+    assert abs(e - ref) < TOL, (e, ref)
+
+
+def test_handle_reuse_across_shapes_and_layouts(engine):
+    """gradient_findif-style reuse: the same handle serves many calls (FiniteDifferences.jl:48-74 makes 6N of them);
+    C-ordered / non-contiguous numpy inputs are accepted (the wrapper hands over column-major copies)."""
+    for o, v, seed in [(3, 9, 1), (5, 23, 2), (2, 17, 3), (5, 23, 2)]:
+        x = fb.synth.make_inputs(o, v, naux=7, seed=seed)
+        ref = oracle.pt_gemm(*_args(x))
+        c_ordered = [np.ascontiguousarray(a) for a in _args(x)]
+        e, _ = engine.triples_conv(o, v, *c_ordered)
+        assert abs(e - ref) < TOL
+    big = np.zeros((4, 4, 8, 8))
+    x = fb.synth.make_inputs(2, 4, naux=5, seed=9)
+    big[::2, ::2, ::2, ::2] = x.T2
+    view = big[::2, ::2, ::2, ::2]
+    e, _ = engine.triples_conv(2, 4, x.T1, view, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+    assert abs(e - oracle.pt_naive(*_args(x))) < TOL
+
+
+def test_random_item_ranges_add_up(engine):
+    o, v = 6, 29
+    x = fb.synth.make_inputs(o, v, naux=9, seed=77)
+    engine.upload_conv(o, v, *_args(x))
+    n = engine.num_items()
+    full, _ = engine.compute(0, -1)
+    rng = np.random.default_rng(5)
+    cuts = sorted(set([0, n] + list(rng.integers(0, n, 7))))
+    parts = [engine.compute(int(cuts[t]), int(cuts[t + 1]))[0] for t in range(len(cuts) - 1)]
+    assert abs(sum(parts) - full) < 1e-13
+    assert abs(full - oracle.pt_gemm(*_args(x))) < TOL
+    assert engine.compute(5, 5)[0] == 0.0
+
+
+def test_error_paths(engine):
+    x = fb.synth.make_inputs(2, 3, naux=3, seed=1)
+    with pytest.raises(fb.FermiException):
+        engine.triples_conv(0, 3, *_args(x))
+    with pytest.raises(fb.FermiException):
+        engine.triples_df(2, 3, 0, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+    eng2 = fb.Engine(0)
+    with pytest.raises(fb.FermiException):
+        eng2.compute(0, -1)          # nothing uploaded
+    with pytest.raises(fb.FermiException):
+        fb.Engine(99)                # no such device
+    eng2.close()
+
+
+def test_df_odd_aux_sizes(engine):
+    for naux in (1, 5, 37):
+        x = fb.synth.make_inputs(3, 13, naux=naux, seed=naux)
+        ref = oracle.pt_gemm(*_args(x))
+        e, _ = engine.triples_df(3, 13, naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+        assert abs(e - ref) < TOL, (naux, e, ref)
