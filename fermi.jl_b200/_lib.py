@@ -145,11 +145,12 @@ class Engine:
         self._check(self._L.fpt_set_profiling(self._h, 1 if on else 0))
 
     def last_profile(self):
-        buf = (ctypes.c_double * 16)()
+        buf = (ctypes.c_double * 24)()
         self._check(self._L.fpt_last_profile(self._h, buf))
-        names = ["wait_item", "zero", "kloops", "rmw", "energy", "total", "token_wait", "_"]
-        out = dict(zip(names, list(buf)[:8]))
-        out.update({"g3_" + k: v for k, v in zip(names, list(buf)[8:])})
+        names = ["wait_item", "zero", "kloops", "rmw", "energy", "total", "token_wait", "rmw_pure", "full_wait", "ov_wait",
+                 "bar_pre_energy", "bar_post_energy"]
+        out = dict(zip(names, list(buf)[:12]))
+        out.update({"g3_" + k: v for k, v in zip(names, list(buf)[12:])})
         return out
 
     def dmma_sweep(self, ilp: int, warps_per_sm: int) -> float:

@@ -49,7 +49,7 @@ struct Ctl {
     BlockTabEntry ent;     // bd, ngemm, gemm[] -- copied from the device block table by TMA; gemm[].p/q/r are positions in (i,j,k)
 };
 static_assert(sizeof(Ctl) % 16 == 0 && offsetof(Ctl, ent) % 16 == 0, "Ctl::ent is a TMA bulk-copy destination");
-constexpr int NPROF = 16;
+constexpr int NPROF = 24;   // 12 phase counters for each of two observer warps
 
 struct SmemTail {
     Ctl ctl[2];
@@ -211,10 +211,10 @@ __device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, d
 // consumer: k-loop of one GEMM.  acc[mt][ct][e]: row tile mt, column tile ct, D element e.
 // Column n of tile ct is (zl = 4ct + (n>>1), s = n&1), so a lane's two D elements are (zl = 4ct + kk, s = e).
 // ---------------------------------------------------------------------------------------------------
-template <int MTW, int NT>
+template <int MTW, int NT, bool PROF>
 __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
                                            double (&acc)[MTW][NT][2], const double* Qsm, SmemTail* tail, int& stage,
-                                           uint32_t& sphase, int lane)
+                                           uint32_t& sphase, int lane, long long* prof)
 {
     const int kk = lane & 3, n = lane >> 2;
     const int boff = ((n & 1) * QBLK) + (n >> 1) * KGROUP + 4 * kk;   // s block + row zl(ct=0) + this lane's 4 kappa
@@ -227,7 +227,10 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
     for (int c = 0; c < nchunks; c++) {
         const int g0 = c * CHUNK_GROUPS;
         const int ng = min(CHUNK_GROUPS, P.G - g0);
+        long long tf = 0;
+        if (PROF) tf = clock64();
         mbar_wait((uint64_t*)&tail->full[stage], sphase);
+        if (PROF) prof[8] += clock64() - tf;
         const double* st = Qsm + stage * QSTAGE_DOUBLES + boff;
         int nstage = stage + 1;
         uint32_t nphase = sphase;
@@ -308,7 +311,7 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
     double acc[MTW][NT][2];
     long long t0 = 0, t1 = 0;
     if (PROF) t0 = clock64();
-    gemm_kloop<MTW, NT>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane);
+    gemm_kloop<MTW, NT, PROF>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
     if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
     const RowSet rs_cur = rs;
     const bool dup_next = (g + 1 < ctl->ent.ngemm) && gemm_is_dup(ctl->item, g + 1);   // twin GEMM: same D, other destinations
@@ -322,10 +325,11 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
         long long tw = 0;
         if (PROF) tw = clock64();
         if (gcount > 0) mbar_wait((uint64_t*)&tail->rmw_done, (gcount - 1) & 1);   // every warp has finished the previous RMW phase
-        if (PROF) prof[6] += clock64() - tw;
+        if (PROF) { const long long t2 = clock64(); prof[6] += t2 - tw; tw = t2; }
         if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane);
         else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
         __syncwarp();
+        if (PROF) prof[7] += clock64() - tw;
         if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done);
         gcount++;
     }
@@ -381,7 +385,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     setmaxnreg_inc<CONSUMER_REGS>();
 
     // ------------------------------- consumers -------------------------------
-    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_start = 0;
     if (PROF) t_start = clock64();
     double esum = 0.0;
@@ -418,13 +422,15 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
             const int nt = gd.TZ >> 2;
             FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
         }
+        if (PROF) t1 = clock64();
         consumer_bar();
-        if (PROF) t0 = clock64();
+        if (PROF) { t0 = clock64(); prof[10] += t0 - t1; }
         {
             const BlockDesc& bd = ctl->ent.bd;
             const int TC = bd.ts[2];
             const int half = tid >> 8, tt = tid & 255;   // two threads per (b,c) column, 8 values of a each
             mbar_wait((uint64_t*)&tail->ov_full, n & 1);      // the 12 a-row OV2 tiles are in the ring area
+            if (PROF) prof[9] += clock64() - t0;
             if (!(P.dbg_flags & 2)) {
                 if (bd.slot_elems == 4096)
                     esum += block_column_energy_t<true>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, Qsm, tt >> 4, tt & 15,
@@ -434,7 +440,9 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
                                                          half * 8, half * 8 + 8);
             }
         }
+        if (PROF) t1 = clock64();
         consumer_bar();       // W slots, the staged tiles and ctl[slot] may be reused
+        if (PROF) prof[11] += clock64() - t1;
         if (lane == 0) {
             mbar_arrive((uint64_t*)&tail->ov_empty);
             mbar_arrive((uint64_t*)&tail->item_empty[slot]);
@@ -454,7 +462,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     }
     if (PROF && lane == 0 && (warp == 0 || warp == NCWARPS - 4)) {   // group 0's and group 3's view
         prof[5] = clock64() - t_start;
-        for (int t = 0; t < 8; t++) prof_out[blockIdx.x * NPROF + (warp ? 8 : 0) + t] = prof[t];
+        for (int t = 0; t < 12; t++) prof_out[blockIdx.x * NPROF + (warp ? 12 : 0) + t] = prof[t];
     }
 }
 

@@ -82,11 +82,12 @@ int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
 
 /* Diagnostics (not part of the drop-in path): with profiling on, fpt_compute runs the instrumented kernel variant and
  * fpt_last_profile returns its phase breakdown in SM cycles summed over CTAs (warp 0's view) --
- * out16 = {wait-for-item, zero, k-loops, RMW epilogues (+token wait, next-GEMM prologue), energy stage, total, token wait, -}
- * for the first warp of consumer group 0 (entries 0-7) and of group 3 (entries 8-15); and a DMMA issue study. */
+ * out24 = {wait-for-item, zero, k-loops, RMW epilogues (+token wait, next-GEMM prologue), energy stage, total, token wait,
+ *          pure RMW, wait on the Q ring inside the k-loops, wait for the staged OV2 tiles, barrier before / after the energy stage}
+ * for the first warp of consumer group 0 (entries 0-11) and of group 3 (entries 12-23); and a DMMA issue study. */
 int fpt_set_profiling(fpt_handle* h, int on);
 int fpt_set_debug_flags(fpt_handle* h, int flags);   /* 1: skip RMW, 2: skip energy stage -- timing studies only, E(T) is wrong */
-int fpt_last_profile(fpt_handle* h, double* out16);
+int fpt_last_profile(fpt_handle* h, double* out24);
 int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops);
 
 const char* fpt_last_error(void);

@@ -9,7 +9,11 @@ integrals over the STO-3G s/p Gaussians, RHF, spin-orbital CCSD (Stanton, Gauss,
 and writes them, in the reference's array layouts, to tests/golden/water_sto3g.npz together with the energies it found.
 tests/test_oracle_kat.py then feeds the stored T1/T2/integrals to the oracle and compares E(T) with the reference's print.
 
-Run from the repo root (about a minute of pure-Python integrals):  python oracle/mini_ccsd.py
+A second case pins it on a value the reference's own test suite asserts: water / 6-31G / df false, `@energy ccsd(t)` total
+-76.121147867765558 (test/test_pT.jl:69-72, rtol 2e-8) -> tests/golden/water_631g.npz.
+
+Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g):
+    python oracle/mini_ccsd.py [sto-3g|6-31g]
 """
 from __future__ import annotations
 
@@ -36,6 +40,25 @@ STO3G = {
           (0, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [-0.9996722919e-01, 0.3995128261e+00, 0.7001154689e+00]),
           (1, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [0.1559162750e+00, 0.6076837186e+00, 0.3919573931e+00])],
 }
+
+
+# 6-31G (Basis Set Exchange; Hehre, Ditchfield, Pople JCP 56, 2257 (1972)); the SP shells are written out as an s and a p shell
+B631G = {
+    "H": [(0, [18.7311370, 2.8253937, 0.6401217], [0.03349460, 0.23472695, 0.81375733]),
+          (0, [0.1612778], [1.0])],
+    "O": [(0, [5484.6717000, 825.2349500, 188.0469600, 52.9645000, 16.8975700, 5.7996353],
+              [0.0018311, 0.0139501, 0.0684451, 0.2327143, 0.4701930, 0.3585209]),
+          (0, [15.5396160, 3.5999336, 1.0137618], [-0.1107775, -0.1480263, 1.1307670]),
+          (1, [15.5396160, 3.5999336, 1.0137618], [0.0708743, 0.3397528, 0.7271586]),
+          (0, [0.2700058], [1.0]),
+          (1, [0.2700058], [1.0])],
+}
+BASES = {"sto-3g": STO3G, "6-31g": B631G}
+# What the reference holds for each case: the printed run of examples/Juliacon2022.ipynb:497-615 (STO-3G) and the Psi4 total
+# energy its own test asserts for `@energy ccsd(t)`, water / 6-31G / df false (test/test_pT.jl:69-72, rtol 2e-8).
+REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd": -75.0187095932, "e_t": -0.0000738086,
+                        "e_ccsd_t": -75.0187834019},
+             "6-31g": {"e_ccsd_t": -76.121147867765558}}
 
 
 def dfact(n):
@@ -161,12 +184,12 @@ def contracted(fn, *bfs, extra=()):
     return val
 
 
-def build_basis():
+def build_basis(basis="sto-3g"):
     bfs, atoms = [], []
     for sym, xyz in GEOM:
         pos = np.array(xyz) / BOHR_TO_ANGSTROM
         atoms.append((Z[sym], pos))
-        for l, exps, coefs in STO3G[sym]:
+        for l, exps, coefs in BASES[basis][sym]:
             for lmn in ([(0, 0, 0)] if l == 0 else [(1, 0, 0), (0, 1, 0), (0, 0, 1)]):
                 bfs.append(BF(pos, lmn, exps, coefs))
     return bfs, atoms
@@ -331,10 +354,10 @@ def pt_spinorbital(t1, t2, A, fs, no):
     return float(np.sum(conn * (conn + disc) / D) / 36.0)
 
 
-def main():
+def main(basis="sto-3g"):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
-    bfs, atoms = build_basis()
+    bfs, atoms = build_basis(basis)
     S, T, V, ERI, enuc = integrals(bfs, atoms)
     ndocc = 5
     e_el, eps, C = rhf(S, T + V, ERI, ndocc)
@@ -353,17 +376,20 @@ def main():
     fo, fv = eps[:o].copy(), eps[o:].copy()
     from oracle import pt_numpy as P
     e_t = P.pt_ijk(T1, T2, OVVV, OOOV, OVOV, fo, fv)
-    print(f"E_nuc   {enuc:.10f}   (reference print  8.8880641743)")
+    ref = REFERENCE[basis]
+    note = lambda k: f"   (reference {ref[k]:.10f})" if k in ref else ""
+    print(f"water / {basis}: o={o} v={v}")
+    print(f"E_nuc   {enuc:.10f}" + note("e_nuc"))
     print(f"E_RHF   {e_rhf:.10f}")
-    print(f"E_corr  {e_cc:.10f}   (reference print -0.0537066985)")
-    print(f"E_CCSD  {e_rhf + e_cc:.10f}   (reference print -75.0187095932)")
-    print(f"E(T)    {e_t:.10f}   (reference print -0.0000738086)   spin-orbital formula: {e_t_so:.10f}")
-    print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}   (reference print -75.0187834019)")
-    out = os.path.join(root, "tests", "golden", "water_sto3g.npz")
+    print(f"E_corr  {e_cc:.10f}" + note("e_corr"))
+    print(f"E_CCSD  {e_rhf + e_cc:.10f}" + note("e_ccsd"))
+    print(f"E(T)    {e_t:.10f}" + note("e_t") + f"   spin-orbital formula: {e_t_so:.10f}")
+    print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}" + note("e_ccsd_t"))
+    out = os.path.join(root, "tests", "golden", "water_" + basis.replace("-", "") + ".npz")
     np.savez(out, T1=T1, T2=T2, OVVV=OVVV, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t,
              e_t_spinorbital=e_t_so)
     print("wrote", out)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "sto-3g")

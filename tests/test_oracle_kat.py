@@ -4,7 +4,11 @@ examples/Juliacon2022.ipynb:461-615 (reference repo) runs `@energy ccsd(t)` for 
 `Final (T) contribution: -0.0000738086` (CCSD correlation -0.0537066985, CCSD(T) -75.0187834019).  oracle/mini_ccsd.py
 rebuilt the inputs of RCCSDpT(ccsd, moints, alg) for that molecule (own integrals, RHF, spin-orbital CCSD; it reproduces
 the reference's printed nuclear repulsion, CCSD correlation and total energies to all 10 printed decimals) and stored
-them in tests/golden/water_sto3g.npz.  Feeding those arrays to the oracle must give the printed E(T)."""
+them in tests/golden/water_sto3g.npz.  Feeding those arrays to the oracle must give the printed E(T).
+
+Second known answer, from the reference's own test suite: test/test_pT.jl:69-72 asserts, for water / 6-31G / `df false`,
+`@energy ccsd(t)` total = -76.121147867765558 (Psi4) to rtol 2e-8.  `python oracle/mini_ccsd.py 6-31g` rebuilds RHF + CCSD for
+that case (tests/golden/water_631g.npz; o=5, v=8); E_RHF + E_CCSD-corr + oracle E(T) lands 5e-12 Eh from the asserted value."""
 import os
 
 import numpy as np
@@ -48,3 +52,33 @@ def test_gpu_matches_reference_known_answer(engine):
     res = fb.RCCSDpT(ccsd, moints, fb.B200())
     assert abs(res.correction - REF_ET) < 5e-11
     assert abs(res.energy - REF_ECCSDT) < 5e-11
+
+
+# ---- water / 6-31G: the value the reference's test suite asserts (test/test_pT.jl:72) ----------------------------------
+G2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "water_631g.npz"))
+REF2_ECCSDT = -76.121147867765558   # test/test_pT.jl:72 (rtol 2e-8 there; 1e-9 Eh absolute here)
+
+
+def _args2():
+    return tuple(np.asfortranarray(G2[k]) for k in ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv"))
+
+
+@pytest.mark.parametrize("impl", ["naive", "gemm", "numpy_ijk", "numpy_ijk2"])
+def test_oracle_matches_reference_test_value_631g(impl):
+    f = {"naive": oracle.pt_naive, "gemm": oracle.pt_gemm, "numpy_ijk": P.pt_ijk, "numpy_ijk2": P.pt_ijk2}[impl]
+    assert G2["T1"].shape == (5, 8) and G2["T2"].shape == (5, 5, 8, 8)
+    e = f(*_args2())
+    total = float(G2["e_rhf"]) + float(G2["e_corr"]) + e
+    assert abs(total - REF2_ECCSDT) < 1e-9, (total, REF2_ECCSDT)
+    assert abs(e - float(G2["e_t_spinorbital"])) < 1e-14
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_test_value_631g(engine):
+    import fermi_jl_b200 as fb
+    a = _args2()
+    ccsd = fb.RCCSD(0.0, float(G2["e_corr"]), float(G2["e_rhf"]) + float(G2["e_corr"]), a[0], a[1])
+    moints = fb.IntegralHelper({"OVVV": a[2], "OOOV": a[3], "OVOV": a[4], "Fii": a[5], "Faa": a[6]})
+    res = fb.RCCSDpT(ccsd, moints, fb.B200())
+    assert abs(res.energy - REF2_ECCSDT) < 1e-9
+    assert abs(res.correction - float(G2["e_t"])) < 1e-12
