@@ -115,11 +115,11 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
     npair = o * (o + 1) // 2
     pr0 = npair
     while pr0 > 0:
-        (_, _), (tb, te) = fb.host.pair_range_items(o, v, pr0 - 1, npair)
+        tb, te = fb.host.pair_range_triplets(o, pr0 - 1, npair)
         pr0 -= 1
         if te - tb >= want:
             break
-    (ib, ie), (tb, te) = fb.host.pair_range_items(o, v, pr0, npair)
+    tb, te = fb.host.pair_range_triplets(o, pr0, npair)
     t0 = time.perf_counter()
     e = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te)
     dt = time.perf_counter() - t0
@@ -135,7 +135,7 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
             if j > i:
                 j = 0; i += 1
     return {"E": e, "seconds": dt, "triplets": ntr, "flops": algorithmic_flops(o, v, ntr), "threads": threads,
-            "items": (ib, ie), "triplet_range": (tb, te)}
+            "triplet_range": (tb, te)}
 
 
 def run_reference(args, name, o, v, naux):
@@ -227,7 +227,7 @@ def main():
     # ---- leg 1: operands resident in HBM ----
     eng.upload_conv(o, v, *[host[k] for k in names])
     n_items = eng.num_items()
-    ib, ie = fb.host.shard_items(n_items, rank, world)
+    ib, ie = eng.shard_items(rank, world)       # contiguous, equal estimated cost
     ntrip = n_triplets(o)
     flops = algorithmic_flops(o, v, ntrip)
     for _ in range(args.warmup):
@@ -299,7 +299,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             s = cpu_reference_sample(x, o, v, budget_s=args.cpu_budget)
-            e_s, _ = eng.compute(*s["items"])
+            eng.set_triplet_window(*s["triplet_range"])   # the same triplets on the GPU
+            e_s, _ = eng.compute(0, -1)
+            eng.set_triplet_window(0, -1)
             cpu = {"value": s["flops"] / s["seconds"] / 1e12, "unit": UNIT, "cores": s["threads"], "kind": "port",
                    "sample": f"triplets [{s['triplet_range'][0]},{s['triplet_range'][1]}) of the i>=j>=k list "
                              f"({s['triplets']} non-zero-weight), {s['seconds']:.1f} s of oracle/pt_oracle.c (OpenMP)",
@@ -309,7 +311,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
                            "o": o, "v": v, "triplets": ntrip, "work_items": n_items,
-                           "parallelism": f"static contiguous shards of the (pair,block,k) work list over {world} rank(s)",
+                           "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} rank(s)",
                            "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 7) // 8 * 8) * 8 / 1e6)},
                 "triplets_per_s": ntrip / (step_ms * 1e-3), "E_T": e_gpu, "E_T_e2e": e_e2e,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},

@@ -27,7 +27,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df",
-           "fpt_num_items", "fpt_compute", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
+           "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
 def library_path() -> str:
@@ -58,7 +58,11 @@ def load_library():
     L.fpt_dmma_sweep.argtypes = [vp, ctypes.c_int, ctypes.c_int, _dp]
     L.fpt_last_error.restype = ctypes.c_char_p
     L.fpt_version.restype = ctypes.c_char_p
-    for f in EXPORTS[:13]:
+    L.fpt_set_kernel_variant.argtypes = [vp, ctypes.c_int]
+    L.fpt_set_triplet_window.argtypes = [vp, ctypes.c_longlong, ctypes.c_longlong]
+    L.fpt_set_item_order.argtypes = [vp, ctypes.c_int]
+    L.fpt_shard_items.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
+    for f in EXPORTS[:17]:
         getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
@@ -141,6 +145,23 @@ class Engine:
     def set_debug_flags(self, flags: int):
         self._check(self._L.fpt_set_debug_flags(self._h, flags))
 
+    def set_triplet_window(self, t_begin: int = 0, t_end: int = -1):
+        """Restrict the work list to positions [t_begin, t_end) of the reference's flattened i>=j>=k list (k fastest)."""
+        self._check(self._L.fpt_set_triplet_window(self._h, t_begin, t_end))
+
+    def set_item_order(self, order: int):
+        self._check(self._L.fpt_set_item_order(self._h, order))
+
+    def shard_items(self, rank: int, world: int):
+        """Item range of part `rank` of `world` (contiguous, equal estimated cost) for `compute`."""
+        b, e = ctypes.c_longlong(), ctypes.c_longlong()
+        self._check(self._L.fpt_shard_items(self._h, rank, world, ctypes.byref(b), ctypes.byref(e)))
+        return b.value, e.value
+
+    def set_kernel_variant(self, variant: int):
+        self._check(self._L.fpt_set_kernel_variant(self._h, variant))
+        self._variant = variant
+
     def set_profiling(self, on: bool):
         self._check(self._L.fpt_set_profiling(self._h, 1 if on else 0))
 
@@ -149,8 +170,15 @@ class Engine:
         self._check(self._L.fpt_last_profile(self._h, buf))
         names = ["wait_item", "zero", "kloops", "rmw", "energy", "total", "token_wait", "rmw_pure", "full_wait", "ov_wait",
                  "bar_pre_energy", "bar_post_energy"]
+        if getattr(self, "_variant", 1) == 2:
+            names = ["wait_item", "setup", "kloops", "park", "energy", "total", "park_wait", "wdone_wait", "full_wait", "ov_wait",
+                     "_", "bar_post_energy"]
         out = dict(zip(names, list(buf)[:12]))
-        out.update({"g3_" + k: v for k, v in zip(names, list(buf)[12:])})
+        if getattr(self, "_variant", 1) == 2:
+            enames = ["wait_item", "wfree_wait", "park_full_wait", "set_barrier", "batches", "total"]
+            out.update({"g3_" + k: v for k, v in zip(enames, list(buf)[12:18])})   # "g3_" = the epilogue warp of quarter 0 here
+        else:
+            out.update({"g3_" + k: v for k, v in zip(names, list(buf)[12:])})
         return out
 
     def dmma_sweep(self, ilp: int, warps_per_sm: int) -> float:

@@ -16,6 +16,7 @@
 #include "../../include/fermi_pt_b200.h"
 #include "fpt_aux_kernels.cuh"
 #include "fpt_triples.cuh"
+#include "fpt_triples2.cuh"
 
 using namespace fpt;
 
@@ -69,6 +70,10 @@ struct fpt_handle {
     int last_grid = 0;
     bool profiling = false;
     int dbg_flags = 0;
+    int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
+    std::vector<double> block_cost;
+    int kernel_variant = 1;   // 1: DMMA warps add their own accumulators into the W slots (fpt_triples.cuh, default);
+                              // 2: experimental epilogue-warp kernel with TMEM parking (fpt_triples2.cuh)
     bool last_profiled = false;
     // multi-GPU (single process): this handle drives devices[0]; peers[] drive the others; one NCCL clique
     std::vector<fpt_handle*> peers;
@@ -139,6 +144,8 @@ static int create_one(int dev, fpt_handle** out)
     CK(cudaEventCreate(&h->ev1));
     CK(cudaFuncSetAttribute(triples_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
     CK(cudaFuncSetAttribute(triples_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
     *out = h;
     return 0;
 }
@@ -218,26 +225,18 @@ static int setup_problem(fpt_handle* h, int o, int v)
     P.nt = num_tiles(v);
     P.Kp = roundup(v + o, KGROUP);
     P.G = P.Kp / KGROUP;
-    P.npair = o * (o + 1) / 2;
     P.nb = num_blocks(P.nt);
     P.dbg_flags = h->dbg_flags;
-    std::vector<i64> prefix(P.npair + 1);
-    i64 acc = 0;
-    for (int pr = 0; pr < P.npair; pr++) {
-        int i, j;
-        tri_decode(pr, i, j);
-        prefix[pr] = acc;
-        acc += (i64)num_k(i, j) * P.nb;
-    }
-    prefix[P.npair] = acc;
-    P.nitems = acc;
+    P.order = h->item_order;
+    P.tw_begin = 0;
+    P.tw_count = num_triplets(o);   // a new problem starts with the full triplet list
+    P.nitems = P.nb * P.tw_count;
     if (h->Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
     if (h->Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
     if (h->OV2.ensure((size_t)ov2_elems(P) * sizeof(double))) return 1;
     if (h->T1d.ensure((size_t)o * v * sizeof(double))) return 1;
     if (h->fo.ensure((size_t)o * sizeof(double))) return 1;
     if (h->fv.ensure((size_t)v * sizeof(double))) return 1;
-    if (h->prefix.ensure(prefix.size() * sizeof(i64))) return 1;
     if (h->partials.ensure((size_t)h->n_sm * 4 * sizeof(double))) return 1;
     if (h->counter.ensure(sizeof(unsigned long long))) return 1;
     if (h->out.ensure(sizeof(double))) return 1;
@@ -253,10 +252,11 @@ static int setup_problem(fpt_handle* h, int o, int v)
     if (h->blocktab.ensure(tab.size() * sizeof(BlockTabEntry))) return 1;
     CK(cudaMemcpyAsync(h->blocktab.p, tab.data(), tab.size() * sizeof(BlockTabEntry), cudaMemcpyHostToDevice, h->stream));
     P.blocktab = (const BlockTabEntry*)h->blocktab.p;
-    CK(cudaMemcpyAsync(h->prefix.p, prefix.data(), prefix.size() * sizeof(i64), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // `prefix` is a local
+    CK(cudaStreamSynchronize(h->stream));   // `tab` is a local
+    h->block_cost.resize((size_t)P.nb);
+    for (i64 b = 0; b < P.nb; b++) h->block_cost[b] = block_cost(tab[b], P.G);
     P.Pt = h->Pt.d(); P.Qt = h->Qt.d(); P.OV2 = h->OV2.d(); P.T1d = h->T1d.d();
-    P.fo = h->fo.d(); P.fv = h->fv.d(); P.pair_prefix = (const i64*)h->prefix.p;
+    P.fo = h->fo.d(); P.fv = h->fv.d();
     return 0;
 }
 
@@ -396,6 +396,45 @@ extern "C" int fpt_num_items(fpt_handle* h, long long* n)
     return 0;
 }
 
+// Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost; returns part `rank`.
+// In block-major order an item's cost depends on its block (diagonal and edge blocks are cheaper), so boundaries are
+// placed on the prefix sum of block_cost; in triplet-major order every stretch of nb items costs the same.
+static void shard_range(const fpt_handle* h, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
+{
+    const Problem& P = h->prob;
+    if (P.order != 1 || P.tw_count <= 0) {
+        *sb = b + (e - b) * rank / world;
+        *se = b + (e - b) * (rank + 1) / world;
+        return;
+    }
+    // cost of items [b, x): whole blocks plus a partial one
+    auto cost_upto = [&](i64 x) {
+        const i64 blk = x / P.tw_count, rem = x - blk * P.tw_count;
+        double c = 0.0;
+        for (i64 t = 0; t < blk; t++) c += h->block_cost[t] * (double)P.tw_count;
+        if (blk < P.nb) c += h->block_cost[blk] * (double)rem;
+        return c;
+    };
+    const double c0 = cost_upto(b), c1 = cost_upto(e);
+    auto boundary = [&](int r) -> i64 {
+        if (r <= 0) return b;
+        if (r >= world) return e;
+        const double target = c0 + (c1 - c0) * r / world;
+        double c = 0.0;
+        for (i64 blk = 0; blk < P.nb; blk++) {
+            const double cb = h->block_cost[blk] * (double)P.tw_count;
+            if (c + cb >= target) {
+                i64 x = blk * P.tw_count + (i64)((target - c) / h->block_cost[blk] + 0.5);
+                return x < b ? b : (x > e ? e : x);
+            }
+            c += cb;
+        }
+        return e;
+    };
+    *sb = boundary(rank);
+    *se = boundary(rank + 1);
+}
+
 // launch the fused kernel + reduction for [item_begin, item_end) on h's device (asynchronous; result in h->out)
 static int compute_launch(fpt_handle* h, i64 item_begin, i64 item_end)
 {
@@ -406,7 +445,14 @@ static int compute_launch(fpt_handle* h, i64 item_begin, i64 item_end)
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
     CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (h->profiling)
+    if (h->kernel_variant == 2) {
+        if (h->profiling)
+            triples_kernel2<true><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, h->stream>>>(
+                P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
+        else
+            triples_kernel2<false><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, h->stream>>>(
+                P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
+    } else if (h->profiling)
         triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(
             P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
     else
@@ -433,10 +479,14 @@ extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_e
     const int ng = 1 + (int)h->peers.size();
     std::vector<fpt_handle*> hs(1, h);
     for (fpt_handle* p : h->peers) hs.push_back(p);
-    // static contiguous shards of the range, one per GPU (equal item counts)
+    // static contiguous shards of the range, one per GPU (equal estimated cost)
     for (int d = 0; d < ng; d++) {
         hs[d]->profiling = h->profiling;
-        if (compute_launch(hs[d], item_begin + n * d / ng, item_begin + n * (d + 1) / ng)) return 1;
+        hs[d]->kernel_variant = h->kernel_variant;
+        hs[d]->prob.order = P.order; hs[d]->prob.tw_begin = P.tw_begin; hs[d]->prob.tw_count = P.tw_count; hs[d]->prob.nitems = P.nitems;
+        i64 sb, se;
+        shard_range(h, item_begin, item_end, d, ng, &sb, &se);
+        if (compute_launch(hs[d], sb, se)) return 1;
     }
     if (ng > 1) {   // the single scalar all-reduce of E(T)
         NCK(g_nccl.GroupStart());
@@ -457,7 +507,8 @@ extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_e
     }
     CK(cudaSetDevice(h->dev));
     *Et = e;
-    const double ntrip = (double)P.o * (P.o + 1) * (P.o + 2) / 6.0 - P.o;
+    // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
+    const double ntrip = (double)P.tw_count;
     h->last.kernel_ms = ms_max;
     h->last.n_items = n;
     h->last.n_triplets = (long long)ntrip;
@@ -476,6 +527,7 @@ static int broadcast_operands(fpt_handle* h)
     for (fpt_handle* p : h->peers) {
         CK(cudaSetDevice(p->dev));
         p->dbg_flags = h->dbg_flags;
+        p->item_order = h->item_order;
         p->loaded = false;
         if (setup_problem(p, P.o, P.v)) return 1;
     }
@@ -565,6 +617,55 @@ extern "C" int fpt_set_debug_flags(fpt_handle* h, int flags)
     if (!h) return fail("fpt_set_debug_flags: NULL handle");
     h->prob.dbg_flags = flags;
     h->dbg_flags = flags;
+    return 0;
+}
+
+// Restrict the work list to positions [t_begin, t_end) of the reference's flattened i >= j >= k triplet list (k fastest,
+// zero-weight i = j = k entries included, exactly the list the loops of ijk.jl:49,63,83 walk); t_end < 0 = to the end.
+extern "C" int fpt_set_triplet_window(fpt_handle* h, long long t_begin, long long t_end)
+{
+    if (!h) return fail("fpt_set_triplet_window: NULL handle");
+    if (!h->loaded) return fail("fpt_set_triplet_window: no problem uploaded");
+    Problem& P = h->prob;
+    const i64 nfull = (i64)P.o * (P.o + 1) * (P.o + 2) / 6;
+    if (t_end < 0 || t_end > nfull) t_end = nfull;
+    if (t_begin < 0) t_begin = 0;
+    if (t_begin > t_end) t_begin = t_end;
+    const i64 u0 = triplets_before(P.o, t_begin), u1 = triplets_before(P.o, t_end);
+    P.tw_begin = u0;
+    P.tw_count = u1 - u0;
+    P.nitems = P.nb * P.tw_count;
+    return 0;
+}
+
+// 1: block-major (default), 0: triplet-major.  Takes effect for the next compute; keeps the triplet window.
+extern "C" int fpt_set_item_order(fpt_handle* h, int order)
+{
+    if (!h) return fail("fpt_set_item_order: NULL handle");
+    if (order != 0 && order != 1) return fail("fpt_set_item_order: order must be 0 or 1, got %d", order);
+    h->item_order = order;
+    h->prob.order = order;
+    return 0;
+}
+
+// Part `rank` of `world` of the current work list, as an item range for fpt_compute: contiguous, equal estimated cost.
+extern "C" int fpt_shard_items(fpt_handle* h, int rank, int world, long long* item_begin, long long* item_end)
+{
+    if (!h || !item_begin || !item_end) return fail("fpt_shard_items: NULL argument");
+    if (!h->loaded) return fail("fpt_shard_items: no problem uploaded");
+    if (world < 1 || rank < 0 || rank >= world) return fail("fpt_shard_items: invalid rank %d of %d", rank, world);
+    i64 sb, se;
+    shard_range(h, 0, h->prob.nitems, rank, world, &sb, &se);
+    *item_begin = sb;
+    *item_end = se;
+    return 0;
+}
+
+extern "C" int fpt_set_kernel_variant(fpt_handle* h, int variant)
+{
+    if (!h) return fail("fpt_set_kernel_variant: NULL handle");
+    if (variant != 1 && variant != 2) return fail("fpt_set_kernel_variant: variant must be 1 or 2, got %d", variant);
+    h->kernel_variant = variant;
     return 0;
 }
 

@@ -159,6 +159,9 @@ struct GemmDesc {
     int dsel[2];            // packed: ra | rb<<2 | rc<<4   (0=x,1=y,2=z)
     int dTb[2], dTc[2];
     int diag_xz;            // X and Z are the same tile: D(s=0) and D(s=1) of different threads alias in the W slot
+    int dfirst[2];          // D[...,s,...] is the first contribution its W slot receives in this item: store, do not add
+    int xinv;               // ceil(65536 / TX): row m = yl*TX + xl  ->  yl = (m * xinv) >> 16 for m < 256
+    int rt_total;           // TX*TY/8 row tiles of 8
 };
 
 // occ = (i,j,k).  Builds the 3*nslot GEMMs of an item.  Returns their number.
@@ -166,6 +169,7 @@ FPT_HD int make_gemms(const BlockDesc& bd, int i, int j, int k, GemmDesc* gd)
 {
     const int occ[3] = {i, j, k};
     int n = 0;
+    bool touched[MAX_SLOTS] = {false, false, false, false, false, false};
     for (int sl = 0; sl < bd.nslot; sl++) {
         const int m = bd.perm_of_slot[sl];
         const int cx = perm3(m, 0), cy = perm3(m, 1), cz = perm3(m, 2);  // which of A/B/C plays X, Y, Z
@@ -176,6 +180,8 @@ FPT_HD int make_gemms(const BlockDesc& bd, int i, int j, int k, GemmDesc* gd)
             g.x0 = bd.t0[cx]; g.y0 = bd.t0[cy]; g.z0 = bd.t0[cz];
             g.TX = bd.ts[cx]; g.TY = bd.ts[cy]; g.TZ = bd.ts[cz];
             g.diag_xz = (bd.tile[cx] == bd.tile[cz]);
+            g.xinv = (65536 + g.TX - 1) / g.TX;
+            g.rt_total = (g.TX * g.TY) >> 3;
             for (int s = 0; s < 2; s++) {
                 // pairing: x <-> (s ? r : q), y <-> p, z <-> (s ? q : r).  sel[pos] = which of x/y/z pairs with occ pos
                 int sel[3];
@@ -195,6 +201,9 @@ FPT_HD int make_gemms(const BlockDesc& bd, int i, int j, int k, GemmDesc* gd)
                 g.dsel[s] = sel[0] | (sel[1] << 2) | (sel[2] << 4);
                 g.dTb[s] = bd.ts[db];
                 g.dTc[s] = bd.ts[dc];
+                // GEMMs run in index order (a twin GEMM's second add directly follows its twin), so "first" is static
+                g.dfirst[s] = touched[dslot] ? 0 : 1;
+                touched[dslot] = true;
             }
         }
     }
@@ -246,19 +255,38 @@ struct BlockTabEntry {
 };
 static_assert(sizeof(BlockTabEntry) % 16 == 0, "BlockTabEntry is moved by 16-byte-granular bulk copies");
 
+// Relative cost of one item of a block, in units of one DMMA.8x8x4 per consumer warp, for the static cost-weighted split of
+// the work list across GPUs: per GEMM the k-loop issues ceil(row tiles / 16) x (TZ/4) x 4 DMMAs per kappa group and warp,
+// plus a fixed epilogue (accumulate into the W slots, next GEMM's setup) worth about 2 full-size groups; per item the
+// energy stage and the item switch cost about 5 full-size groups (phase profile profiles/r01_phase_c4_mid.json, tuned on
+// the measured 8-way shard times at the C4 shape).
+FPT_HD double block_cost(const BlockTabEntry& e, int G)
+{
+    double c = 5.0 * 32.0;
+    for (int g = 0; g < e.ngemm; g++) {
+        const int mtw = (e.gemm[g].rt_total + 15) / 16, nt = e.gemm[g].TZ >> 2;
+        c += (double)(mtw * nt * 4) * G + 2.0 * 32.0;
+    }
+    return c;
+}
+
 // ---- problem description --------------------------------------------------------------------------
 struct Problem {
     int o, v, vp, nt, Kp, G;
-    int npair;
     i64 nb;        // blocks per triplet
-    i64 nitems;
+    // Work list: items = (non-zero-weight triplet u in the window [tw_begin, tw_begin + tw_count)) x (block).
+    // order 1 (default): block-major, u fastest -- every CTA of the grid works on the same tile triple, so the
+    //     6*o P panels of that block (42 MB at C4) stay L2-resident while all triplets stream through them;
+    // order 0: triplet-major, block fastest -- concurrent CTAs share P_i, P_j, P_k of one triplet.
+    int order;
+    i64 tw_begin, tw_count;
+    i64 nitems;    // nb * tw_count
     const double* Pt;
     const double* Qt;
     const double* OV2;
     const double* T1d;
     const double* fo;
     const double* fv;
-    const i64* pair_prefix;   // npair+1 entries: first item of pair (i,j), pair index = i(i+1)/2+j (host / emulator only)
     const BlockTabEntry* blocktab;   // nb entries (device)
     int dbg_flags;            // diagnostics only (results become wrong): 1 = skip RMW epilogues, 2 = skip energy stage
 };
@@ -267,20 +295,6 @@ FPT_HD i64 pt_row(const Problem& P, int p, int y, int x) { return (((i64)p * P.v
 FPT_HD i64 qt_row(const Problem& P, int q, int r, int g, int z) { return ((((i64)q * P.o + r) * P.G + g) * P.vp + z) * KGROUP; }
 
 struct ItemDesc { int i, j, k; int A, B, C; };
-
-FPT_HD void item_decode(const Problem& P, i64 item, ItemDesc& it)
-{
-    int lo = 0, hi = P.npair;   // find pair with prefix[pr] <= item < prefix[pr+1]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (P.pair_prefix[mid] <= item) lo = mid; else hi = mid;
-    }
-    tri_decode(lo, it.i, it.j);
-    const i64 rem = item - P.pair_prefix[lo];
-    const int nk = num_k(it.i, it.j);
-    it.k = (int)(rem % nk);
-    tetra_decode(rem / nk, it.A, it.B, it.C);
-}
 
 // OV2 is stored in 16x16 tiles so that the 18 tiles an item's energy stage reads are 2 KB contiguous blocks (one TMA L2
 // prefetch each) and the in-tile offsets are shift/adds.
@@ -304,20 +318,34 @@ FPT_HD bool gemm_is_dup(const ItemDesc& it, int g)
     return (pi == 1 && it.i == it.j) || (pi == 2 && it.j == it.k);
 }
 
-// Same decode without the prefix table: the number of non-zero-weight triplets before pair (i,j) is
-// T(i,j) = i(i+1)(i+2)/6 - i + j(j+1)/2, and item = nb*T(i,j) + block*nk + k.
+// Non-zero-weight triplets i >= j >= k (not i = j = k, ijk.jl:133) in the reference's loop order (i, then j, then k
+// fastest; ijk.jl:49,63,83) are numbered u = 0 .. ntrip-1; T(i,j) = i(i+1)(i+2)/6 - i + j(j+1)/2 of them precede pair (i,j).
+FPT_HD i64 num_triplets(int o) { return (i64)o * (o + 1) * (o + 2) / 6 - o; }
+FPT_HD void triplet_decode(int o, i64 u, int& i_, int& j_, int& k_)
+{
+    int i = 0;
+    while (i + 1 < o && (i64)(i + 1) * (i + 2) * (i + 3) / 6 - (i + 1) <= u) i++;
+    const i64 ti = (i64)i * (i + 1) * (i + 2) / 6 - i;
+    int j = 0;   // pair (i,j) holds num_k(i,j) = j+1 triplets (j < i) or i (j = i, the last pair of this i)
+    while (j + 1 <= i && (i64)(j + 1) * (j + 2) / 2 <= u - ti) j++;
+    i_ = i; j_ = j; k_ = (int)(u - ti - (i64)j * (j + 1) / 2);
+}
+// position t in the reference's full list of i >= j >= k triplets (zero-weight ones included) -> number of
+// non-zero-weight triplets before it (the diagonal triplet (m,m,m) sits at t = m(m+1)(m+2)/6 + m(m+1)/2 + m)
+FPT_HD i64 triplets_before(int o, i64 t)
+{
+    i64 ndiag = 0;
+    for (int m = 0; m < o; m++)
+        if ((i64)m * (m + 1) * (m + 2) / 6 + (i64)m * (m + 1) / 2 + m < t) ndiag++;
+    return t - ndiag;
+}
+
 FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block)
 {
-    const i64 u = item / P.nb;
-    int i = 0;
-    while (i + 1 < P.o && (i64)(i + 1) * (i + 2) * (i + 3) / 6 - (i + 1) <= u) i++;
-    const i64 ti = (i64)i * (i + 1) * (i + 2) / 6 - i;
-    int j = 0;
-    while (j + 1 <= i && (i64)(j + 1) * (j + 2) / 2 <= u - ti) j++;
-    const i64 rem = item - P.nb * (ti + (i64)j * (j + 1) / 2);
-    const int nk = num_k(i, j);
-    it.i = i; it.j = j; it.k = (int)(rem % nk);
-    block = rem / nk;
+    i64 u;
+    if (P.order == 1) { block = item / P.tw_count; u = item - block * P.tw_count; }
+    else              { u = item / P.nb; block = item - u * P.nb; }
+    triplet_decode(P.o, P.tw_begin + u, it.i, it.j, it.k);
     tetra_decode(block, it.A, it.B, it.C);
 }
 

@@ -103,8 +103,9 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
 // Producer: one thread.  Streams the Q chunks of every GEMM of every item through the ring.  Item n+1 is fetched and
 // decoded while the chunks of item n are still streaming (right after its first GEMM), so the ring never runs dry at an
 // item boundary.
+template <class Tail>
 __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
-                                              double* Qsm, SmemTail* tail)
+                                              double* Qsm, Tail* tail)
 {
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
     const i64 gstride = (i64)P.vp * KGROUP;   // doubles between consecutive kappa groups of one (q,r) in Qt
@@ -190,7 +191,7 @@ __device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd,
         const bool ok = (mt < mtw) && (rt < rt_total);
         rs.nvalid += ok ? 1 : 0;
         const int m = ok ? rt * 8 + r : r;
-        const int yl = m / gd.TX;
+        const int yl = (m * gd.xinv) >> 16;   // m / TX
         const int xl = m - yl * gd.TX;
         rs.off[mt] = (yl * P.vp + xl) * P.Kp;
     }
@@ -211,9 +212,9 @@ __device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, d
 // consumer: k-loop of one GEMM.  acc[mt][ct][e]: row tile mt, column tile ct, D element e.
 // Column n of tile ct is (zl = 4ct + (n>>1), s = n&1), so a lane's two D elements are (zl = 4ct + kk, s = e).
 // ---------------------------------------------------------------------------------------------------
-template <int MTW, int NT, bool PROF>
+template <int MTW, int NT, bool PROF, class Tail>
 __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
-                                           double (&acc)[MTW][NT][2], const double* Qsm, SmemTail* tail, int& stage,
+                                           double (&acc)[MTW][NT][2], const double* Qsm, Tail* tail, int& stage,
                                            uint32_t& sphase, int lane, long long* prof)
 {
     const int kk = lane & 3, n = lane >> 2;
@@ -281,7 +282,7 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 #pragma unroll
     for (int mt = 0; mt < MTW; mt++) {
         const int m = (rs.rt0 + mt) * 8 + r;
-        yl[mt] = m / gd.TX;
+        yl[mt] = (m * gd.xinv) >> 16;   // m / TX
         xl[mt] = m - yl[mt] * gd.TX;
     }
 #pragma unroll
@@ -289,13 +290,19 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
         if (e == 1 && gd.diag_xz) consumer_bar();
         const int dbase = gd.dbase[e], sel = gd.dsel[e], Tb = gd.dTb[e], Tc = gd.dTc[e];
+        const bool first = gd.dfirst[e] != 0;   // first contribution to this slot in the item: store (the slots are never zeroed)
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) {
             if (mt < rs.nvalid) {
                 DestIter it;
                 dest_iter_init_fast(dbase, sel, Tb, Tc, xl[mt], yl[mt], kk, it);
+                if (first) {
 #pragma unroll
-                for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
+                    for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] = acc[mt][ct][e];
+                } else {
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
+                }
             }
         }
     }
@@ -406,12 +413,8 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         RowSet rs;
         rows_setup(P, ctl->ent.gemm[0], occ_pick(ctl->item, ctl->ent.gemm[0].p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
-        {   // zero the live W slots
-            const int nz2 = (ctl->ent.bd.nslot * ctl->ent.bd.slot_elems) >> 1;
-            double2* w2 = reinterpret_cast<double2*>(Wsm);
-            for (int idx = tid; idx < nz2; idx += NCTHREADS) w2[idx] = make_double2(0.0, 0.0);
-        }
-        consumer_bar();
+        // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst); the barrier at the
+        // end of the previous item's energy stage already ordered those stores after its reads
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 
         for (int g = 0; g < ngemm; g++) {

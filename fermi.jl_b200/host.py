@@ -146,25 +146,27 @@ class RCCSDpT:
         self.stats = st
 
 
-# ---- static work list helpers (mirror of fpt_layout.h; used for sharding across ranks) -----------------------
-def work_layout(o: int, v: int):
-    """(nb, prefix): blocks per triplet and the first item of every (i>=j) pair; pair index = i(i+1)/2 + j.
-    Items are ordered pair-major, then block, then k (k fastest); the zero-weight i=j=k triplet is skipped."""
+# ---- static work list helpers (mirror of fpt_layout.h) ---------------------------------------------------------
+def num_blocks(v: int) -> int:
+    """Tile triples A >= B >= C of the virtual range (tiles of 16 over roundup4(v))."""
     vp = (v + 3) // 4 * 4
     nt = (vp + 15) // 16
-    nb = nt * (nt + 1) * (nt + 2) // 6
-    prefix = [0]
-    for i in range(o):
-        for j in range(i + 1):
-            nk = j if i == j else j + 1
-            prefix.append(prefix[-1] + nk * nb)
-    return nb, prefix
+    return nt * (nt + 1) * (nt + 2) // 6
 
 
-def pair_range_items(o: int, v: int, pr0: int, pr1: int):
-    """Item range [b,e) covering pairs [pr0,pr1) and the matching range of the reference's flattened
-    (i,j,k) triplet list (k fastest) -- contiguous because pairs are."""
-    _, prefix = work_layout(o, v)
+def num_triplets(o: int) -> int:
+    """Non-zero-weight triplets i >= j >= k (ijk.jl:133 gives i = j = k weight 0)."""
+    return o * (o + 1) * (o + 2) // 6 - o
+
+
+def num_items(o: int, v: int) -> int:
+    """Items of the full work list: (non-zero-weight triplet) x (tile triple)."""
+    return num_blocks(v) * num_triplets(o)
+
+
+def pair_range_triplets(o: int, pr0: int, pr1: int):
+    """Positions [tb, te) of pairs [pr0, pr1) (pair index = i(i+1)/2 + j) in the reference's flattened i>=j>=k triplet
+    list (k fastest, ijk.jl:49,63,83) -- the window `Engine.set_triplet_window` and the oracle's t_begin/t_end take."""
 
     def first_triplet(pr):
         i = 0
@@ -173,9 +175,9 @@ def pair_range_items(o: int, v: int, pr0: int, pr1: int):
         j = pr - i * (i + 1) // 2
         return i * (i + 1) * (i + 2) // 6 + j * (j + 1) // 2
 
-    return (prefix[pr0], prefix[pr1]), (first_triplet(pr0), first_triplet(pr1))
+    return first_triplet(pr0), first_triplet(pr1)
 
 
 def shard_items(n_items: int, rank: int, world: int):
-    """Static contiguous split of the work list across ranks (equal item counts)."""
+    """Equal-count contiguous split of an item range (host-side tests); GPUs use the cost-weighted `Engine.shard_items`."""
     return n_items * rank // world, n_items * (rank + 1) // world

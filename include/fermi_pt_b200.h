@@ -76,6 +76,19 @@ int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double* T1, const
 int fpt_num_items(fpt_handle* h, long long* n_items);
 int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et_partial, fpt_stats* stats);
 
+/* The static work list.  An item is (triplet i >= j >= k, tile triple of the virtual range); the list holds every item of
+ * the triplets in the current window.
+ *  - fpt_set_triplet_window: restrict the list to positions [t_begin, t_end) of the reference's own flattened triplet list
+ *    (the order its loops walk, ijk.jl:49,63,83: i, then j <= i, then k <= j fastest; zero-weight i = j = k entries count as
+ *    positions but do no work).  t_end < 0 = to the end.  A new upload resets the window to all triplets.
+ *  - fpt_set_item_order: 1 (default) block-major -- all triplets of one tile triple before the next, which keeps that tile
+ *    triple's operand panels L2-resident; 0 triplet-major.
+ *  - fpt_shard_items: part `rank` of `world` of the list as a contiguous item range of equal estimated cost -- what each
+ *    GPU computes (one process per GPU passes it to fpt_compute; a multi-GPU handle does the same split internally). */
+int fpt_set_triplet_window(fpt_handle* h, long long t_begin, long long t_end);
+int fpt_set_item_order(fpt_handle* h, int order);
+int fpt_shard_items(fpt_handle* h, int rank, int world, long long* item_begin, long long* item_end);
+
 /* FP64 pipe calibration for the roofline denominator: variant 0 = DMMA.8x8x4 stream, 1 = DFMA stream.
  * Returns sustained TFLOP/s over `ms_target` milliseconds of back-to-back launches. */
 int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
@@ -86,6 +99,7 @@ int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
  *          pure RMW, wait on the Q ring inside the k-loops, wait for the staged OV2 tiles, barrier before / after the energy stage}
  * for the first warp of consumer group 0 (entries 0-11) and of group 3 (entries 12-23); and a DMMA issue study. */
 int fpt_set_profiling(fpt_handle* h, int on);
+int fpt_set_kernel_variant(fpt_handle* h, int variant);   /* 1 (default): the DMMA warps add their accumulators into the W slots; 2: experimental epilogue-warp kernel (TMEM parking) */
 int fpt_set_debug_flags(fpt_handle* h, int flags);   /* 1: skip RMW, 2: skip energy stage -- timing studies only, E(T) is wrong */
 int fpt_last_profile(fpt_handle* h, double* out24);
 int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops);

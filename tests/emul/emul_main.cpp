@@ -6,7 +6,8 @@
 // checks its E(T) against the oracle, so layout bugs are caught without a GPU.
 //
 // Exported C function:
-//   fpt_emulate(o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, item_begin, item_end, &Et)
+//   fpt_emulate(o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, order, t_begin, t_end, item_begin, item_end, &Et, &nitems)
+// (order / triplet window / item range as in fpt_set_item_order, fpt_set_triplet_window, fpt_compute)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,20 +19,31 @@
 using namespace fpt;
 
 extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
-                           const double* OVOV, const double* fo, const double* fv, long long item_begin, long long item_end,
-                           double* Et, long long* nitems_out)
+                           const double* OVOV, const double* fo, const double* fv, int order, long long t_begin, long long t_end,
+                           long long item_begin, long long item_end, double* Et, long long* nitems_out)
 {
-    Problem P;
+    Problem P{};
     P.o = o; P.v = v; P.vp = padded_v(v); P.nt = num_tiles(v);
     P.Kp = roundup(v + o, KGROUP); P.G = P.Kp / KGROUP;
-    P.npair = o * (o + 1) / 2; P.nb = num_blocks(P.nt);
-    std::vector<i64> prefix(P.npair + 1);
-    i64 acc = 0;
-    for (int pr = 0; pr < P.npair; pr++) { int i, j; tri_decode(pr, i, j); prefix[pr] = acc; acc += (i64)num_k(i, j) * P.nb; }
-    prefix[P.npair] = acc;
-    P.nitems = acc;
-    if (nitems_out) *nitems_out = acc;
-    P.pair_prefix = prefix.data();
+    P.nb = num_blocks(P.nt);
+    // independent enumeration of the reference's triplet list (ijk.jl:49,63,83) to check the closed-form decodes against
+    struct Trip { int i, j, k; };
+    std::vector<Trip> trips;        // non-zero-weight triplets of the window, in order
+    {
+        i64 t = 0;
+        const i64 nfull = (i64)o * (o + 1) * (o + 2) / 6;
+        if (t_end < 0 || t_end > nfull) t_end = nfull;
+        for (int i = 0; i < o; i++)
+            for (int j = 0; j <= i; j++)
+                for (int k = 0; k <= j; k++, t++)
+                    if (t >= t_begin && t < t_end && !(i == j && j == k)) trips.push_back({i, j, k});
+    }
+    P.order = order;
+    P.tw_begin = triplets_before(o, t_begin);
+    P.tw_count = triplets_before(o, t_end) - P.tw_begin;
+    if (P.tw_count != (i64)trips.size()) { fprintf(stderr, "triplets_before disagrees with the enumeration\n"); return 9; }
+    P.nitems = P.nb * P.tw_count;
+    if (nitems_out) *nitems_out = P.nitems;
 
     // ---- layout prep (same formulas as prep_* kernels) ----
     std::vector<double> Pt((size_t)o * P.vp * P.vp * P.Kp, 0.0), Qt((size_t)o * o * P.G * P.vp * KGROUP, 0.0),
@@ -64,13 +76,17 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
     std::vector<double> W((size_t)MAX_SLOTS * TMAX * TMAX * TMAX);
     double E = 0.0;
     for (i64 item = item_begin; item < item_end; item++) {
-        ItemDesc it, it2;
-        item_decode(P, item, it);
-        i64 blk2;
-        item_decode_cf(P, item, it2, blk2);
-        if (it.i != it2.i || it.j != it2.j || it.k != it2.k || it.A != it2.A || it.B != it2.B || it.C != it2.C) {
-            fprintf(stderr, "closed-form item decode disagrees at %lld\n", item);
-            return 7;
+        ItemDesc it;
+        i64 blk;
+        item_decode_cf(P, item, it, blk);
+        {
+            const i64 u = order == 1 ? item % P.tw_count : item / P.nb;
+            const i64 b = order == 1 ? item / P.tw_count : item % P.nb;
+            const Trip& tr = trips[(size_t)u];
+            if (it.i != tr.i || it.j != tr.j || it.k != tr.k || blk != b) {
+                fprintf(stderr, "closed-form item decode disagrees at %lld\n", item);
+                return 7;
+            }
         }
         if (!(it.i >= it.j && it.j >= it.k) || (it.i == it.j && it.j == it.k) || !(it.A >= it.B && it.B >= it.C) || it.A >= P.nt) {
             fprintf(stderr, "bad item decode %lld -> %d %d %d / %d %d %d\n", item, it.i, it.j, it.k, it.A, it.B, it.C);

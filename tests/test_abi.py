@@ -77,8 +77,10 @@ def test_argument_checking_mirrors_reference():
 
 
 def test_work_layout_matches_device_header():
-    # host.work_layout mirrors fpt_layout.h (tiles of 16 + remainder, pair-major items, i=j=k skipped)
-    nb, prefix = fb.host.work_layout(5, 19)      # vp=20 -> 2 tiles -> 4 blocks
-    assert nb == 4
-    assert prefix[-1] == nb * (5 * 6 * 7 // 6 - 5)
+    # host helpers mirror fpt_layout.h (tiles of 16 + remainder; items = tile triples x non-zero-weight triplets)
+    assert fb.host.num_blocks(19) == 4           # vp=20 -> 2 tiles -> 4 blocks
+    assert fb.host.num_triplets(5) == 5 * 6 * 7 // 6 - 5
+    assert fb.host.num_items(5, 19) == 4 * 30
     assert fb.host.shard_items(10, 0, 3) == (0, 3) and fb.host.shard_items(10, 2, 3) == (6, 10)
+    # pairs (2,0),(2,1),(2,2) of o=3 sit at positions [4, 10) of the reference's i>=j>=k list
+    assert fb.host.pair_range_triplets(3, 3, 6) == (4, 10)

@@ -30,12 +30,11 @@ def _worker(rank, world, port, out):
         bufs[k] = t.numpy()
     L = ctypes.CDLL(os.path.join(ROOT, "tests", "emul", "libfpt_emul.so"))
     dp = ctypes.POINTER(ctypes.c_double)
-    L.fpt_emulate.argtypes = [ctypes.c_int, ctypes.c_int] + [dp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, dp,
-                                                                        ctypes.POINTER(ctypes.c_longlong)]
-    _, prefix = fb.host.work_layout(o, v)
-    ib, ie = fb.host.shard_items(prefix[-1], rank, world)
+    L.fpt_emulate.argtypes = [ctypes.c_int, ctypes.c_int] + [dp] * 7 + [ctypes.c_int] + [ctypes.c_longlong] * 4 + [
+        dp, ctypes.POINTER(ctypes.c_longlong)]
+    ib, ie = fb.host.shard_items(fb.host.num_items(o, v), rank, world)
     e, n = ctypes.c_double(), ctypes.c_longlong()
-    rc = L.fpt_emulate(o, v, *[bufs[k].ctypes.data_as(dp) for k in names], ib, ie, ctypes.byref(e), ctypes.byref(n))
+    rc = L.fpt_emulate(o, v, *[bufs[k].ctypes.data_as(dp) for k in names], 1, 0, -1, ib, ie, ctypes.byref(e), ctypes.byref(n))
     assert rc == 0
     t = torch.tensor([e.value], dtype=torch.float64)
     dist.all_reduce(t)

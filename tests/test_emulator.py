@@ -16,13 +16,14 @@ _dp = ctypes.POINTER(ctypes.c_double)
 @pytest.fixture(scope="module")
 def emul(built):
     L = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "emul", "libfpt_emul.so"))
-    L.fpt_emulate.argtypes = [ctypes.c_int, ctypes.c_int] + [_dp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, _dp,
-                                                                         ctypes.POINTER(ctypes.c_longlong)]
+    L.fpt_emulate.argtypes = [ctypes.c_int, ctypes.c_int] + [_dp] * 7 + [ctypes.c_int] + [ctypes.c_longlong] * 4 + [
+        _dp, ctypes.POINTER(ctypes.c_longlong)]
 
-    def run(x, ib=0, ie=-1):
+    def run(x, ib=0, ie=-1, order=1, tb=0, te=-1):
         arrs = [np.asfortranarray(a) for a in (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)]
         e, n = ctypes.c_double(), ctypes.c_longlong()
-        rc = L.fpt_emulate(x.o, x.v, *[a.ctypes.data_as(_dp) for a in arrs], ib, ie, ctypes.byref(e), ctypes.byref(n))
+        rc = L.fpt_emulate(x.o, x.v, *[a.ctypes.data_as(_dp) for a in arrs], order, tb, te, ib, ie, ctypes.byref(e),
+                           ctypes.byref(n))
         assert rc == 0, f"emulator self-check failed with code {rc}"
         return e.value, n.value
 
@@ -35,18 +36,23 @@ def test_emulator_matches_oracle(emul, o, v):
     e, n = emul(x)
     ref = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
     assert abs(e - ref) < 1e-13, (e, ref)
-    nb, prefix = fb.host.work_layout(o, v)
-    assert n == prefix[-1]
+    assert n == fb.host.num_items(o, v)
 
 
-def test_item_shards_add_up_and_match_triplet_ranges(emul):
+@pytest.mark.parametrize("order", [0, 1])
+def test_item_shards_add_up_and_match_triplet_ranges(emul, order):
     o, v = 4, 21
     x = fb.synth.make_inputs(o, v, naux=8, seed=5)
-    full, n = emul(x)
-    parts = [emul(x, *fb.host.shard_items(n, r, 3))[0] for r in range(3)]
+    full, n = emul(x, order=order)
+    parts = [emul(x, *fb.host.shard_items(n, r, 3), order=order)[0] for r in range(3)]
     assert abs(sum(parts) - full) < 1e-15
     npair = o * (o + 1) // 2
-    (ib, ie), (tb, te) = fb.host.pair_range_items(o, v, npair - 3, npair)
-    part, _ = emul(x, ib, ie)
+    tb, te = fb.host.pair_range_triplets(o, npair - 3, npair)
+    part, npart = emul(x, order=order, tb=tb, te=te)
     ref = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te)
     assert abs(part - ref) < 1e-14
+    assert 0 < npart < n
+    # a window that starts and ends inside pairs, cutting through zero-weight diagonal entries
+    part2, _ = emul(x, order=order, tb=3, te=13)
+    ref2 = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=3, t_end=13)
+    assert abs(part2 - ref2) < 1e-14

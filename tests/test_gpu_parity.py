@@ -57,13 +57,23 @@ def test_c4_h2o6_shape_partial_and_sharded(engine):
     engine.upload_conv(o, v, *_args(x))
     n = engine.num_items()
     npair = o * (o + 1) // 2
-    (ib, ie), (tb, te) = fb.host.pair_range_items(o, v, npair - 2, npair)
-    part, _ = engine.compute(ib, ie)
+    tb, te = fb.host.pair_range_triplets(o, npair - 2, npair)
+    engine.set_triplet_window(tb, te)
+    part, _ = engine.compute(0, -1)
     ref = oracle.pt_gemm(*_args(x), t_begin=tb, t_end=te)
     assert abs(part - ref) < TOL, (part, ref)
+    engine.set_triplet_window(0, -1)
+    assert engine.num_items() == n == fb.host.num_items(o, v)
     full, st = engine.compute(0, -1)
-    shards = [engine.compute(*fb.host.shard_items(n, r, 8))[0] for r in range(8)]
+    ranges = [engine.shard_items(r, 8) for r in range(8)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(ranges[r][1] == ranges[r + 1][0] for r in range(7))
+    shards = [engine.compute(*rg)[0] for rg in ranges]
     assert abs(sum(shards) - full) < 1e-11, (sum(shards), full)
+    engine.set_item_order(0)                      # triplet-major order: same items, same energy
+    full0, _ = engine.compute(0, -1)
+    shards0 = [engine.compute(*engine.shard_items(r, 3))[0] for r in range(3)]
+    engine.set_item_order(1)
+    assert abs(full0 - full) < 1e-11 and abs(sum(shards0) - full) < 1e-11
     e_df, _ = engine.triples_df(o, v, 64, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
     assert abs(e_df - full) < TOL, (e_df, full)
 
@@ -166,3 +176,18 @@ def test_df_odd_aux_sizes(engine):
         ref = oracle.pt_gemm(*_args(x))
         e, _ = engine.triples_df(3, 13, naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
         assert abs(e - ref) < TOL, (naux, e, ref)
+
+
+@pytest.mark.parametrize("o,v", [(3, 20), (5, 53), (4, 44)])
+def test_epilogue_warp_kernel_variant(engine, o, v):
+    """The experimental kernel (epilogue warps fed through TMEM parking, fpt_triples2.cuh) must give the same E(T)."""
+    x = fb.synth.make_inputs(o, v, naux=16, seed=11)
+    ref = oracle.pt_gemm(*_args(x))
+    engine.upload_conv(o, v, *_args(x))
+    try:
+        engine.set_kernel_variant(2)
+        e2, _ = engine.compute(0, -1)
+    finally:
+        engine.set_kernel_variant(1)
+    e1, _ = engine.compute(0, -1)
+    assert abs(e2 - ref) < TOL and abs(e1 - ref) < TOL, (e1, e2, ref)

@@ -7,7 +7,9 @@ import fermi_jl_b200 as fb
 args = [int(a) for a in sys.argv[1:] if a.lstrip("-").isdigit()]
 shapes = list(zip(args[0::2], args[1::2])) or [(24, 114)]
 eng = fb.Engine(0)
-out = {}
+variant = 1 if "--v1" in sys.argv else 2
+eng.set_kernel_variant(variant)
+out = {"variant": variant}
 for o, v in shapes:
     x = fb.synth.make_inputs(o, v, naux=32)
     eng.upload_conv(o, v, x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
@@ -30,4 +32,4 @@ for o, v in shapes:
     out[f"o{o}v{v}"] = rec
     print(json.dumps(rec), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/gpu_phase.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/gpu_phase_v{variant}.json", "w"), indent=1)

@@ -45,8 +45,10 @@ json.dump(res, open("gpurun_out/c5_result.json", "w"), indent=1)
 if check:
     import oracle
     npair = o * (o + 1) // 2
-    (ib, ie), (tb, te) = fb.host.pair_range_items(o, v, npair - 1, npair)
-    e_part, _ = eng.compute(ib, ie)
+    tb, te = fb.host.pair_range_triplets(o, npair - 1, npair)
+    eng.set_triplet_window(tb, te)
+    e_part, _ = eng.compute(0, -1)
+    eng.set_triplet_window(0, -1)
     try:
         h = {"OVVV": OVVV.cpu().numpy().reshape(-1).reshape((o, v, v, v), order="F"),
              "OOOV": OOOV.cpu().numpy().reshape(-1).reshape((o, o, o, v), order="F"),
