@@ -26,7 +26,7 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df",
+EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -62,7 +62,9 @@ def load_library():
     L.fpt_set_triplet_window.argtypes = [vp, ctypes.c_longlong, ctypes.c_longlong]
     L.fpt_set_item_order.argtypes = [vp, ctypes.c_int]
     L.fpt_shard_items.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
-    for f in EXPORTS[:17]:
+    L.fpt_triples_ao.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
+    L.fpt_upload_ao.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
+    for f in EXPORTS[:19]:
         getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
@@ -118,6 +120,17 @@ class Engine:
         e, st = ctypes.c_double(), Stats()
         self._check(self._L.fpt_triples_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
         return e.value, st.asdict()
+
+    def triples_ao(self, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv):
+        """(T) from the AO-basis ERI tensor and the occupied / virtual MO coefficient blocks (GPU AO -> MO transform)."""
+        ps = [_ptr(a) for a in (T1, T2, AOERI, Co, Cv, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_ao(self._h, nbf, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def upload_ao(self, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, AOERI, Co, Cv, fo, fv)]
+        self._check(self._L.fpt_upload_ao(self._h, nbf, o, v, *[p for p, _ in ps]))
 
     def upload_conv(self, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv):
         ps = [_ptr(a) for a in (T1, T2, OVVV, OOOV, OVOV, fo, fv)]

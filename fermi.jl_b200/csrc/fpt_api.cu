@@ -63,6 +63,8 @@ struct fpt_handle {
     DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out, prof, blocktab;
     // staging for raw inputs
     DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
+    // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
+    DevBuf sCo, sCv, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV;
     Problem prob{};
     bool loaded = false;
     fpt_stats last{};
@@ -189,7 +191,7 @@ extern "C" int fpt_destroy(fpt_handle* h)
     h->peers.clear();
     cudaSetDevice(h->dev);
     DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof, &h->blocktab,
-                      &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
+                      &h->sCo, &h->sCv, &h->aoQ1, &h->aoQ2v, &h->aoQ2o, &h->aoQ3vv, &h->aoQ3vo, &h->aoQ3oo, &h->aoOVVV, &h->aoOOOV, &h->aoOVOV, &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
     for (DevBuf* b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -569,6 +571,95 @@ extern "C" int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const doubl
 {
     auto t0 = std::chrono::steady_clock::now();
     if (fpt_upload_df(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)) return 1;
+    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
+    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (st) *st = h->last;
+    return 0;
+}
+
+// ---- AO -> MO route (replaces Chonky.jl:28-114 for the three blocks the (T) path reads) --------------------------
+static int quarter(fpt_handle* h, double* C, const double* A, const double* B, i64 M, int N, int Q, i64 ldc = 0)
+{
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+    quarter_gemm_kernel<<<grid, 128, 0, h->stream>>>(C, A, B, M, N, Q, ldc ? ldc : M);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// AOERI[mu,nu,rho,sigma] (nbf^4, column-major, chemist notation as in aoints["ERI"]), Co = C[:, occupied] (nbf x o),
+// Cv = C[:, virtual] (nbf x v): the frozen-core / dropped-virtual slices the reference takes in Chonky.jl:38-41.
+extern "C" int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                             const double* Co, const double* Cv, const double* fo, const double* fv)
+{
+    if (!h) return fail("fpt_upload_ao: NULL handle");
+    if (!T1 || !T2 || !AOERI || !Co || !Cv || !fo || !fv) return fail("fpt_upload_ao: NULL array argument");
+    if (nbf < 1 || o < 1 || v < 1 || o + v > nbf) return fail("fpt_upload_ao: invalid dimensions nbf=%d o=%d v=%d", nbf, o, v);
+    CK(cudaSetDevice(h->dev));
+    auto t0 = std::chrono::steady_clock::now();
+    h->loaded = false;
+    h->launches = 0;
+    double h2d = 0.0;
+    const i64 n1 = nbf, n2 = n1 * nbf, n3 = n2 * nbf;
+    const double *dCo, *dCv;
+    if (stage_in(h, h->sCo, Co, (size_t)nbf * o, &dCo, &h2d)) return 1;
+    if (stage_in(h, h->sCv, Cv, (size_t)nbf * v, &dCv, &h2d)) return 1;
+    if (h->aoQ1.ensure((size_t)n3 * o * sizeof(double))) return 1;
+    // quarter 1: Q1[(nu,rho,sigma), i] = sum_mu AOERI[mu,(nu,rho,sigma)] Co[mu,i], streamed over sigma slabs of the AO tensor
+    {
+        const bool on_dev = is_device_ptr(AOERI);
+        int schunk = nbf;
+        if (!on_dev) {
+            const size_t budget = (size_t)512 << 20;
+            schunk = (int)(budget / ((size_t)n3 * sizeof(double)));
+            if (schunk < 1) schunk = 1;
+            if (schunk > nbf) schunk = nbf;
+            if (h->sChunk.ensure((size_t)schunk * n3 * sizeof(double))) return 1;
+        }
+        for (int s0 = 0; s0 < nbf; s0 += schunk) {
+            const int sn = (nbf - s0 < schunk) ? nbf - s0 : schunk;
+            const double* src = AOERI + (size_t)s0 * n3;
+            if (!on_dev) {
+                CK(cudaMemcpyAsync(h->sChunk.p, src, (size_t)sn * n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                h2d += (double)sn * n3 * sizeof(double);
+                src = h->sChunk.d();
+            }
+            // rows (nu,rho,sigma) of this slab are rows [s0*nbf^2, (s0+sn)*nbf^2) of Q1, whose leading dimension is nbf^3
+            if (quarter(h, h->aoQ1.d() + (size_t)s0 * n2, src, dCo, (i64)sn * n2, o, nbf, n3)) return 1;
+        }
+    }
+    // quarter 2: contract nu.  Q2v[(rho,sigma,i), a], Q2o[(rho,sigma,i), j]
+    if (h->aoQ2v.ensure((size_t)n2 * o * v * sizeof(double))) return 1;
+    if (h->aoQ2o.ensure((size_t)n2 * o * o * sizeof(double))) return 1;
+    if (quarter(h, h->aoQ2v.d(), h->aoQ1.d(), dCv, n2 * o, v, nbf)) return 1;
+    if (quarter(h, h->aoQ2o.d(), h->aoQ1.d(), dCo, n2 * o, o, nbf)) return 1;
+    // quarter 3: contract rho.  Q3vv[(sigma,i,a), b], Q3vo[(sigma,i,a), j], Q3oo[(sigma,i,j), k]
+    if (h->aoQ3vv.ensure((size_t)n1 * o * v * v * sizeof(double))) return 1;
+    if (h->aoQ3vo.ensure((size_t)n1 * o * v * o * sizeof(double))) return 1;
+    if (h->aoQ3oo.ensure((size_t)n1 * o * o * o * sizeof(double))) return 1;
+    if (quarter(h, h->aoQ3vv.d(), h->aoQ2v.d(), dCv, n1 * o * v, v, nbf)) return 1;
+    if (quarter(h, h->aoQ3vo.d(), h->aoQ2v.d(), dCo, n1 * o * v, o, nbf)) return 1;
+    if (quarter(h, h->aoQ3oo.d(), h->aoQ2o.d(), dCo, n1 * o * o, o, nbf)) return 1;
+    // quarter 4: contract sigma with Cv -> OVVV[i,a,b,c], OVOV[i,a,j,b], OOOV[i,j,k,a] in the reference's layouts
+    if (h->aoOVVV.ensure((size_t)o * v * v * v * sizeof(double))) return 1;
+    if (h->aoOVOV.ensure((size_t)o * v * o * v * sizeof(double))) return 1;
+    if (h->aoOOOV.ensure((size_t)o * o * o * v * sizeof(double))) return 1;
+    if (quarter(h, h->aoOVVV.d(), h->aoQ3vv.d(), dCv, (i64)o * v * v, v, nbf)) return 1;
+    if (quarter(h, h->aoOVOV.d(), h->aoQ3vo.d(), dCv, (i64)o * v * o, v, nbf)) return 1;
+    if (quarter(h, h->aoOOOV.d(), h->aoQ3oo.d(), dCv, (i64)o * o * o, v, nbf)) return 1;
+    const int ao_launches = h->launches;
+    if (fpt_upload_conv(h, o, v, T1, T2, h->aoOVVV.d(), h->aoOOOV.d(), h->aoOVOV.d(), fo, fv)) return 1;
+    h->launches += ao_launches;
+    h->last.h2d_bytes += h2d;
+    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+extern "C" int fpt_triples_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                              const double* Co, const double* Cv, const double* fo, const double* fv, double* Et, fpt_stats* st)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    if (fpt_upload_ao(h, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv)) return 1;
     if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
     h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (st) *st = h->last;

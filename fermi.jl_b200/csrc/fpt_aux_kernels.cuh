@@ -248,4 +248,56 @@ __global__ void __launch_bounds__(128) df_gemm_kernel(Problem P, double* out, co
             }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K5: one quarter of the AO -> MO integral transformation (Chonky.jl:28-114 computes OOOV/OVOV/OVVV with four-index
+// @tensoropt contractions on the CPU).  C[m + ldc*n] = sum_q A[q + Q*m] * B[q + Q*n]: both operands have the contracted AO index
+// fastest and the result has the surviving indices of A fastest, so chaining four calls rotates
+// (mu nu rho sigma) -> (nu rho sigma | i) -> (rho sigma i | x) -> (sigma i x | y) -> (i x y | z): every quarter contracts a
+// contiguous index and the last one lands in the reference's own column-major [i,x,y,z] layout.  Same DMMA.8x8x4 tiling
+// as K3 (64x64 CTA tile, fragments from global).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) quarter_gemm_kernel(double* __restrict__ C, const double* __restrict__ A,
+                                                           const double* __restrict__ B, i64 M, int N, int Q, i64 ldc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = lane >> 2, kk = lane & 3;
+    const i64 m0 = (i64)blockIdx.x * 64 + (warp >> 1) * 32;
+    const int n0 = blockIdx.y * 64 + (warp & 1) * 32;
+    const double* ap[4];
+    const double* bp[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        i64 m = m0 + 8 * t + r; if (m >= M) m = M - 1;
+        ap[t] = A + (i64)Q * m;
+        int n = n0 + 8 * t + r; if (n >= N) n = N - 1;
+        bp[t] = B + (i64)Q * n;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < Q; k0 += 4) {
+        const int k = k0 + kk;
+        const bool ok = k < Q;
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { a[t] = ok ? __ldg(ap[t] + k) : 0.0; b[t] = ok ? __ldg(bp[t] + k) : 0.0; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const i64 m = m0 + 8 * i + r;
+                const int n = n0 + 8 * j + 2 * kk + e;
+                if (m < M && n < N) C[m + ldc * n] = acc[i][j][e];
+            }
+}
+
 }  // namespace fpt

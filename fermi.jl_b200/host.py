@@ -77,9 +77,29 @@ class IntegralHelper:
     For a DF helper (eri_type in {"RIFIT","JKFIT"}, ERITypes.jl:19) the 4-index keys are *not* materialised
     (the reference would do so lazily, DFERI.jl:88-180); the B200 path consumes BOO/BOV/BVV directly."""
 
-    def __init__(self, cache: dict | None = None, eri_type: str = "Chonky"):
+    def __init__(self, cache: dict | None = None, eri_type: str = "Chonky", aoints: "IntegralHelper | None" = None,
+                 C=None, ndocc: int | None = None, drop_occ: int = 0, drop_vir: int = 0):
+        """`aoints` (an AO-basis helper holding "ERI"), `C` (MO coefficients, nbf x nmo), `ndocc`, `drop_occ`, `drop_vir`:
+        what the reference's dense helper uses to build MO blocks on demand (Chonky.jl:28-114: I.orbitals.C,
+        I.molecule.Nα, Options drop_occ / drop_vir).  With them and no cached "OVVV" the B200 path transforms on the GPU."""
         self.cache = dict(cache or {})
         self.eri_type = eri_type
+        self.aoints = aoints
+        self.C = C
+        self.ndocc = ndocc
+        self.drop_occ = drop_occ
+        self.drop_vir = drop_vir
+
+    @property
+    def has_ao_route(self) -> bool:
+        return (self.eri_type == "Chonky" and self.aoints is not None and "ERI" in self.aoints and self.C is not None
+                and self.ndocc is not None)
+
+    def orbital_blocks(self):
+        """(Co, Cv) = C[:, (1+drop_occ):ndocc], C[:, (ndocc+1):(nbf-drop_vir)] (Chonky.jl:38-41, 1-based there)."""
+        C = np.asarray(self.C)
+        nmo = C.shape[1]
+        return (np.asfortranarray(C[:, self.drop_occ:self.ndocc]), np.asfortranarray(C[:, self.ndocc:nmo - self.drop_vir]))
 
     @property
     def is_df(self) -> bool:
@@ -134,6 +154,12 @@ class RCCSDpT:
             BOO, BOV, BVV = moints["BOO"], moints["BOV"], moints["BVV"]
             naux = BOV.shape[0]
             Et, st = eng.triples_df(o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)
+        elif "OVVV" not in moints and moints.has_ao_route:
+            # the reference would now run compute_OVVV!/OOOV!/OVOV! on the CPU (Chonky.jl:28-114); the AO tensor goes to the GPU
+            Co, Cv = moints.orbital_blocks()
+            if Co.shape[1] != o or Cv.shape[1] != v:
+                raise FermiException(f"orbital blocks ({Co.shape[1]} occupied, {Cv.shape[1]} virtual) do not match T1 {(o, v)}")
+            Et, st = eng.triples_ao(Co.shape[0], o, v, T1, T2, moints.aoints["ERI"], Co, Cv, fo, fv)
         else:
             Et, st = eng.triples_conv(o, v, T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv)
         t = time.perf_counter() - t0

@@ -121,3 +121,23 @@ def load(path: str) -> PTInputs:
     return PTInputs(o, v, naux, arrs["T1"], arrs["T2"], arrs["fo"], arrs["fv"],
                     arrs.get("BOO", z(0, o, o)), arrs.get("BOV", z(0, o, v)), arrs.get("BVV", z(0, v, v)),
                     arrs.get("OVVV"), arrs.get("OOOV"), arrs.get("OVOV"), seed=hdr.get("seed", 0))
+
+
+def make_ao_inputs(nbf: int, ndocc: int, drop_occ: int = 0, drop_vir: int = 0, naux: int = 24, seed: int = 20240517):
+    """Synthetic inputs of the AO route: an 8-fold symmetric AO ERI tensor (contracted from one symmetric factor), an
+    orthogonal MO coefficient matrix, and amplitudes / orbital energies for the active space
+    o = ndocc - drop_occ, v = nbf - ndocc - drop_vir.  Returns (AOERI, C, T1, T2, fo, fv), Fortran-ordered."""
+    rng = np.random.default_rng(seed)
+    o, v = ndocc - drop_occ, nbf - ndocc - drop_vir
+    ts, bs = default_scales(o, v, naux)
+    B = bs * rng.standard_normal((naux, nbf, nbf))
+    B = 0.5 * (B + B.transpose(0, 2, 1))
+    F = np.asfortranarray
+    AOERI = F(np.einsum("Qmn,Qrs->mnrs", B, B, optimize=True))
+    C, _ = np.linalg.qr(rng.standard_normal((nbf, nbf)))
+    T1 = F(ts * rng.standard_normal((o, v)))
+    T2 = ts * rng.standard_normal((o, o, v, v))
+    T2 = F(0.5 * (T2 + T2.transpose(1, 0, 3, 2)))
+    fo = -np.sort(rng.uniform(0.3, 2.0, o))[::-1].copy()
+    fv = np.sort(rng.uniform(0.1, 3.0, v))
+    return AOERI, F(C), T1, T2, fo, fv

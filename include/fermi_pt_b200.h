@@ -66,7 +66,17 @@ int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, cons
                    const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
                    fpt_stats* stats);
 
-/* Staged form of the two calls above (used for sharded multi-GPU runs and kernel-only timing):
+/* Same, from the AO-basis integrals: replaces the reference's dense AO -> MO contractions for the three blocks the (T)
+ * path reads (Chonky.jl:28-48 OOOV, :72-92 OVOV, :94-114 OVVV) with four quarter transformations on the GPU, so the o*v^3
+ * block never exists on the host.  AOERI = aoints["ERI"], nbf^4 column-major (mu|nu rho sigma chemist order as stored by
+ * the reference); Co = C[:, (1+drop_occ):ndocc] (nbf x o) and Cv = C[:, (ndocc+1):(nbf-drop_vir)] (nbf x v), the slices
+ * Chonky.jl:38-41 takes. */
+int fpt_triples_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                   const double* Co, const double* Cv, const double* fo, const double* fv, double* Et, fpt_stats* stats);
+int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                  const double* Co, const double* Cv, const double* fo, const double* fv);
+
+/* Staged form of the calls above (used for sharded multi-GPU runs and kernel-only timing):
  * upload = copy + layout prep, operands stay resident on the GPU; compute = fused kernel over the item range
  * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T). */
 int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,

@@ -208,3 +208,17 @@ def pt_spinorbital_bruteforce(T1, T2, OVVV, OOOV, OVOV, fo, fv):
     D = (eo[:, None, None, None, None, None] + eo[None, :, None, None, None, None] + eo[None, None, :, None, None, None]
          - ev[None, None, None, :, None, None] - ev[None, None, None, None, :, None] - ev[None, None, None, None, None, :])
     return float(np.sum(C * (C + S) / D) / 36.0)
+
+
+def mo_blocks_from_ao(AOERI, C, ndocc, drop_occ=0, drop_vir=0):
+    """The reference's dense AO -> MO contractions for the three blocks the (T) path reads -- transcription of
+    src/Core/Integrals/ROIntegrals/Chonky.jl: compute_OOOV! (:28-48), compute_OVOV! (:72-92), compute_OVVV! (:94-114).
+    o = (1+core):ndocc, v = (ndocc+1):(nbf-inac) there (1-based); returns (OVVV, OOOV, OVOV), Fortran-ordered."""
+    nmo = C.shape[1]
+    Co = C[:, drop_occ:ndocc]
+    Cv = C[:, ndocc:nmo - drop_vir]
+    F = np.asfortranarray
+    OOOV = np.einsum("mnrs,mi,nj,rk,sa->ijka", AOERI, Co, Co, Co, Cv, optimize=True)   # :45
+    OVOV = np.einsum("mnrs,mi,na,rj,sb->iajb", AOERI, Co, Cv, Co, Cv, optimize=True)   # :89
+    OVVV = np.einsum("mnrs,mi,na,rb,sc->iabc", AOERI, Co, Cv, Cv, Cv, optimize=True)   # :111
+    return F(OVVV), F(OOOV), F(OVOV)

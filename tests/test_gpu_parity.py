@@ -191,3 +191,24 @@ def test_epilogue_warp_kernel_variant(engine, o, v):
         engine.set_kernel_variant(1)
     e1, _ = engine.compute(0, -1)
     assert abs(e2 - ref) < TOL and abs(e1 - ref) < TOL, (e1, e2, ref)
+
+
+@pytest.mark.parametrize("nbf,ndocc,drop_occ,drop_vir", [(9, 3, 0, 0), (14, 4, 1, 2), (30, 6, 1, 0), (47, 5, 0, 3)])
+def test_ao_route_matches_oracle(engine, nbf, ndocc, drop_occ, drop_vir):
+    """fpt_triples_ao (GPU quarter transforms) against the oracle fed with the einsum transcription of
+    Chonky.jl:28-114, including frozen-core / dropped-virtual slices and AO dimensions that are not multiples of 4."""
+    from oracle import pt_numpy as PN
+    AO, C, T1, T2, fo, fv = fb.synth.make_ao_inputs(nbf, ndocc, drop_occ, drop_vir, seed=5)
+    OVVV, OOOV, OVOV = PN.mo_blocks_from_ao(AO, C, ndocc, drop_occ, drop_vir)
+    ref = oracle.pt_gemm(T1, T2, OVVV, OOOV, OVOV, fo, fv)
+    o, v = T1.shape
+    Co, Cv = np.asfortranarray(C[:, drop_occ:ndocc]), np.asfortranarray(C[:, ndocc:nbf - drop_vir])
+    e, st = engine.triples_ao(nbf, o, v, T1, T2, AO, Co, Cv, fo, fv)
+    assert abs(e - ref) < TOL, (e, ref)
+    # through the interface mirror: an IntegralHelper without cached MO blocks but with the AO helper and orbitals
+    ao = fb.IntegralHelper({"ERI": AO})
+    moints = fb.IntegralHelper({"Fii": fo, "Faa": fv}, aoints=ao, C=C, ndocc=ndocc, drop_occ=drop_occ, drop_vir=drop_vir)
+    res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, T1, T2), moints, fb.B200())
+    assert abs(res.correction - ref) < TOL
+    with pytest.raises(fb.FermiException):
+        engine.triples_ao(nbf, o, nbf, T1, T2, AO, Co, Cv, fo, fv)      # o + v > nbf

@@ -86,3 +86,21 @@ def test_synth_symmetries_and_dump_roundtrip(tmp_path):
     y = fb.synth.load(str(tmp_path / "d"))
     for k in ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv", "BOO", "BOV", "BVV"):
         assert np.array_equal(getattr(x, k), getattr(y, k))
+
+
+def test_ao_to_mo_transcription_against_factorised_form():
+    """oracle.pt_numpy.mo_blocks_from_ao (Chonky.jl:28-114) vs. transforming the DF-like factor first."""
+    import fermi_jl_b200 as fb
+    from oracle import pt_numpy as PN
+    nbf, ndocc, dc, dv = 12, 4, 1, 2
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((7, nbf, nbf)); B = 0.5 * (B + B.transpose(0, 2, 1))
+    AO = np.einsum("Qmn,Qrs->mnrs", B, B)
+    C, _ = np.linalg.qr(rng.standard_normal((nbf, nbf)))
+    Co, Cv = C[:, dc:ndocc], C[:, ndocc:nbf - dv]
+    Bov = np.einsum("Qmn,mi,na->Qia", B, Co, Cv); Bvv = np.einsum("Qmn,ma,nb->Qab", B, Cv, Cv); Boo = np.einsum("Qmn,mi,nj->Qij", B, Co, Co)
+    OVVV, OOOV, OVOV = PN.mo_blocks_from_ao(AO, C, ndocc, dc, dv)
+    assert np.abs(OVVV - np.einsum("Qia,Qbc->iabc", Bov, Bvv)).max() < 1e-12
+    assert np.abs(OOOV - np.einsum("Qij,Qka->ijka", Boo, Bov)).max() < 1e-12
+    assert np.abs(OVOV - np.einsum("Qia,Qjb->iajb", Bov, Bov)).max() < 1e-12
+    assert OVVV.shape == (3, 6, 6, 6) and OVVV.flags.f_contiguous

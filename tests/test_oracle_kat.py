@@ -82,3 +82,22 @@ def test_gpu_matches_reference_test_value_631g(engine):
     res = fb.RCCSDpT(ccsd, moints, fb.B200())
     assert abs(res.energy - REF2_ECCSDT) < 1e-9
     assert abs(res.correction - float(G2["e_t"])) < 1e-12
+
+
+# ---- AO route on the real molecule: AO integrals + RHF orbitals of the STO-3G run -> GPU AO->MO transform -> (T) ----------
+def test_stored_ao_tensor_reproduces_stored_mo_blocks():
+    OVVV, OOOV, OVOV = P.mo_blocks_from_ao(G["AOERI"], G["C"], ndocc=5)      # Chonky.jl:28-114 transcription
+    assert np.abs(OVVV - G["OVVV"]).max() < 1e-13 and np.abs(OOOV - G["OOOV"]).max() < 1e-13
+    assert np.abs(OVOV - G["OVOV"]).max() < 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_ao_route_matches_reference_known_answer(engine):
+    import fermi_jl_b200 as fb
+    a = _args()
+    ao = fb.IntegralHelper({"ERI": np.asfortranarray(G["AOERI"])})
+    moints = fb.IntegralHelper({"Fii": a[5], "Faa": a[6]}, aoints=ao, C=np.asfortranarray(G["C"]), ndocc=5)
+    ccsd = fb.RCCSD(0.0, REF_ECORR, float(G["e_rhf"]) + float(G["e_corr"]), a[0], a[1])
+    res = fb.RCCSDpT(ccsd, moints, fb.B200())
+    assert abs(res.correction - REF_ET) < 5e-11
+    assert abs(res.energy - REF_ECCSDT) < 5e-11
