@@ -16,7 +16,8 @@ module FermiB200
 
 using Fermi
 using Fermi.Options
-using Fermi.Integrals: IntegralHelper, AbstractERI, AbstractDFERI
+using Fermi.Integrals: IntegralHelper, AbstractERI, AbstractDFERI, Chonky
+using Fermi.Orbitals: AtomicOrbitals
 using Fermi.Orbitals: AbstractRestrictedOrbitals
 import Fermi.CoupledCluster: RCCSD, RCCSDpT, RpTAlgorithm, get_rpt_alg, ijk, ijk2, abc
 import Fermi: output, Molecule, FermiException
@@ -98,6 +99,20 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
                         (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                          Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
                         handle(), o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, Et, st))
+        elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV")
+            # dense AO integrals and no cached (ov|vv): instead of compute_OVVV!/OOOV!/OVOV! on the CPU (Chonky.jl:28-114) hand
+            # the AO tensor and the orbital blocks over; the AO helper is built exactly as ROIntegrals.jl:1-7 builds it
+            aoorbs = AtomicOrbitals(moints.molecule, moints.basis)
+            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=moints.basis, eri_type=moints.eri_type)
+            AOERI = dense(aoints["ERI"])
+            C = moints.orbitals.C
+            core = Options.get("drop_occ"); inac = Options.get("drop_vir")
+            ndocc = moints.molecule.Nα; nbf = size(C, 1)
+            Co = dense(C[:, (1+core):ndocc]); Cv = dense(C[:, (ndocc+1):(nbf-inac)])       # Chonky.jl:38-41
+            check(ccall((:fpt_triples_ao, LIB), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                         Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
+                        handle(), nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv, Et, st))
         else
             OVVV = dense(moints["OVVV"]); OOOV = dense(moints["OOOV"]); OVOV = dense(moints["OVOV"])
             check(ccall((:fpt_triples_conv, LIB), Cint,
