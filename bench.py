@@ -109,7 +109,8 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
     """Time the CPU restatement (oracle.pt_gemm, OpenMP) on a bounded sample of trailing (i,j) pairs."""
     import oracle
     import fermi_jl_b200 as fb
-    threads = oracle.num_threads()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    threads = max(oracle.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     per_trip = algorithmic_flops(o, v, 1) / (threads * 12e9)      # guess: ~12 GFLOP/s per core
     want = max(1, int(budget_s / max(per_trip, 1e-9)))
     npair = o * (o + 1) // 2
@@ -121,7 +122,7 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
             break
     tb, te = fb.host.pair_range_triplets(o, pr0, npair)
     t0 = time.perf_counter()
-    e = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te)
+    e = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te, nthreads=threads)
     dt = time.perf_counter() - t0
     # zero-weight i=j=k triplets inside the range do no work
     ntr = 0
@@ -297,7 +298,7 @@ def main():
                 "peak_source": "live DMMA.8x8x4 register-resident stream on this GPU (fpt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "kernel_ms_per_launch": kern_ms}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU baseline is a rank-0, N = 1 measurement
             s = cpu_reference_sample(x, o, v, budget_s=args.cpu_budget)
             eng.set_triplet_window(*s["triplet_range"])   # the same triplets on the GPU
             e_s, _ = eng.compute(0, -1)
