@@ -11,6 +11,7 @@ from . import build as _build
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _LIB = None
+DEFAULT_KERNEL_VARIANT = 1   # mirrors fpt_handle::kernel_variant in csrc/fpt_api.cu
 
 
 class FermiException(Exception):
@@ -38,7 +39,7 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("FERMI_PT_B200_LIB", _build.LIB)   # diagnostics: a variant build of the same ABI
     if not os.path.exists(path):
         raise FermiException(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
     L = ctypes.CDLL(path)
@@ -175,6 +176,10 @@ class Engine:
         self._check(self._L.fpt_set_kernel_variant(self._h, variant))
         self._variant = variant
 
+    @property
+    def kernel_variant(self) -> int:
+        return getattr(self, "_variant", DEFAULT_KERNEL_VARIANT)
+
     def set_profiling(self, on: bool):
         self._check(self._L.fpt_set_profiling(self._h, 1 if on else 0))
 
@@ -183,11 +188,11 @@ class Engine:
         self._check(self._L.fpt_last_profile(self._h, buf))
         names = ["wait_item", "zero", "kloops", "rmw", "energy", "total", "token_wait", "rmw_pure", "full_wait", "ov_wait",
                  "bar_pre_energy", "bar_post_energy"]
-        if getattr(self, "_variant", 1) == 2:
+        if self.kernel_variant == 2:
             names = ["wait_item", "setup", "kloops", "park", "energy", "total", "park_wait", "wdone_wait", "full_wait", "ov_wait",
                      "_", "bar_post_energy"]
         out = dict(zip(names, list(buf)[:12]))
-        if getattr(self, "_variant", 1) == 2:
+        if self.kernel_variant == 2:
             enames = ["wait_item", "wfree_wait", "park_full_wait", "set_barrier", "batches", "total"]
             out.update({"g3_" + k: v for k, v in zip(enames, list(buf)[12:18])})   # "g3_" = the epilogue warp of quarter 0 here
         else:
