@@ -27,7 +27,7 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao",
+EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao", "fpt_triples_ao_sparse", "fpt_upload_ao_sparse",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -65,7 +65,10 @@ def load_library():
     L.fpt_shard_items.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
     L.fpt_triples_ao.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
     L.fpt_upload_ao.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
-    for f in EXPORTS[:19]:
+    L.fpt_triples_ao_sparse.argtypes = ([vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_longlong, vp, ctypes.c_int]
+                                        + [vp] * 5 + [_dp, ctypes.POINTER(Stats)])
+    L.fpt_upload_ao_sparse.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_longlong, vp, ctypes.c_int] + [vp] * 5
+    for f in EXPORTS[:21]:
         getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
@@ -127,6 +130,22 @@ class Engine:
         ps = [_ptr(a) for a in (T1, T2, AOERI, Co, Cv, fo, fv)]
         e, st = ctypes.c_double(), Stats()
         self._check(self._L.fpt_triples_ao(self._h, nbf, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def triples_ao_sparse(self, nbf, o, v, T1, T2, indexes, data, Co, Cv, fo, fv):
+        """(T) from the sparse AO list: `indexes` (nint, 4) zero-based int16/int32, `data` (nint,) (FermiSparse fields)."""
+        idx = np.ascontiguousarray(indexes)
+        if idx.dtype not in (np.int16, np.int32):
+            idx = idx.astype(np.int32)
+        if idx.ndim != 2 or idx.shape[1] != 4 or idx.shape[0] != len(data):
+            raise FermiException(f"invalid sparse ERI list: indexes {idx.shape}, data {np.shape(data)}")
+        vals = np.ascontiguousarray(data, dtype=np.float64)
+        ps = [_ptr(a) for a in (T1, T2)]
+        qs = [_ptr(a) for a in (Co, Cv, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_ao_sparse(self._h, nbf, o, v, ps[0][0], ps[1][0], len(vals), ctypes.c_void_p(idx.ctypes.data),
+                                                  idx.dtype.itemsize, ctypes.c_void_p(vals.ctypes.data), *[p for p, _ in qs],
+                                                  ctypes.byref(e), ctypes.byref(st)))
         return e.value, st.asdict()
 
     def upload_ao(self, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv):

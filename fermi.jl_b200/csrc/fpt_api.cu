@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -64,7 +65,7 @@ struct fpt_handle {
     // staging for raw inputs
     DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
     // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
-    DevBuf sCo, sCv, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV;
+    DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV;
     Problem prob{};
     bool loaded = false;
     fpt_stats last{};
@@ -191,7 +192,7 @@ extern "C" int fpt_destroy(fpt_handle* h)
     h->peers.clear();
     cudaSetDevice(h->dev);
     DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof, &h->blocktab,
-                      &h->sCo, &h->sCv, &h->aoQ1, &h->aoQ2v, &h->aoQ2o, &h->aoQ3vv, &h->aoQ3vo, &h->aoQ3oo, &h->aoOVVV, &h->aoOOOV, &h->aoOVOV, &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
+                      &h->sCo, &h->sCv, &h->aoDense, &h->sIdx, &h->sVals, &h->aoQ1, &h->aoQ2v, &h->aoQ2o, &h->aoQ3vv, &h->aoQ3vo, &h->aoQ3oo, &h->aoOVVV, &h->aoOOOV, &h->aoOVOV, &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
     for (DevBuf* b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -652,6 +653,64 @@ extern "C" int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double*
     h->launches += ao_launches;
     h->last.h2d_bytes += h2d;
     h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+// Sparse AO list (the reference's default conventional container): `nint` symmetry-unique integrals, vals[z] = (mu nu|rho sigma)
+// with zero-based indices idx[4z..4z+3] stored as `index_bytes`-wide integers (2: Vector{NTuple{4,Int16}}, 4: Int32).
+extern "C" int fpt_upload_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
+                                    const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
+                                    const double* fo, const double* fv)
+{
+    if (!h) return fail("fpt_upload_ao_sparse: NULL handle");
+    if (!T1 || !T2 || !Co || !Cv || !fo || !fv || (nint > 0 && (!idx || !vals))) return fail("fpt_upload_ao_sparse: NULL array argument");
+    if (nbf < 1 || o < 1 || v < 1 || o + v > nbf || nint < 0) return fail("fpt_upload_ao_sparse: invalid dimensions nbf=%d o=%d v=%d nint=%lld", nbf, o, v, nint);
+    if (index_bytes != 2 && index_bytes != 4) return fail("fpt_upload_ao_sparse: index_bytes must be 2 or 4, got %d", index_bytes);
+    if (index_bytes == 2 && nbf > 32767) return fail("fpt_upload_ao_sparse: nbf=%d does not fit 16-bit indices", nbf);
+    CK(cudaSetDevice(h->dev));
+    auto t0 = std::chrono::steady_clock::now();
+    const size_t n4 = (size_t)nbf * nbf * nbf * nbf;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (n4 * sizeof(double) > free_b + h->aoDense.cap)
+        return fail("fpt_upload_ao_sparse: the dense AO tensor (%.1f GB for nbf=%d) does not fit the device", n4 * 8e-9, nbf);
+    if (h->aoDense.ensure(n4 * sizeof(double))) return 1;
+    CK(cudaMemsetAsync(h->aoDense.p, 0, n4 * sizeof(double), h->stream));
+    double h2d = 0.0;
+    if (nint > 0) {
+        const bool idx_dev = is_device_ptr(idx);
+        const void* didx = idx;
+        if (!idx_dev) {
+            if (h->sIdx.ensure((size_t)nint * 4 * index_bytes)) return 1;
+            CK(cudaMemcpyAsync(h->sIdx.p, idx, (size_t)nint * 4 * index_bytes, cudaMemcpyHostToDevice, h->stream));
+            h2d += (double)nint * 4 * index_bytes;
+            didx = h->sIdx.p;
+        }
+        const double* dvals;
+        if (stage_in(h, h->sVals, vals, (size_t)nint, &dvals, &h2d)) return 1;
+        const int grid = (int)std::min<long long>((nint + 255) / 256, 148LL * 32);
+        if (index_bytes == 2)
+            expand_sparse_eri_kernel<short><<<grid, 256, 0, h->stream>>>(h->aoDense.d(), (const short*)didx, dvals, nint, nbf);
+        else
+            expand_sparse_eri_kernel<int><<<grid, 256, 0, h->stream>>>(h->aoDense.d(), (const int*)didx, dvals, nint, nbf);
+        CK(cudaGetLastError());
+    }
+    if (fpt_upload_ao(h, nbf, o, v, T1, T2, h->aoDense.d(), Co, Cv, fo, fv)) return 1;
+    h->launches += 1;
+    h->last.h2d_bytes += h2d;
+    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+extern "C" int fpt_triples_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
+                                     const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
+                                     const double* fo, const double* fv, double* Et, fpt_stats* st)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    if (fpt_upload_ao_sparse(h, nbf, o, v, T1, T2, nint, idx, index_bytes, vals, Co, Cv, fo, fv)) return 1;
+    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
+    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (st) *st = h->last;
     return 0;
 }
 

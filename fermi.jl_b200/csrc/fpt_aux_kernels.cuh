@@ -300,4 +300,30 @@ __global__ void __launch_bounds__(128) quarter_gemm_kernel(double* __restrict__ 
             }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K6: sparse AO integral list -> dense AO tensor.  The reference's default AO container is a list of the symmetry-unique
+// non-negligible (mu nu|rho sigma) with zero-based index 4-tuples (FermiSparse, Arrays.jl:9-12; filled by
+// AtomicIntegrals.jl:48-52); its MO builders scatter every entry to its up-to-8 permutational images while contracting
+// the first index (Sparse.jl:78-151, 236-313, 316-393).  Here the images are written into a zero-initialised dense tensor
+// (plain stores: images of one entry that coincide carry the same value), which then feeds the K5 chain.
+// ---------------------------------------------------------------------------------------------------
+template <typename Ti>
+__global__ void expand_sparse_eri_kernel(double* __restrict__ AO, const Ti* __restrict__ idx, const double* __restrict__ vals,
+                                         i64 nint, int nbf)
+{
+    const i64 n1 = nbf, n2 = n1 * nbf, n3 = n2 * nbf;
+    for (i64 z = (i64)blockIdx.x * blockDim.x + threadIdx.x; z < nint; z += (i64)gridDim.x * blockDim.x) {
+        const i64 m = idx[4 * z], n = idx[4 * z + 1], r = idx[4 * z + 2], s = idx[4 * z + 3];
+        const double V = vals[z];
+        AO[m + n1 * n + n2 * r + n3 * s] = V;
+        AO[n + n1 * m + n2 * r + n3 * s] = V;
+        AO[m + n1 * n + n2 * s + n3 * r] = V;
+        AO[n + n1 * m + n2 * s + n3 * r] = V;
+        AO[r + n1 * s + n2 * m + n3 * n] = V;
+        AO[s + n1 * r + n2 * m + n3 * n] = V;
+        AO[r + n1 * s + n2 * n + n3 * m] = V;
+        AO[s + n1 * r + n2 * n + n3 * m] = V;
+    }
+}
+
 }  // namespace fpt

@@ -61,6 +61,13 @@ def get_rpt_alg():
 
 # ---- inputs ------------------------------------------------------------------------------------------------
 @dataclass
+class FermiSparse:
+    """Backend/Arrays.jl:9-12: `indexes::Vector{NTuple{N,Ti}}` (zero-based, here an (nint, N) integer array) and `data`."""
+    indexes: np.ndarray
+    data: np.ndarray
+
+
+@dataclass
 class RCCSD:
     """RCCSD.jl:61-69."""
     guessenergy: float
@@ -94,6 +101,12 @@ class IntegralHelper:
     def has_ao_route(self) -> bool:
         return (self.eri_type == "Chonky" and self.aoints is not None and "ERI" in self.aoints and self.C is not None
                 and self.ndocc is not None)
+
+    @property
+    def ao_is_sparse(self) -> bool:
+        """AO helper of type SparseERI: aoints["ERI"] is a FermiSparse (Arrays.jl:9-12) -- here any object with
+        `.indexes` ((nint,4) zero-based) and `.data` ((nint,))."""
+        return self.has_ao_route and hasattr(self.aoints["ERI"], "indexes")
 
     def orbital_blocks(self):
         """(Co, Cv) = C[:, (1+drop_occ):ndocc], C[:, (ndocc+1):(nbf-drop_vir)] (Chonky.jl:38-41, 1-based there)."""
@@ -159,7 +172,11 @@ class RCCSDpT:
             Co, Cv = moints.orbital_blocks()
             if Co.shape[1] != o or Cv.shape[1] != v:
                 raise FermiException(f"orbital blocks ({Co.shape[1]} occupied, {Cv.shape[1]} virtual) do not match T1 {(o, v)}")
-            Et, st = eng.triples_ao(Co.shape[0], o, v, T1, T2, moints.aoints["ERI"], Co, Cv, fo, fv)
+            if moints.ao_is_sparse:    # the reference's default AO container (Sparse.jl:78-151,236-393 on the CPU)
+                eri = moints.aoints["ERI"]
+                Et, st = eng.triples_ao_sparse(Co.shape[0], o, v, T1, T2, eri.indexes, eri.data, Co, Cv, fo, fv)
+            else:
+                Et, st = eng.triples_ao(Co.shape[0], o, v, T1, T2, moints.aoints["ERI"], Co, Cv, fo, fv)
         else:
             Et, st = eng.triples_conv(o, v, T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv)
         t = time.perf_counter() - t0

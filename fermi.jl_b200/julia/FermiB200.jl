@@ -99,6 +99,21 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
                         (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                          Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
                         handle(), o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, Et, st))
+        elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV") && get(ENV, "FERMI_PT_B200_AO", "sparse") == "sparse"
+            # default conventional route of the reference: the MO helper is Chonky, its AO helper holds the *sparse* list
+            # (IntegralHelper.jl:88-90); instead of Sparse.jl:78-151,236-393 on the CPU the list itself goes to the GPU
+            aoorbs = AtomicOrbitals(moints.molecule, moints.basis)
+            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=moints.basis, eri_type=Fermi.Integrals.SparseERI())
+            eri = aoints["ERI"]                                   # FermiSparse{Float64,Int16,4}: .indexes (zero-based), .data
+            C = moints.orbitals.C
+            core = Options.get("drop_occ"); inac = Options.get("drop_vir")
+            ndocc = moints.molecule.Nα; nbf = size(C, 1)
+            Co = dense(C[:, (1+core):ndocc]); Cv = dense(C[:, (ndocc+1):(nbf-inac)])
+            Ti = eltype(eltype(eri.indexes))
+            check(ccall((:fpt_triples_ao_sparse, LIB), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Clonglong, Ptr{Cvoid}, Cint, Ptr{Cdouble},
+                         Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
+                        handle(), nbf, o, v, T1, T2, length(eri.data), eri.indexes, sizeof(Ti), eri.data, Co, Cv, fo, fv, Et, st))
         elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV")
             # dense AO integrals and no cached (ov|vv): instead of compute_OVVV!/OOOV!/OVOV! on the CPU (Chonky.jl:28-114) hand
             # the AO tensor and the orbital blocks over; the AO helper is built exactly as ROIntegrals.jl:1-7 builds it

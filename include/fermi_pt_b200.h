@@ -76,6 +76,19 @@ int fpt_triples_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const
 int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
                   const double* Co, const double* Cv, const double* fo, const double* fv);
 
+/* Same, from the reference's default AO container for conventional integrals: the sparse list of symmetry-unique
+ * (mu nu|rho sigma) values (FermiSparse, Arrays.jl:9-12, built in AtomicIntegrals.jl:48-52) that Sparse.jl:78-151 (OOOV),
+ * :236-313 (OVOV), :316-393 (OVVV) scatter and contract on the CPU.  vals = aoints["ERI"].data (nint doubles), idx =
+ * aoints["ERI"].indexes: nint zero-based 4-tuples stored contiguously as index_bytes-wide signed integers (2 for
+ * Vector{NTuple{4,Int16}}, 4 for Int32).  The list is expanded on the GPU into the dense tensor (nbf^4 doubles must fit the
+ * device), then the fpt_triples_ao path runs. */
+int fpt_triples_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
+                          const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
+                          const double* fo, const double* fv, double* Et, fpt_stats* stats);
+int fpt_upload_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
+                         const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
+                         const double* fo, const double* fv);
+
 /* Staged form of the calls above (used for sharded multi-GPU runs and kernel-only timing):
  * upload = copy + layout prep, operands stay resident on the GPU; compute = fused kernel over the item range
  * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T). */

@@ -222,3 +222,56 @@ def mo_blocks_from_ao(AOERI, C, ndocc, drop_occ=0, drop_vir=0):
     OVOV = np.einsum("mnrs,mi,na,rj,sb->iajb", AOERI, Co, Cv, Co, Cv, optimize=True)   # :89
     OVVV = np.einsum("mnrs,mi,na,rb,sc->iabc", AOERI, Co, Cv, Cv, Cv, optimize=True)   # :111
     return F(OVVV), F(OOOV), F(OVOV)
+
+
+def _index2(i, j):
+    """Backend/Arrays.jl:34-40."""
+    return (j * (j + 1)) // 2 + i if i < j else (i * (i + 1)) // 2 + j
+
+
+def ovvv_from_sparse(indexes, data, C, ndocc, drop_occ=0, drop_vir=0):
+    """Transcription of compute_OVVV! for the sparse AO list (Sparse.jl:316-393): every symmetry-unique integral is scattered,
+    times Co[.,i], to the images the reference enumerates case by case (its gamma flags), giving the partially contracted
+    i-nu-rho-sigma array, which is then contracted with Cv three times.  Pure-Python loops: small cases only."""
+    nbf, nmo = C.shape
+    Co = C[:, drop_occ:ndocc]
+    Cv = C[:, ndocc:nmo - drop_vir]
+    no = Co.shape[1]
+    X = np.zeros((no, nbf, nbf, nbf))
+    for (m, n, r, s), V in zip(indexes, data):
+        g_mn = m != n
+        g_rs = r != s
+        g_ab = _index2(m, n) != _index2(r, s)
+        Vm, Vn, Vr, Vs = V * Co[m], V * Co[n], V * Co[r], V * Co[s]
+        if g_ab and g_mn and g_rs:
+            X[:, n, r, s] += Vm; X[:, n, s, r] += Vm; X[:, m, r, s] += Vn; X[:, m, s, r] += Vn
+            X[:, s, m, n] += Vr; X[:, s, n, m] += Vr; X[:, r, m, n] += Vs; X[:, r, n, m] += Vs
+        elif g_ab and g_mn:
+            X[:, n, r, s] += Vm; X[:, m, r, s] += Vn; X[:, s, m, n] += Vr; X[:, s, n, m] += Vr
+        elif g_ab and g_rs:
+            X[:, n, r, s] += Vm; X[:, n, s, r] += Vm; X[:, s, m, n] += Vr; X[:, r, m, n] += Vs
+        elif g_mn and g_rs:
+            X[:, n, r, s] += Vm; X[:, n, s, r] += Vm; X[:, m, r, s] += Vn; X[:, m, s, r] += Vn
+        elif g_ab:
+            X[:, n, r, s] += Vm; X[:, s, m, n] += Vr
+        else:
+            X[:, n, r, s] += Vm
+    return np.asfortranarray(np.einsum("inrs,na,rb,sc->iabc", X, Cv, Cv, Cv, optimize=True))   # :389-391
+
+
+def sparse_from_dense(AOERI, threshold=0.0):
+    """Symmetry-unique entries (mu >= nu, rho >= sigma, (mu nu) >= (rho sigma)) of a dense AO tensor with |value| > threshold,
+    as (indexes (nint,4) int16 zero-based, data) -- the shape of the list GaussianBasis.sparseERI_2e4c hands the reference
+    (AtomicIntegrals.jl:48-52)."""
+    nbf = AOERI.shape[0]
+    idx, vals = [], []
+    for m in range(nbf):
+        for n in range(m + 1):
+            for r in range(nbf):
+                for s in range(r + 1):
+                    if _index2(m, n) < _index2(r, s):
+                        continue
+                    V = AOERI[m, n, r, s]
+                    if abs(V) > threshold:
+                        idx.append((m, n, r, s)); vals.append(V)
+    return np.array(idx, dtype=np.int16).reshape(-1, 4), np.array(vals)

@@ -215,3 +215,48 @@ def test_ao_route_matches_oracle(engine, nbf, ndocc, drop_occ, drop_vir):
     assert abs(res.correction - ref) < TOL
     with pytest.raises(fb.FermiException):
         engine.triples_ao(nbf, o, nbf, T1, T2, AO, Co, Cv, fo, fv)      # o + v > nbf
+
+
+def test_full_size_invariances(engine):
+    """Size-independent properties at the full (H2O)6 shape (o=24, v=114), where the oracle only covers a window:
+    E(T) is invariant under a relabelling of the virtual orbitals and of the occupied orbitals (the tile a label falls in,
+    the padding and the i>=j>=k / a>=b>=c orderings all change), and it is homogeneous of degree 2 in the amplitudes."""
+    o, v = 24, 114
+    x = fb.synth.make_inputs(o, v, naux=48, seed=9)
+    e0, _ = engine.triples_conv(o, v, *_args(x))
+    rng = np.random.default_rng(1)
+    pv, po = rng.permutation(v), rng.permutation(o)
+    F = np.asfortranarray
+    ev, _ = engine.triples_conv(o, v, F(x.T1[:, pv]), F(x.T2[:, :, pv][:, :, :, pv]), F(x.OVVV[:, pv][:, :, pv][:, :, :, pv]),
+                                F(x.OOOV[:, :, :, pv]), F(x.OVOV[:, pv][:, :, :, pv]), x.fo, x.fv[pv].copy())
+    assert abs(ev - e0) < 1e-12, (ev, e0)
+    eo, _ = engine.triples_conv(o, v, F(x.T1[po]), F(x.T2[po][:, po]), F(x.OVVV[po]), F(x.OOOV[po][:, po][:, :, po]),
+                                F(x.OVOV[po][:, :, po]), x.fo[po].copy(), x.fv)
+    assert abs(eo - e0) < 1e-12, (eo, e0)
+    s = 1.75
+    es, _ = engine.triples_conv(o, v, F(s * x.T1), F(s * x.T2), x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+    assert abs(es - s * s * e0) < 1e-12, (es, s * s * e0)
+
+
+@pytest.mark.parametrize("nbf,ndocc,drop_occ,drop_vir,thr,itype", [(9, 3, 0, 0, 0.0, np.int16), (14, 4, 1, 2, 0.0, np.int32),
+                                                                    (26, 6, 1, 0, 1e-4, np.int16)])
+def test_sparse_ao_route_matches_oracle(engine, nbf, ndocc, drop_occ, drop_vir, thr, itype):
+    """fpt_triples_ao_sparse (sparse AO list -> dense tensor on the GPU -> quarter transforms) against the oracle fed with MO
+    blocks from the dense tensor *rebuilt from the same list* (so that a screening threshold changes both sides alike)."""
+    from oracle import pt_numpy as PN
+    AO, C, T1, T2, fo, fv = fb.synth.make_ao_inputs(nbf, ndocc, drop_occ, drop_vir, seed=6)
+    idx, vals = PN.sparse_from_dense(AO, threshold=thr)
+    AOs = np.zeros_like(AO)
+    for (m, n, r, s), V in zip(idx, vals):
+        for a, b, c, d in ((m, n, r, s), (n, m, r, s), (m, n, s, r), (n, m, s, r), (r, s, m, n), (s, r, m, n), (r, s, n, m), (s, r, n, m)):
+            AOs[a, b, c, d] = V
+    OVVV, OOOV, OVOV = PN.mo_blocks_from_ao(AOs, C, ndocc, drop_occ, drop_vir)
+    ref = oracle.pt_gemm(T1, T2, OVVV, OOOV, OVOV, fo, fv)
+    o, v = T1.shape
+    Co, Cv = np.asfortranarray(C[:, drop_occ:ndocc]), np.asfortranarray(C[:, ndocc:nbf - drop_vir])
+    e, st = engine.triples_ao_sparse(nbf, o, v, T1, T2, idx.astype(itype), vals, Co, Cv, fo, fv)
+    assert abs(e - ref) < TOL, (e, ref)
+    ao = fb.IntegralHelper({"ERI": fb.FermiSparse(idx, vals)}, eri_type="SparseERI")
+    moints = fb.IntegralHelper({"Fii": fo, "Faa": fv}, aoints=ao, C=C, ndocc=ndocc, drop_occ=drop_occ, drop_vir=drop_vir)
+    res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, T1, T2), moints, fb.B200())
+    assert abs(res.correction - ref) < TOL

@@ -104,3 +104,36 @@ def test_ao_to_mo_transcription_against_factorised_form():
     assert np.abs(OOOV - np.einsum("Qij,Qka->ijka", Boo, Bov)).max() < 1e-12
     assert np.abs(OVOV - np.einsum("Qia,Qjb->iajb", Bov, Bov)).max() < 1e-12
     assert OVVV.shape == (3, 6, 6, 6) and OVVV.flags.f_contiguous
+
+
+def test_oracle_invariances():
+    """Properties the full-size GPU tests rely on: E(T) is invariant under relabelling virtual / occupied orbitals and
+    homogeneous of degree 2 in (T1, T2)."""
+    import fermi_jl_b200 as fb
+    o, v = 4, 9
+    x = fb.synth.make_inputs(o, v, naux=8, seed=9)
+    F = np.asfortranarray
+    e0 = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+    rng = np.random.default_rng(1)
+    pv, po = rng.permutation(v), rng.permutation(o)
+    ev = oracle.pt_gemm(F(x.T1[:, pv]), F(x.T2[:, :, pv][:, :, :, pv]), F(x.OVVV[:, pv][:, :, pv][:, :, :, pv]),
+                        F(x.OOOV[:, :, :, pv]), F(x.OVOV[:, pv][:, :, :, pv]), x.fo, x.fv[pv].copy())
+    eo = oracle.pt_gemm(F(x.T1[po]), F(x.T2[po][:, po]), F(x.OVVV[po]), F(x.OOOV[po][:, po][:, :, po]),
+                        F(x.OVOV[po][:, :, po]), x.fo[po].copy(), x.fv)
+    es = oracle.pt_gemm(F(1.75 * x.T1), F(1.75 * x.T2), x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+    assert abs(ev - e0) < 1e-15 and abs(eo - e0) < 1e-15 and abs(es - 1.75 ** 2 * e0) < 1e-15
+
+
+def test_sparse_ao_list_transcription():
+    """oracle.pt_numpy.ovvv_from_sparse (the case-by-case scatter of Sparse.jl:316-393) equals the dense contraction of the
+    tensor the list was taken from -- i.e. expanding every unique integral to its 8 images (what the GPU does) is what the
+    reference's gamma cases amount to."""
+    from oracle import pt_numpy as PN
+    import fermi_jl_b200 as fb
+    nbf, ndocc, dc, dv = 8, 3, 1, 1
+    AO, C, *_ = fb.synth.make_ao_inputs(nbf, ndocc, dc, dv, seed=2)
+    idx, vals = PN.sparse_from_dense(AO)
+    assert len(vals) == (nbf * (nbf + 1) // 2) * (nbf * (nbf + 1) // 2 + 1) // 2
+    OVVV_sparse = PN.ovvv_from_sparse(idx, vals, C, ndocc, dc, dv)
+    OVVV, _, _ = PN.mo_blocks_from_ao(AO, C, ndocc, dc, dv)
+    assert np.abs(OVVV_sparse - OVVV).max() < 1e-13
