@@ -81,7 +81,9 @@ dense(A) = A isa Array{Float64} ? A : collect(Float64, A)
 
 function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T<:AbstractFloat,
                                                                               E<:AbstractERI,O<:AbstractRestrictedOrbitals}
-    T === Float64 || throw(FermiException("the B200 (T) path is Float64 only (got $T)"))
+    # `@set precision single` (T = Float32, IntegralHelper.jl:58-68): the arrays are widened once (dense() below) and the
+    # correction is evaluated in FP64 on the GPU -- at least as accurate as the reference's Float32 loops; the result struct
+    # keeps the caller's T
     output("\n   • Perturbative Triples Started\n")
     output("   - Contraction Engine: B200 DMMA (libfermi_pt_b200)")
     T1 = dense(ccsd.T1); T2 = dense(ccsd.T2)
@@ -139,7 +141,7 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
     output("Finished in {:5.5f} s", t)
     output("Final (T) contribution: {:15.10f}", Et[])
     output("CCSD(T) energy:         {:15.10f}", Et[] + ccsd.energy)
-    return RCCSDpT{T}(ccsd, Et[] + ccsd.energy, Et[])        # ijk.jl:149
+    return RCCSDpT{T}(ccsd, T(Et[] + ccsd.energy), T(Et[]))  # ijk.jl:149
 end
 
 end # module

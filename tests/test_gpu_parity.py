@@ -260,3 +260,16 @@ def test_sparse_ao_route_matches_oracle(engine, nbf, ndocc, drop_occ, drop_vir, 
     moints = fb.IntegralHelper({"Fii": fo, "Faa": fv}, aoints=ao, C=C, ndocc=ndocc, drop_occ=drop_occ, drop_vir=drop_vir)
     res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, T1, T2), moints, fb.B200())
     assert abs(res.correction - ref) < TOL
+
+
+def test_single_precision_inputs_are_widened(engine):
+    """`@set precision single` hands Float32 arrays (IntegralHelper.jl:58-68); the path widens them and computes in FP64:
+    E(T) must equal the oracle evaluated on the same (rounded) values."""
+    o, v = 4, 23
+    x = fb.synth.make_inputs(o, v, naux=12, seed=3)
+    f32 = [np.asfortranarray(a.astype(np.float32)) for a in _args(x)]
+    ref = oracle.pt_gemm(*[np.asfortranarray(a.astype(np.float64)) for a in f32])
+    moints = fb.IntegralHelper({"OVVV": f32[2], "OOOV": f32[3], "OVOV": f32[4], "Fii": f32[5], "Faa": f32[6]})
+    res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, f32[0], f32[1]), moints, fb.B200())
+    assert abs(res.correction - ref) < TOL
+    assert abs(res.correction - oracle.pt_gemm(*_args(x))) < 1e-6 * abs(ref) * 100   # and close to the FP64 problem
