@@ -83,6 +83,9 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
     i64 block;
     item_decode_cf(P, it, ctl->item, block);
     ctl->cur_item = it;
+    // ctl->ent was last read by the consumers with ordinary loads (generic proxy); the bulk copy below writes it through the
+    // async proxy.  The mbarrier hand-off (item_empty) orders the two only within the generic proxy: a proxy fence is required.
+    fence_proxy_async();
     mbar_arrive_expect_tx(item_full, (uint32_t)sizeof(BlockTabEntry));
     tma_bulk_g2s(&ctl->ent, P.blocktab + block, (uint32_t)sizeof(BlockTabEntry), item_full);
     // the energy stage of this item (one item ahead of the consumers) reads 18 OV2 tiles of 2 KB: pull them into L2 now
@@ -129,6 +132,10 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
             for (int c = 0; c < nchunks; c++) {
                 const int ng = min(CHUNK_GROUPS, P.G - c * CHUNK_GROUPS);
                 mbar_wait((uint64_t*)&tail->empty[stage], sphase ^ 1);
+                // WAR across proxies: the consumers' LDS reads of this stage (generic proxy) must be ordered before the bulk
+                // copies (async proxy) that refill it.  Acquiring `empty` is not enough -- with one-group stages the refill was
+                // measurably overtaking the reads (wrong energies for 0.5 % of the 18-GEMM items) until this fence was added.
+                fence_proxy_async();
                 uint64_t* fb = (uint64_t*)&tail->full[stage];
                 mbar_arrive_expect_tx(fb, (uint32_t)ng * 2u * row_bytes);
                 double* st = Qsm + stage * QSTAGE_DOUBLES;
@@ -156,6 +163,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
                 mbar_wait((uint64_t*)&tail->empty[st], ph ^ 1);
                 if (++st == QSTAGES) { st = 0; ph ^= 1; }
             }
+            fence_proxy_async();   // same hazard: the ring area was read with LDS, the OV2 tiles arrive through the async proxy
             uint64_t* ob = (uint64_t*)&tail->ov_full;
             mbar_arrive_expect_tx(ob, (uint32_t)(OV_STAGE_TILES * 256 * sizeof(double)));
 #pragma unroll 1

@@ -273,3 +273,14 @@ def test_single_precision_inputs_are_widened(engine):
     res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, f32[0], f32[1]), moints, fb.B200())
     assert abs(res.correction - ref) < TOL
     assert abs(res.correction - oracle.pt_gemm(*_args(x))) < 1e-6 * abs(ref) * 100   # and close to the FP64 problem
+
+
+@pytest.mark.parametrize("o,v", [(3, 127), (4, 126), (6, 124)])
+def test_nine_group_k_all_distinct_tile_triples(engine, o, v):
+    """K = v + o in (128, 144] -> nine kappa-groups, vp = 128 -> eight full tiles: the shape on which a ring refill overtaking
+    the consumers' shared-memory reads (missing cross-proxy fence, see producer_loop) showed up first."""
+    x = fb.synth.make_inputs(o, v, naux=16)
+    ref = oracle.pt_gemm(*_args(x))
+    for _ in range(3):
+        e, _ = engine.triples_conv(o, v, *_args(x))
+        assert abs(e - ref) < TOL, (e, ref)
