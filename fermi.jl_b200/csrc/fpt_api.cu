@@ -251,6 +251,7 @@ static int setup_problem(fpt_handle* h, int o, int v)
         tetra_decode(b, A, B, C);
         make_block(A, B, C, P.vp, tab[b].bd);
         tab[b].ngemm = make_gemms(tab[b].bd, 0, 1, 2, tab[b].gemm);
+        make_fast_order(tab[b]);
     }
     if (h->blocktab.ensure(tab.size() * sizeof(BlockTabEntry))) return 1;
     CK(cudaMemcpyAsync(h->blocktab.p, tab.data(), tab.size() * sizeof(BlockTabEntry), cudaMemcpyHostToDevice, h->stream));

@@ -252,8 +252,55 @@ struct BlockTabEntry {
     BlockDesc bd;
     int ngemm;
     GemmDesc gemm[MAX_GEMMS];
+    // "Load-accumulate-store" order for blocks of three distinct tiles (nslot == 6): a permutation of the 18 GEMMs in which
+    // two consecutive GEMMs never write the same W slot.  A GEMM can then start from the current slot contents (accumulators
+    // initialised by LDS, or zero where ffirst says it is the slot's first contribution in this order) and finish with
+    // plain stores: the only ordering it needs is against the GEMM *two* steps back, a whole k-loop earlier.
+    unsigned char forder[MAX_GEMMS + 2];
+    unsigned char ffirst[MAX_GEMMS + 2];   // bit s: D[..., s, ...] of forder[t] is the first contribution to its slot
+    int fast_ok;
+    int pad_;
 };
 static_assert(sizeof(BlockTabEntry) % 16 == 0, "BlockTabEntry is moved by 16-byte-granular bulk copies");
+
+FPT_HD int gemm_slot(const BlockDesc& bd, const GemmDesc& g, int s) { return g.dbase[s] / bd.slot_elems; }
+
+// depth-first search for the order described at BlockTabEntry::forder (18 nodes, dense compatibility graph: trivial); host only
+inline bool fast_order_dfs(const BlockTabEntry& e, unsigned char* order, bool* used, int depth)
+{
+    if (depth == e.ngemm) return true;
+    for (int g = 0; g < e.ngemm; g++) {
+        if (used[g]) continue;
+        if (depth > 0) {
+            const GemmDesc& pr = e.gemm[order[depth - 1]];
+            const GemmDesc& cu = e.gemm[g];
+            bool clash = false;
+            for (int s = 0; s < 2; s++)
+                for (int t = 0; t < 2; t++) clash = clash || gemm_slot(e.bd, pr, s) == gemm_slot(e.bd, cu, t);
+            if (clash) continue;
+        }
+        used[g] = true; order[depth] = (unsigned char)g;
+        if (fast_order_dfs(e, order, used, depth + 1)) return true;
+        used[g] = false;
+    }
+    return false;
+}
+
+inline void make_fast_order(BlockTabEntry& e)
+{
+    e.fast_ok = 0; e.pad_ = 0;
+    for (int t = 0; t < MAX_GEMMS + 2; t++) { e.forder[t] = 0; e.ffirst[t] = 0; }
+    if (e.bd.nslot != MAX_SLOTS || e.ngemm != MAX_GEMMS) return;
+    bool used[MAX_GEMMS] = {};
+    if (!fast_order_dfs(e, e.forder, used, 0)) return;
+    bool touched[MAX_SLOTS] = {};
+    for (int t = 0; t < e.ngemm; t++)
+        for (int s = 0; s < 2; s++) {
+            const int sl = gemm_slot(e.bd, e.gemm[e.forder[t]], s);
+            if (!touched[sl]) { e.ffirst[t] |= (unsigned char)(1 << s); touched[sl] = true; }
+        }
+    e.fast_ok = 1;
+}
 
 // Relative cost of one item of a block, in units of one DMMA.8x8x4 per consumer warp, for the static cost-weighted split of
 // the work list across GPUs: per GEMM the k-loop issues ceil(row tiles / 16) x (TZ/4) x 4 DMMAs per kappa group and warp,

@@ -53,7 +53,7 @@ constexpr int NPROF = 24;   // 12 phase counters for each of two observer warps
 
 struct SmemTail {
     Ctl ctl[2];
-    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2], rmw_done, ov_full, ov_empty;
+    unsigned long long full[QSTAGES], empty[QSTAGES], item_full[2], item_empty[2], rmw_done[2], ov_full, ov_empty;
     double red[NCWARPS];
 };
 
@@ -63,8 +63,14 @@ __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 
 // RMW phases of *different* GEMMs may touch the same W elements (through different thread->element maps), RMW phases of
 // the same GEMM never do (except the diag_xz aliasing handled inside gemm_rmw).  So all warps add their accumulators
-// concurrently, and a split mbarrier orders consecutive GEMMs: every warp arrives on `rmw_done` after its RMW(g) and waits
-// for that phase to complete before its RMW(g+1) -- a whole k-loop later, so the wait practically never blocks.
+// concurrently, and split mbarriers order the GEMMs: the n-th slot update of the launch ("event" n, counted by `gcount`
+// identically in every warp) arrives on rmw_done[n & 1]; its phase number there is n >> 1.
+//   * accumulate path: before event n a warp waits for event n-1 (every warp's RMW of the previous GEMM is done) -- a whole
+//     k-loop after that RMW, so the wait practically never blocks;
+//   * load-accumulate-store path (blocks of three distinct tiles, triplets without twin GEMMs; BlockTabEntry::forder): the
+//     accumulators *start* from the slot contents (LDS, or zero for a slot's first contribution) and are *stored* back after
+//     the k-loop.  No FP64 add, no load->add->store chain between two k-loops; since consecutive GEMMs of that order write
+//     different slots, a warp only waits for event n-2 before it loads.
 
 // ---------------------------------------------------------------------------------------------------
 // producer: one thread
@@ -106,7 +112,12 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
 // Producer: one thread.  Streams the Q chunks of every GEMM of every item through the ring.  Item n+1 is fetched and
 // decoded while the chunks of item n are still streaming (right after its first GEMM), so the ring never runs dry at an
 // item boundary.
-template <class Tail>
+__device__ __forceinline__ bool item_is_fast(const Problem& P, const Ctl* ctl)
+{
+    return ctl->ent.fast_ok && ctl->item.i != ctl->item.j && ctl->item.j != ctl->item.k && !(P.dbg_flags & 64);
+}
+
+template <bool FASTOK, class Tail>
 __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
                                               double* Qsm, Tail* tail)
 {
@@ -122,8 +133,10 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
         mbar_wait((uint64_t*)&tail->item_full[slot], (n >> 1) & 1);   // own TMA copy of the table entry has landed
         if (ctl->cur_item < 0) break;
         const int ngemm = ctl->ent.ngemm;
-        for (int g = 0; g < ngemm; g++) {
-            if (gemm_is_dup(ctl->item, g)) continue;   // no k-loop for twin GEMMs (i == j or j == k)
+        const bool fast = FASTOK && item_is_fast(P, ctl);
+        for (int t = 0; t < ngemm; t++) {
+            const int g = fast ? ctl->ent.forder[t] : t;
+            if (!fast && gemm_is_dup(ctl->item, g)) continue;   // no k-loop for twin GEMMs (i == j or j == k)
             const GemmDesc& gd = ctl->ent.gemm[g];
             const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
             const int q = occ_pick(ctl->item, gd.q), r = occ_pick(ctl->item, gd.r);
@@ -148,7 +161,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
                 }
                 if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
             }
-            if (g == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
+            if (t == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
                 const uint32_t m = n + 1;
                 mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
                 producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
@@ -220,7 +233,7 @@ __device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, d
 // consumer: k-loop of one GEMM.  acc[mt][ct][e]: row tile mt, column tile ct, D element e.
 // Column n of tile ct is (zl = 4ct + (n>>1), s = n&1), so a lane's two D elements are (zl = 4ct + kk, s = e).
 // ---------------------------------------------------------------------------------------------------
-template <int MTW, int NT, bool PROF, class Tail>
+template <int MTW, int NT, bool PROF, bool ZERO = true, class Tail>
 __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
                                            double (&acc)[MTW][NT][2], const double* Qsm, Tail* tail, int& stage,
                                            uint32_t& sphase, int lane, long long* prof)
@@ -228,10 +241,12 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
     const int kk = lane & 3, n = lane >> 2;
     const int boff = ((n & 1) * QBLK) + (n >> 1) * KGROUP + 4 * kk;   // s block + row zl(ct=0) + this lane's 4 kappa
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+    if (ZERO) {
 #pragma unroll
-    for (int mt = 0; mt < MTW; mt++)
+        for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
-        for (int ct = 0; ct < NT; ct++) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
+            for (int ct = 0; ct < NT; ct++) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
+    }
 
     for (int c = 0; c < nchunks; c++) {
         const int g0 = c * CHUNK_GROUPS;
@@ -280,10 +295,12 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
     }
 }
 
-// RMW of the accumulators into the W slots
-template <int MTW, int NT>
-__device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, const double (&acc)[MTW][NT][2], double* Wsm,
-                                         int lane)
+// The accumulators of one GEMM <-> its two W slots.  MODE 0: add into the slots (store where this is the slot's first
+// contribution); MODE 1: load the slot contents into the accumulators (zero for a first contribution, bit s of `first_bits`);
+// MODE 2: store the accumulators.
+template <int MTW, int NT, int MODE>
+__device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs, double (&acc)[MTW][NT][2], double* Wsm, int lane,
+                                            int first_bits)
 {
     const int kk = lane & 3, r = lane >> 2;
     int xl[MTW], yl[MTW];
@@ -296,21 +313,32 @@ __device__ __forceinline__ void gemm_rmw(const GemmDesc& gd, const RowSet& rs, c
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
-        if (e == 1 && gd.diag_xz) consumer_bar();
+        if (MODE == 0 && e == 1 && gd.diag_xz) consumer_bar();
         const int dbase = gd.dbase[e], sel = gd.dsel[e], Tb = gd.dTb[e], Tc = gd.dTc[e];
-        const bool first = gd.dfirst[e] != 0;   // first contribution to this slot in the item: store (the slots are never zeroed)
+        const bool first = MODE == 0 ? gd.dfirst[e] != 0 : ((first_bits >> e) & 1) != 0;
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) {
             if (mt < rs.nvalid) {
                 DestIter it;
                 dest_iter_init_fast(dbase, sel, Tb, Tc, xl[mt], yl[mt], kk, it);
-                if (first) {
+                if (MODE == 1) {
+                    if (first) {
+#pragma unroll
+                        for (int ct = 0; ct < NT; ct++) acc[mt][ct][e] = 0.0;
+                    } else {
+#pragma unroll
+                        for (int ct = 0; ct < NT; ct++) acc[mt][ct][e] = Wsm[dest_iter_off(it, ct)];
+                    }
+                } else if (MODE == 2 || first) {   // first contribution to this slot in the item: the slots are never zeroed
 #pragma unroll
                     for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] = acc[mt][ct][e];
                 } else {
 #pragma unroll
                     for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
                 }
+            } else if (MODE == 1) {
+#pragma unroll
+                for (int ct = 0; ct < NT; ct++) acc[mt][ct][e] = 0.0;
             }
         }
     }
@@ -339,16 +367,49 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
     for (int rep = 0; rep <= (dup_next ? 1 : 0); rep++) {
         long long tw = 0;
         if (PROF) tw = clock64();
-        if (gcount > 0) mbar_wait((uint64_t*)&tail->rmw_done, (gcount - 1) & 1);   // every warp has finished the previous RMW phase
+        if (gcount > 0)   // every warp has finished the previous slot update (event gcount-1)
+            mbar_wait((uint64_t*)&tail->rmw_done[(gcount - 1) & 1], ((gcount - 1) >> 1) & 1);
         if (PROF) { const long long t2 = clock64(); prof[6] += t2 - tw; tw = t2; }
-        if (!(P.dbg_flags & 1)) gemm_rmw<MTW, NT>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane);
+        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 0>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane, 0);
         else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
         __syncwarp();
         if (PROF) prof[7] += clock64() - tw;
-        if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done);
+        if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done[gcount & 1]);
         gcount++;
     }
     if (PROF) prof[3] += clock64() - t1;
+}
+
+// load-accumulate-store form of one GEMM (see the comment at the top): g = forder[t], gnext = forder[t+1] or -1
+template <int MTW, int NT, bool PROF>
+__device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl, int g, int gnext, int first_bits, RowSet& rs,
+                                               double4x (&a)[ABUF][MTW_MAX], double* Wsm, const double* Qsm, SmemTail* tail,
+                                               int& stage, uint32_t& sphase, uint32_t& gcount, int warp, int lane, long long* prof)
+{
+    const GemmDesc& gd = ctl->ent.gemm[g];
+    double acc[MTW][NT][2];
+    long long t0 = 0, t1 = 0;
+    if (PROF) t0 = clock64();
+    if (gcount > 1)   // every warp's stores of the slot update two steps back (event gcount-2) are in the slots
+        mbar_wait((uint64_t*)&tail->rmw_done[gcount & 1], ((gcount - 2) >> 1) & 1);
+    if (PROF) { t1 = clock64(); prof[6] += t1 - t0; }
+    if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, first_bits);
+    else gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, 3);
+    if (PROF) { t0 = clock64(); prof[7] += t0 - t1; }
+    gemm_kloop<MTW, NT, PROF, false>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
+    if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
+    const RowSet rs_cur = rs;
+    if (gnext >= 0) {
+        const GemmDesc& gn = ctl->ent.gemm[gnext];
+        rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        a_prologue<MTW_MAX>(P, rs, a);
+    }
+    if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 2>(gd, rs_cur, acc, Wsm, lane, 0);
+    else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done[gcount & 1]);
+    gcount++;
+    if (PROF) { const long long t2 = clock64(); prof[7] += t2 - t1; prof[3] += t2 - t1; }
 }
 
 #define FPT_DISPATCH_NT(MTWc, NTv, CALL)                                   \
@@ -384,7 +445,8 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
     if (tid == 0) {
         for (int s = 0; s < QSTAGES; s++) { mbar_init((uint64_t*)&tail->full[s], 1); mbar_init((uint64_t*)&tail->empty[s], NCWARPS); }
         for (int s = 0; s < 2; s++) { mbar_init((uint64_t*)&tail->item_full[s], 1); mbar_init((uint64_t*)&tail->item_empty[s], NCWARPS); }
-        mbar_init((uint64_t*)&tail->rmw_done, NCWARPS);
+        mbar_init((uint64_t*)&tail->rmw_done[0], NCWARPS);
+        mbar_init((uint64_t*)&tail->rmw_done[1], NCWARPS);
         mbar_init((uint64_t*)&tail->ov_full, 1);
         mbar_init((uint64_t*)&tail->ov_empty, NCWARPS);
         fence_mbar_init();
@@ -394,7 +456,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
 
     if (warp >= NCWARPS) {   // producer warpgroup
         setmaxnreg_dec<PRODUCER_REGS>();
-        if (warp == NCWARPS && lane == 0) producer_loop(P, item_begin, item_end, counter, Qsm, tail);
+        if (warp == NCWARPS && lane == 0) producer_loop<true>(P, item_begin, item_end, counter, Qsm, tail);
         return;
     }
     setmaxnreg_inc<CONSUMER_REGS>();
@@ -418,20 +480,35 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (PROF) { t1 = clock64(); prof[0] += t1 - t0; }
 
         const int ngemm = ctl->ent.ngemm;
+        const bool fast = item_is_fast(P, ctl);
+        const int gfirst = fast ? ctl->ent.forder[0] : 0;
         RowSet rs;
-        rows_setup(P, ctl->ent.gemm[0], occ_pick(ctl->item, ctl->ent.gemm[0].p), warp, lane, rs);
+        rows_setup(P, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
         a_prologue<MTW_MAX>(P, rs, a);
-        // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst); the barrier at the
-        // end of the previous item's energy stage already ordered those stores after its reads
+        // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst / ffirst); the
+        // barrier at the end of the previous item's energy stage already ordered those stores after its reads
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 
-        for (int g = 0; g < ngemm; g++) {
-            if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
-            const GemmDesc& gd = ctl->ent.gemm[g];
-            const int rt_total = (gd.TX * gd.TY) >> 3;
-            const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
-            const int nt = gd.TZ >> 2;
-            FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+        if (fast) {
+            for (int t = 0; t < ngemm; t++) {
+                const int g = ctl->ent.forder[t];
+                const int gnext = t + 1 < ngemm ? ctl->ent.forder[t + 1] : -1;
+                const int fbits = ctl->ent.ffirst[t];
+                const GemmDesc& gd = ctl->ent.gemm[g];
+                const int rt_total = (gd.TX * gd.TY) >> 3;
+                const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
+                const int nt = gd.TZ >> 2;
+                FPT_DISPATCH(mtw, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+            }
+        } else {
+            for (int g = 0; g < ngemm; g++) {
+                if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
+                const GemmDesc& gd = ctl->ent.gemm[g];
+                const int rt_total = (gd.TX * gd.TY) >> 3;
+                const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
+                const int nt = gd.TZ >> 2;
+                FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+            }
         }
         if (PROF) t1 = clock64();
         consumer_bar();

@@ -308,7 +308,7 @@ triples_kernel2(Problem P, i64 item_begin, i64 item_end, unsigned long long* cou
 
     if (warp >= NCWARPS + NEWARPS) {   // producer warpgroup
         setmaxnreg_dec<PRODUCER_REGS2>();
-        if (warp == NCWARPS + NEWARPS && lane == 0) producer_loop(P, item_begin, item_end, counter, Qsm, tail);
+        if (warp == NCWARPS + NEWARPS && lane == 0) producer_loop<false>(P, item_begin, item_end, counter, Qsm, tail);
         return;
     }
     if (warp >= NCWARPS) {             // epilogue warpgroup
