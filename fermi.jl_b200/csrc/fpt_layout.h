@@ -302,17 +302,18 @@ inline void make_fast_order(BlockTabEntry& e)
     e.fast_ok = 1;
 }
 
-// Relative cost of one item of a block, in units of one DMMA.8x8x4 per consumer warp, for the static cost-weighted split of
-// the work list across GPUs: per GEMM the k-loop issues ceil(row tiles / 16) x (TZ/4) x 4 DMMAs per kappa group and warp,
-// plus a fixed epilogue (accumulate into the W slots, next GEMM's setup) worth about 2 full-size groups; per item the
-// energy stage and the item switch cost about 5 full-size groups (phase profile profiles/r01_phase_c4_mid.json, tuned on
-// the measured 8-way shard times at the C4 shape).
+// Relative cost of one item of a block, in units of one DMMA.8x8x4 on one SM sub-partition, for the static cost-weighted
+// split of the work list across GPUs: per GEMM and kappa group the busiest sub-partition issues (row tiles of its four
+// warps) x (TZ/4) x 4 DMMAs (row tiles are dealt evenly to the 16 warps, warp w sits on sub-partition w % 4), plus a fixed
+// epilogue (slot update, next GEMM's setup) worth about 2 full-size groups; per item the energy stage and the item switch
+// cost about 5 full-size groups (phase profile profiles/r01_phase_c4_mid.json, tuned on the measured 8-way shard times at C4).
 FPT_HD double block_cost(const BlockTabEntry& e, int G)
 {
-    double c = 5.0 * 32.0;
+    double c = 5.0 * 128.0;
     for (int g = 0; g < e.ngemm; g++) {
-        const int mtw = (e.gemm[g].rt_total + 15) / 16, nt = e.gemm[g].TZ >> 2;
-        c += (double)(mtw * nt * 4) * G + 2.0 * 32.0;
+        const int rt = e.gemm[g].rt_total, nt = e.gemm[g].TZ >> 2;
+        const int tiles = 4 * (rt >> 4) + (((rt & 15) + 3) >> 2);
+        c += (double)(tiles * nt * 4) * G + 2.0 * 128.0;
     }
     return c;
 }

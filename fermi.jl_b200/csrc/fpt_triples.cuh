@@ -198,35 +198,73 @@ struct RowSet {
     int rt0;                   // first row tile of this warp
 };
 
-__device__ __forceinline__ void rows_setup(const Problem& P, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
+// Row tiles (8 rows) of a GEMM are dealt to the 16 consumer warps as evenly as possible: warp w owns `nv` consecutive tiles
+// starting at rt0.  (ceil(rt_total/16) tiles for every warp would make the surplus warps multiply padding: 7 % of the DMMAs at C4.)
+__device__ __forceinline__ void warp_rows(int rt_total, int w, int& rt0, int& nv)
+{
+    const int base = rt_total >> 4, extra = rt_total & (NCWARPS - 1);
+    nv = base + (w < extra ? 1 : 0);
+    rt0 = w * base + min(w, extra);
+}
+
+__device__ __forceinline__ void rows_setup2(const Problem& P, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
 {
     const int r = lane >> 2, kk = lane & 3;
-    const int rt_total = (gd.TX * gd.TY) >> 3;
-    const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
     rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 4 * kk;
-    rs.nvalid = 0;
-    rs.rt0 = warp * mtw;
+    warp_rows(gd.rt_total, warp, rs.rt0, rs.nvalid);
 #pragma unroll
     for (int mt = 0; mt < MTW_MAX; mt++) {
-        const int rt = warp * mtw + mt;
-        const bool ok = (mt < mtw) && (rt < rt_total);
-        rs.nvalid += ok ? 1 : 0;
-        const int m = ok ? rt * 8 + r : r;
-        const int yl = (m * gd.xinv) >> 16;   // m / TX
+        const int m = (mt < rs.nvalid) ? (rs.rt0 + mt) * 8 + r : r;
+        const int yl = (m * gd.xinv) >> 16;
         const int xl = m - yl * gd.TX;
         rs.off[mt] = (yl * P.vp + xl) * P.Kp;
     }
 }
 
-template <int MTW>
-__device__ __forceinline__ void a_prologue(const Problem& P, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX])
+__device__ __forceinline__ void a_prologue2(const Problem& P, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX])
 {
+    if (P.G > 0) {
 #pragma unroll
-    for (int d = 0; d < APREF; d++)
-        if (d < P.G) {
+        for (int mt = 0; mt < MTW_MAX; mt++)
+            if (mt < rs.nvalid) a[0][mt] = ldg_stream_f64x4(rs.base + rs.off[mt]);
+    }
+}
+
+// a warp without rows in this GEMM still takes part in the Q ring protocol
+template <class Tail>
+__device__ __forceinline__ void kloop_idle(const Problem& P, Tail* tail, int& stage, uint32_t& sphase, int lane)
+{
+    const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
+    for (int c = 0; c < nchunks; c++) {
+        mbar_wait((uint64_t*)&tail->full[stage], sphase);
+        __syncwarp();
+        if (lane == 0) mbar_arrive((uint64_t*)&tail->empty[stage]);
+        if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
+    }
+}
+
+// accumulators -> TMEM, column order (e, mt, ct) so that the epilogue fetches the 4 column tiles of one (e, mt) with one x8 load
+template <int MTW, int NT>
+__device__ __forceinline__ void park_acc(const double (&acc)[MTW][NT][2], uint32_t taddr)
+{
+    uint32_t v[32];
 #pragma unroll
-            for (int mt = 0; mt < MTW; mt++) a[d][mt] = ldg_stream_f64x4(rs.base + rs.off[mt] + d * KGROUP);
-        }
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int ct = 0; ct < 4; ct++) {
+                const int idx = (e * 2 + mt) * 4 + ct;
+                if (mt < MTW && ct < NT) {
+                    v[2 * idx] = (uint32_t)__double2loint(acc[mt < MTW ? mt : 0][ct < NT ? ct : 0][e]);
+                    v[2 * idx + 1] = (uint32_t)__double2hiint(acc[mt < MTW ? mt : 0][ct < NT ? ct : 0][e]);
+                } else {
+                    v[2 * idx] = 0u;
+                    v[2 * idx + 1] = 0u;
+                }
+            }
+    tmem_st32(taddr, v);
+    tmem_wait_st();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -351,18 +389,19 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
                                           uint32_t& gcount, int warp, int lane, long long* prof)
 {
     const GemmDesc& gd = ctl->ent.gemm[g];
-    double acc[MTW][NT][2];
+    double acc[MTW > 0 ? MTW : 1][NT][2];
     long long t0 = 0, t1 = 0;
     if (PROF) t0 = clock64();
-    gemm_kloop<MTW, NT, PROF>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
+    if constexpr (MTW > 0) gemm_kloop<MTW, NT, PROF>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
+    else kloop_idle(P, tail, stage, sphase, lane);   // no rows in this GEMM: only keep the ring protocol in step
     if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
     const RowSet rs_cur = rs;
     const bool dup_next = (g + 1 < ctl->ent.ngemm) && gemm_is_dup(ctl->item, g + 1);   // twin GEMM: same D, other destinations
     const int gnext = g + (dup_next ? 2 : 1);
     if (gnext < ctl->ent.ngemm) {
         const GemmDesc& gn = ctl->ent.gemm[gnext];
-        rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
-        a_prologue<MTW_MAX>(P, rs, a);
+        rows_setup2(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        a_prologue2(P, rs, a);
     }
     for (int rep = 0; rep <= (dup_next ? 1 : 0); rep++) {
         long long tw = 0;
@@ -370,8 +409,12 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
         if (gcount > 0)   // every warp has finished the previous slot update (event gcount-1)
             mbar_wait((uint64_t*)&tail->rmw_done[(gcount - 1) & 1], ((gcount - 1) >> 1) & 1);
         if (PROF) { const long long t2 = clock64(); prof[6] += t2 - tw; tw = t2; }
-        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 0>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane, 0);
-        else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
+        if constexpr (MTW > 0) {
+            if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 0>(ctl->ent.gemm[g + rep], rs_cur, acc, Wsm, lane, 0);
+            else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];   // keep the accumulators alive
+        } else if (ctl->ent.gemm[g + rep].diag_xz && !(P.dbg_flags & 1)) {
+            consumer_bar();   // the CTA-wide barrier between the two column halves inside gemm_wslots
+        }
         __syncwarp();
         if (PROF) prof[7] += clock64() - tw;
         if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done[gcount & 1]);
@@ -387,25 +430,30 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
                                                int& stage, uint32_t& sphase, uint32_t& gcount, int warp, int lane, long long* prof)
 {
     const GemmDesc& gd = ctl->ent.gemm[g];
-    double acc[MTW][NT][2];
+    double acc[MTW > 0 ? MTW : 1][NT][2];
     long long t0 = 0, t1 = 0;
     if (PROF) t0 = clock64();
     if (gcount > 1)   // every warp's stores of the slot update two steps back (event gcount-2) are in the slots
         mbar_wait((uint64_t*)&tail->rmw_done[gcount & 1], ((gcount - 2) >> 1) & 1);
     if (PROF) { t1 = clock64(); prof[6] += t1 - t0; }
-    if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, first_bits);
-    else gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, 3);
+    if constexpr (MTW > 0) {
+        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, first_bits);
+        else gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, 3);
+    }
     if (PROF) { t0 = clock64(); prof[7] += t0 - t1; }
-    gemm_kloop<MTW, NT, PROF, false>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
+    if constexpr (MTW > 0) gemm_kloop<MTW, NT, PROF, false>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
+    else kloop_idle(P, tail, stage, sphase, lane);
     if (PROF) { t1 = clock64(); prof[2] += t1 - t0; }
     const RowSet rs_cur = rs;
     if (gnext >= 0) {
         const GemmDesc& gn = ctl->ent.gemm[gnext];
-        rows_setup(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
-        a_prologue<MTW_MAX>(P, rs, a);
+        rows_setup2(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        a_prologue2(P, rs, a);
     }
-    if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 2>(gd, rs_cur, acc, Wsm, lane, 0);
-    else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];
+    if constexpr (MTW > 0) {
+        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 2>(gd, rs_cur, acc, Wsm, lane, 0);
+        else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive((uint64_t*)&tail->rmw_done[gcount & 1]);
     gcount++;
@@ -422,6 +470,7 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
 #define FPT_DISPATCH(MTWv, NTv, CALL)                                      \
     do {                                                                   \
         switch (MTWv) {                                                    \
+        case 0: FPT_DISPATCH_NT(0, NTv, CALL) break;                       \
         case 1: FPT_DISPATCH_NT(1, NTv, CALL) break;                       \
         default: FPT_DISPATCH_NT(2, NTv, CALL) break;                      \
         }                                                                  \
@@ -483,8 +532,8 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         const bool fast = item_is_fast(P, ctl);
         const int gfirst = fast ? ctl->ent.forder[0] : 0;
         RowSet rs;
-        rows_setup(P, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
-        a_prologue<MTW_MAX>(P, rs, a);
+        rows_setup2(P, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
+        a_prologue2(P, rs, a);
         // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst / ffirst); the
         // barrier at the end of the previous item's energy stage already ordered those stores after its reads
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
@@ -494,20 +543,15 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
                 const int g = ctl->ent.forder[t];
                 const int gnext = t + 1 < ngemm ? ctl->ent.forder[t + 1] : -1;
                 const int fbits = ctl->ent.ffirst[t];
-                const GemmDesc& gd = ctl->ent.gemm[g];
-                const int rt_total = (gd.TX * gd.TY) >> 3;
-                const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
-                const int nt = gd.TZ >> 2;
-                FPT_DISPATCH(mtw, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                const int nt = ctl->ent.gemm[g].TZ >> 2;
+                // rs (set up during the previous GEMM) holds this warp's share of row tiles: 0, 1 or 2
+                FPT_DISPATCH(rs.nvalid, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         } else {
             for (int g = 0; g < ngemm; g++) {
                 if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
-                const GemmDesc& gd = ctl->ent.gemm[g];
-                const int rt_total = (gd.TX * gd.TY) >> 3;
-                const int mtw = (rt_total + NCWARPS - 1) / NCWARPS;
-                const int nt = gd.TZ >> 2;
-                FPT_DISPATCH(mtw, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                const int nt = ctl->ent.gemm[g].TZ >> 2;
+                FPT_DISPATCH(rs.nvalid, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         }
         if (PROF) t1 = clock64();

@@ -48,75 +48,6 @@ __device__ __forceinline__ uint32_t park_addr(uint32_t tmem_base, int q, int cw,
     return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((cw * PARK_BUFS + buf) * PARK_COLS);
 }
 
-// Row tiles (8 rows) of a GEMM are dealt to the 16 consumer warps as evenly as possible: warp w owns `nv` consecutive tiles
-// starting at rt0.  (The first kernel gives every warp ceil(rt_total/16) tiles and lets the surplus warps multiply padding.)
-__device__ __forceinline__ void warp_rows(int rt_total, int w, int& rt0, int& nv)
-{
-    const int base = rt_total >> 4, extra = rt_total & (NCWARPS - 1);
-    nv = base + (w < extra ? 1 : 0);
-    rt0 = w * base + min(w, extra);
-}
-
-__device__ __forceinline__ void rows_setup2(const Problem& P, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
-{
-    const int r = lane >> 2, kk = lane & 3;
-    rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 4 * kk;
-    warp_rows(gd.rt_total, warp, rs.rt0, rs.nvalid);
-#pragma unroll
-    for (int mt = 0; mt < MTW_MAX; mt++) {
-        const int m = (mt < rs.nvalid) ? (rs.rt0 + mt) * 8 + r : r;
-        const int yl = (m * gd.xinv) >> 16;
-        const int xl = m - yl * gd.TX;
-        rs.off[mt] = (yl * P.vp + xl) * P.Kp;
-    }
-}
-
-__device__ __forceinline__ void a_prologue2(const Problem& P, const RowSet& rs, double4x (&a)[ABUF][MTW_MAX])
-{
-    if (P.G > 0) {
-#pragma unroll
-        for (int mt = 0; mt < MTW_MAX; mt++)
-            if (mt < rs.nvalid) a[0][mt] = ldg_stream_f64x4(rs.base + rs.off[mt]);
-    }
-}
-
-// a warp without rows in this GEMM still takes part in the Q ring protocol
-template <class Tail>
-__device__ __forceinline__ void kloop_idle(const Problem& P, Tail* tail, int& stage, uint32_t& sphase, int lane)
-{
-    const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
-    for (int c = 0; c < nchunks; c++) {
-        mbar_wait((uint64_t*)&tail->full[stage], sphase);
-        __syncwarp();
-        if (lane == 0) mbar_arrive((uint64_t*)&tail->empty[stage]);
-        if (++stage == QSTAGES) { stage = 0; sphase ^= 1; }
-    }
-}
-
-// accumulators -> TMEM, column order (e, mt, ct) so that the epilogue fetches the 4 column tiles of one (e, mt) with one x8 load
-template <int MTW, int NT>
-__device__ __forceinline__ void park_acc(const double (&acc)[MTW][NT][2], uint32_t taddr)
-{
-    uint32_t v[32];
-#pragma unroll
-    for (int e = 0; e < 2; e++)
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int ct = 0; ct < 4; ct++) {
-                const int idx = (e * 2 + mt) * 4 + ct;
-                if (mt < MTW && ct < NT) {
-                    v[2 * idx] = (uint32_t)__double2loint(acc[mt < MTW ? mt : 0][ct < NT ? ct : 0][e]);
-                    v[2 * idx + 1] = (uint32_t)__double2hiint(acc[mt < MTW ? mt : 0][ct < NT ? ct : 0][e]);
-                } else {
-                    v[2 * idx] = 0u;
-                    v[2 * idx + 1] = 0u;
-                }
-            }
-    tmem_st32(taddr, v);
-    tmem_wait_st();
-}
-
 // one GEMM of an item on a consumer warp: k-loop, next GEMM's row setup and first A loads, park the accumulators.
 // MTW = number of row tiles this warp owns in this GEMM (0: none, it only keeps the ring and parking protocols in step).
 template <int MTW, int NT, bool PROF>
