@@ -97,6 +97,32 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         GemmDesc gd[MAX_GEMMS];
         const int ng = make_gemms(bd, 0, 1, 2, gd);   // positions, as in the device block table
         for (int g = 0; g < ng; g++) { gd[g].p = occ_pick(it, gd[g].p); gd[g].q = occ_pick(it, gd[g].q); gd[g].r = occ_pick(it, gd[g].r); }
+        {   // the load-accumulate-store order of the block table (BlockTabEntry::forder / ffirst) must be a permutation of the
+            // GEMMs in which neighbours write different slots, with exactly the first contribution of every slot flagged
+            BlockTabEntry ent{};
+            ent.bd = bd; ent.ngemm = ng;
+            for (int g = 0; g < ng; g++) ent.gemm[g] = gd[g];
+            make_fast_order(ent);
+            if ((bd.nslot == MAX_SLOTS) != (ent.fast_ok != 0)) { fprintf(stderr, "fast order missing for a six-slot block\n"); return 10; }
+            if (ent.fast_ok) {
+                bool seen[MAX_GEMMS] = {}, touched[MAX_SLOTS] = {};
+                for (int t = 0; t < ng; t++) {
+                    const int g = ent.forder[t];
+                    if (g >= ng || seen[g]) { fprintf(stderr, "fast order is not a permutation\n"); return 11; }
+                    seen[g] = true;
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        const int sl = gemm_slot(bd, gd[g], s2);
+                        if (t > 0)
+                            for (int s3 = 0; s3 < 2; s3++)
+                                if (sl == gemm_slot(bd, gd[ent.forder[t - 1]], s3)) { fprintf(stderr, "neighbours share a slot\n"); return 12; }
+                        const bool first = !touched[sl];
+                        if (first != (((ent.ffirst[t] >> s2) & 1) != 0)) { fprintf(stderr, "wrong first-contribution flag\n"); return 13; }
+                        touched[sl] = true;
+                    }
+                    if (gemm_slot(bd, gd[g], 0) == gemm_slot(bd, gd[g], 1)) { fprintf(stderr, "six-slot block with aliasing halves\n"); return 14; }
+                }
+            }
+        }
         std::fill(W.begin(), W.begin() + (size_t)bd.nslot * bd.slot_elems, 0.0);
         std::vector<int> hits((size_t)bd.nslot * bd.slot_elems, 0);
         std::vector<double> Dbuf;   // D of the last computed GEMM, [m][s][zl]
