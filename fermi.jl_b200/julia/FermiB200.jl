@@ -104,8 +104,9 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
         elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV") && get(ENV, "FERMI_PT_B200_AO", "sparse") == "sparse"
             # default conventional route of the reference: the MO helper is Chonky, its AO helper holds the *sparse* list
             # (IntegralHelper.jl:88-90); instead of Sparse.jl:78-151,236-393 on the CPU the list itself goes to the GPU
-            aoorbs = AtomicOrbitals(moints.molecule, moints.basis)
-            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=moints.basis, eri_type=Fermi.Integrals.SparseERI())
+            basis = moints.orbitals.basis                          # ROIntegrals.jl:3
+            aoorbs = AtomicOrbitals(moints.molecule, basis)
+            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=basis, eri_type=Fermi.Integrals.SparseERI())
             eri = aoints["ERI"]                                   # FermiSparse{Float64,Int16,4}: .indexes (zero-based), .data
             C = moints.orbitals.C
             core = Options.get("drop_occ"); inac = Options.get("drop_vir")
@@ -119,8 +120,9 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
         elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV")
             # dense AO integrals and no cached (ov|vv): instead of compute_OVVV!/OOOV!/OVOV! on the CPU (Chonky.jl:28-114) hand
             # the AO tensor and the orbital blocks over; the AO helper is built exactly as ROIntegrals.jl:1-7 builds it
-            aoorbs = AtomicOrbitals(moints.molecule, moints.basis)
-            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=moints.basis, eri_type=moints.eri_type)
+            basis = moints.orbitals.basis                          # ROIntegrals.jl:3
+            aoorbs = AtomicOrbitals(moints.molecule, basis)
+            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=basis, eri_type=moints.eri_type)
             AOERI = dense(aoints["ERI"])
             C = moints.orbitals.C
             core = Options.get("drop_occ"); inac = Options.get("drop_vir")
