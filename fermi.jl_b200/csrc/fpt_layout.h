@@ -444,6 +444,14 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     return point_energy(w, vv, Dd, a, b, c, (double)(2 - (i == j) - (j == k)));
 }
 
+// Staging area of the energy stage's OV2 tiles: tile t = 2*pair + col sits in ring stage t/4 at tile slot t%4, so that the
+// producer can refill a ring stage with its four tiles as soon as the consumers have released that stage, while the last
+// k-loop still runs out of the other stages.  OV_STAGE_STRIDE = doubles per ring stage (checked in fpt_triples.cuh).
+constexpr int OV_STAGE_STRIDE = 1096;
+constexpr int OV_TILES_PER_STAGE = 4;
+FPT_HD int ov_stage_off(int t) { return (t / OV_TILES_PER_STAGE) * OV_STAGE_STRIDE + (t % OV_TILES_PER_STAGE) * 256; }
+#define OVP(k) ((((k) >> 1) * fpt::OV_STAGE_STRIDE) + (((k) & 1) * 512))   /* offset of pair k's (B, C) tile couple */
+
 // `ovs` holds the 12 OV2 tiles whose row index is a -- [(pair: jk,kj,ik,ki,ij,ji) x (column tile: B, C)][16][16] -- staged in
 // shared memory by the producer (TMA) so that the a-loop has no global loads; see ov2_stage_src.
 template <bool ALL16>
@@ -500,17 +508,17 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
         double Yd, Zd, p;
         const double t1i_a = t1i[a], t1j_a = t1j[a], t1k_a = t1k[a];
         // D0 = t1i_a jk_bc + ik_ac t1j_b + ij_ab t1k_c
-        p = t1i_a * jk_bc + sac[2 * 512 + ac] * t1j_b + sab[4 * 512 + ab] * t1k_c;  Yd = p;  X += w0 * p;
+        p = t1i_a * jk_bc + sac[OVP(2) + ac] * t1j_b + sab[OVP(4) + ab] * t1k_c;  Yd = p;  X += w0 * p;
         // D1 = t1i_a jk_cb + ik_ab t1j_c + ij_ac t1k_b
-        p = t1i_a * jk_cb + sab[2 * 512 + ab] * t1j_c + sac[4 * 512 + ac] * t1k_b;  Zd = p;  X += w1 * p;
+        p = t1i_a * jk_cb + sab[OVP(2) + ab] * t1j_c + sac[OVP(4) + ac] * t1k_b;  Zd = p;  X += w1 * p;
         // D2 = t1i_b jk_ac + ik_bc t1j_a + ij_ba t1k_c
-        p = t1i_b * sac[0 * 512 + ac] + ik_bc * t1j_a + sab[5 * 512 + ab] * t1k_c;  Zd += p; X += w2 * p;
+        p = t1i_b * sac[OVP(0) + ac] + ik_bc * t1j_a + sab[OVP(5) + ab] * t1k_c;  Zd += p; X += w2 * p;
         // D3 = t1i_b jk_ca + ik_ba t1j_c + ij_bc t1k_a
-        p = t1i_b * sac[1 * 512 + ac] + sab[3 * 512 + ab] * t1j_c + ij_bc * t1k_a;  Yd += p; X += w3 * p;
+        p = t1i_b * sac[OVP(1) + ac] + sab[OVP(3) + ab] * t1j_c + ij_bc * t1k_a;  Yd += p; X += w3 * p;
         // D4 = t1i_c jk_ab + ik_cb t1j_a + ij_ca t1k_b
-        p = t1i_c * sab[0 * 512 + ab] + ik_cb * t1j_a + sac[5 * 512 + ac] * t1k_b;  Yd += p; X += w4 * p;
+        p = t1i_c * sab[OVP(0) + ab] + ik_cb * t1j_a + sac[OVP(5) + ac] * t1k_b;  Yd += p; X += w4 * p;
         // D5 = t1i_c jk_ba + ik_ca t1j_b + ij_cb t1k_a
-        p = t1i_c * sab[1 * 512 + ab] + sac[3 * 512 + ac] * t1j_b + ij_cb * t1k_a;  Zd += p; X += w5 * p;
+        p = t1i_c * sab[OVP(1) + ab] + sac[OVP(3) + ac] * t1j_b + ij_cb * t1k_a;  Zd += p; X += w5 * p;
         const double Y = Ye + Yd, Z = Zo + Zd;
         const double Ef = (Y - 2.0 * Z) * Ye + (Z - 2.0 * Y) * Zo + 3.0 * X;                       // ijk.jl:132
         const double den = (Dbc - P.fv[a]) * (double)(1 + (a == b) + (b == c));                   // ijk.jl:133

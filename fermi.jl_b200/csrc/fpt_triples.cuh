@@ -35,7 +35,9 @@ static_assert(NCTHREADS * CONSUMER_REGS + 128 * PRODUCER_REGS <= NTHREADS * LAUN
 constexpr int QSTAGES = 3;
 constexpr int QBLK = (TMAX + 1) * KGROUP + 2;      // doubles per (group, s) block: TZ rows of 16 kappa, skewed by 16 B mod 128 B
                                                    // so that the s=0 / s=1 halves of a quarter-warp hit disjoint banks
-static_assert(OV_STAGE_TILES * 256 <= QSTAGES * CHUNK_GROUPS * 2 * QBLK, "the energy stage's OV2 tiles are staged in the Q ring area");
+static_assert(OV_STAGE_TILES == QSTAGES * OV_TILES_PER_STAGE && OV_TILES_PER_STAGE * 256 <= CHUNK_GROUPS * 2 * QBLK &&
+                  OV_STAGE_STRIDE == CHUNK_GROUPS * 2 * QBLK,
+              "the energy stage's OV2 tiles are staged in the Q ring area, four per ring stage");
 constexpr int QSTAGE_DOUBLES = CHUNK_GROUPS * 2 * QBLK;                // 1096 doubles = 8768 B
 constexpr int WSLOT_DOUBLES = MAX_SLOTS * TMAX * TMAX * TMAX;          // 24576 doubles = 192 KB
 constexpr int MTW_MAX = 2;
@@ -167,21 +169,23 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
                 producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
             }
         }
-        // Energy stage of this item: once the consumers have drained the ring (all stages released), its area is reused
-        // for the 12 OV2 tiles whose row index is a, so that the a-loop of the energy stage reads shared memory only.
+        // Energy stage of this item: the ring area is reused for the 12 OV2 tiles whose row index is a, so that the a-loop of the
+        // energy stage reads shared memory only.  Stage by stage, oldest first: as soon as the consumers have released a stage
+        // (its last Q chunk is consumed) its four tiles are fetched, while the last k-loop still runs out of the other stages.
         {
             int st = stage;
             uint32_t ph = sphase;
-            for (int t = 0; t < QSTAGES; t++) {
-                mbar_wait((uint64_t*)&tail->empty[st], ph ^ 1);
-                if (++st == QSTAGES) { st = 0; ph ^= 1; }
-            }
-            fence_proxy_async();   // same hazard: the ring area was read with LDS, the OV2 tiles arrive through the async proxy
             uint64_t* ob = (uint64_t*)&tail->ov_full;
             mbar_arrive_expect_tx(ob, (uint32_t)(OV_STAGE_TILES * 256 * sizeof(double)));
+            for (int t = 0; t < QSTAGES; t++) {
+                mbar_wait((uint64_t*)&tail->empty[st], ph ^ 1);
+                fence_proxy_async();   // same hazard as above: the stage was read with LDS, the tiles arrive through the async proxy
 #pragma unroll 1
-            for (int t = 0; t < OV_STAGE_TILES; t++)
-                tma_bulk_g2s(Qsm + t * 256, P.OV2 + ov2_stage_src(P, ctl->item, t), 256 * sizeof(double), ob);
+                for (int u = 0; u < OV_TILES_PER_STAGE; u++)
+                    tma_bulk_g2s(Qsm + st * QSTAGE_DOUBLES + u * 256, P.OV2 + ov2_stage_src(P, ctl->item, st * OV_TILES_PER_STAGE + u),
+                                 256 * sizeof(double), ob);
+                if (++st == QSTAGES) { st = 0; ph ^= 1; }
+            }
             mbar_wait((uint64_t*)&tail->ov_empty, n & 1);   // energy stage done: the ring may be refilled
         }
     }
@@ -470,7 +474,7 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
 #define FPT_DISPATCH(MTWv, NTv, CALL)                                      \
     do {                                                                   \
         switch (MTWv) {                                                    \
-        case 0: FPT_DISPATCH_NT(0, NTv, CALL) break;                       \
+        case 0: { constexpr int MTW = 0, NT = 1; CALL; } break;            \
         case 1: FPT_DISPATCH_NT(1, NTv, CALL) break;                       \
         default: FPT_DISPATCH_NT(2, NTv, CALL) break;                      \
         }                                                                  \
@@ -544,14 +548,18 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
                 const int gnext = t + 1 < ngemm ? ctl->ent.forder[t + 1] : -1;
                 const int fbits = ctl->ent.ffirst[t];
                 const int nt = ctl->ent.gemm[g].TZ >> 2;
-                // rs (set up during the previous GEMM) holds this warp's share of row tiles: 0, 1 or 2
-                FPT_DISPATCH(rs.nvalid, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                // rs (set up during the previous GEMM) holds this warp's share of row tiles: 0, 1 or 2.  The broadcast tells the
+                // compiler that the value is warp-uniform: without it the k-loops are compiled as potentially divergent code
+                // (BSSY / WARPSYNC / BRA.DIV in the hot loop, no uniform-datapath instructions: -1.5 % on full-tile shapes)
+                const int nv = __shfl_sync(0xffffffffu, rs.nvalid, 0);
+                FPT_DISPATCH(nv, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         } else {
             for (int g = 0; g < ngemm; g++) {
                 if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
                 const int nt = ctl->ent.gemm[g].TZ >> 2;
-                FPT_DISPATCH(rs.nvalid, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                const int nv = __shfl_sync(0xffffffffu, rs.nvalid, 0);   // warp-uniform, see above
+                FPT_DISPATCH(nv, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         }
         if (PROF) t1 = clock64();

@@ -155,9 +155,9 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         }
         for (size_t t = 0; t < hits.size(); t++)
             if (hits[t] != 6) { fprintf(stderr, "slot element %zu received %d contributions (want 6)\n", t, hits[t]); return 4; }
-        std::vector<double> ovs((size_t)OV_STAGE_TILES * 256);
+        std::vector<double> ovs((size_t)(OV_STAGE_TILES / OV_TILES_PER_STAGE) * OV_STAGE_STRIDE);
         for (int t = 0; t < OV_STAGE_TILES; t++)
-            for (int e = 0; e < 256; e++) ovs[(size_t)t * 256 + e] = P.OV2[ov2_stage_src(P, it, t) + e];
+            for (int e = 0; e < 256; e++) ovs[(size_t)ov_stage_off(t) + e] = P.OV2[ov2_stage_src(P, it, t) + e];
         double e_pt = 0.0, e_col = 0.0;
         for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
         for (int bl = 0; bl < bd.ts[1]; bl++)
