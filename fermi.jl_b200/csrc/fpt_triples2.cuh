@@ -280,7 +280,7 @@ triples_kernel2(Problem P, i64 item_begin, i64 item_end, unsigned long long* cou
             const GemmDesc& gd = ctl->ent.gemm[g];
             const int nt = gd.TZ >> 2;
             // rs (set up during the previous GEMM) holds this warp's share of row tiles: 0, 1 or 2
-            switch (rs.nvalid) {
+            switch (__shfl_sync(0xffffffffu, rs.nvalid, 0)) {   // broadcast: warp-uniform for the compiler (see fpt_triples.cuh)
             case 0: FPT_DISPATCH_NT(0, nt, (gemm_body2<MTW, NT, PROF>(P, ctl, g, rs, a, Qsm, tail, stage, sphase, pcount, tmem_base, warp, lane, prof))) break;
             case 1: FPT_DISPATCH_NT(1, nt, (gemm_body2<MTW, NT, PROF>(P, ctl, g, rs, a, Qsm, tail, stage, sphase, pcount, tmem_base, warp, lane, prof))) break;
             default: FPT_DISPATCH_NT(2, nt, (gemm_body2<MTW, NT, PROF>(P, ctl, g, rs, a, Qsm, tail, stage, sphase, pcount, tmem_base, warp, lane, prof))) break;
