@@ -360,7 +360,7 @@ __device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs
         const bool first = MODE == 0 ? gd.dfirst[e] != 0 : ((first_bits >> e) & 1) != 0;
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) {
-            if (mt < rs.nvalid) {
+            {   // MTW is this warp's own tile count (dispatch on rs.nvalid): every mt < MTW is a valid row tile
                 DestIter it;
                 dest_iter_init_fast(dbase, sel, Tb, Tc, xl[mt], yl[mt], kk, it);
                 if (MODE == 1) {
@@ -378,9 +378,6 @@ __device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs
 #pragma unroll
                     for (int ct = 0; ct < NT; ct++) Wsm[dest_iter_off(it, ct)] += acc[mt][ct][e];
                 }
-            } else if (MODE == 1) {
-#pragma unroll
-                for (int ct = 0; ct < NT; ct++) acc[mt][ct][e] = 0.0;
             }
         }
     }
