@@ -124,7 +124,7 @@ static int nccl_load()
 static int broadcast_operands(fpt_handle* h);
 
 extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
-extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.2 (sm_100a)"; }
+extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.3 (sm_100a)"; }
 
 static int create_one(int dev, fpt_handle** out)
 {

@@ -1,5 +1,6 @@
-// Inline-PTX wrappers used by the sm_100a kernels: DMMA.8x8x4, streaming 16-byte global loads, TMA bulk copies
-// (cp.async.bulk, SASS UBLKCP) completing on mbarriers, mbarrier wait/arrive, named barriers.
+// Inline-PTX wrappers used by the sm_100a kernels: DMMA.8x8x4, streaming 32-byte global loads, TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) completing on mbarriers, mbarrier wait/arrive, named barriers, proxy fences, setmaxnreg,
+// and the tensor-memory wrappers (tcgen05.alloc / st / ld) of the experimental epilogue-warp kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,12 +14,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
-}
-__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p)
-{
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
 }
 struct __align__(32) double4x { double x, y, z, w; };
 // 256-bit streaming load (sm_100: LDG.E.256): one full 128-byte line per row for the 4 lanes that share it
