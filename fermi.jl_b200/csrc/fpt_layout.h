@@ -41,6 +41,7 @@ constexpr int KGROUP = 16;     // kappa per group: one 32-byte (256-bit) load pe
 constexpr int CHUNK_GROUPS = 2;  // kappa groups per shared-memory Q stage (32 kappa)
 constexpr int MAX_SLOTS = 6;
 constexpr int MAX_GEMMS = 18;
+constexpr int SYM_GEMMS = 12;   // GEMMs of a six-slot block that run for a triplet with i = j or j = k
 
 typedef long long i64;
 
@@ -260,28 +261,49 @@ struct BlockTabEntry {
     unsigned char ffirst[MAX_GEMMS + 2];   // bit s: D[..., s, ...] of forder[t] is the first contribution to its slot
     int fast_ok;
     int pad_;
+    // The same for triplets with two equal occupied indices (class 0: i = j, class 1: j = k), where only 12 GEMMs run and the
+    // W tensor is completed by symmetry in the energy stage (see sym_emask): order and first-contribution flags of those 12.
+    unsigned char sorder[2][SYM_GEMMS];
+    unsigned char sfirst[2][SYM_GEMMS];
 };
 static_assert(sizeof(BlockTabEntry) % 16 == 0, "BlockTabEntry is moved by 16-byte-granular bulk copies");
 
 FPT_HD int gemm_slot(const BlockDesc& bd, const GemmDesc& g, int s) { return g.dbase[s] / bd.slot_elems; }
 
-// depth-first search for the order described at BlockTabEntry::forder (18 nodes, dense compatibility graph: trivial); host only
-inline bool fast_order_dfs(const BlockTabEntry& e, unsigned char* order, bool* used, int depth)
+// Triplets with i = j (class 0) or j = k (class 1) in a six-slot block.  For i = j the operands of the p = j GEMM equal those
+// of the p = i GEMM and the two column halves of the p = k GEMM are equal (Q_ij = Q_ji); the contributions that are *not*
+// computed are exactly the computed ones with the first two W indices exchanged:  W[x,y,z] = T[x,y,z] + T[y,x,z], where T
+// collects  p = i (both halves)  and  p = k (half s = 0 only).  For j = k:  W[x,y,z] = T[x,y,z] + T[x,z,y]  with T from
+// p = j (both halves) and p = i (half s = 0).  The energy stage adds the mirror image when it reads the slots
+// (block_column_energy_t, `sym`), so 12 of the 18 GEMMs run, none is added twice, and every one of them can take the
+// load-accumulate-store form.  sym_emask: which column halves of GEMM position `pi` (0 = i, 1 = j, 2 = k) are kept
+// (bit s), 0 = the GEMM does not run.
+FPT_HD int sym_emask(int cls, int pi)
 {
-    if (depth == e.ngemm) return true;
-    for (int g = 0; g < e.ngemm; g++) {
-        if (used[g]) continue;
+    if (cls == 0) return pi == 0 ? 3 : (pi == 2 ? 1 : 0);
+    return pi == 1 ? 3 : (pi == 0 ? 1 : 0);
+}
+
+// depth-first search for an order of `n` nodes (GEMM index, kept halves) in which neighbours write different slots
+// (18 or 12 nodes, dense compatibility graph: trivial); host only
+inline bool slot_order_dfs(const BlockTabEntry& e, const unsigned char* node_g, const unsigned char* node_mask, int n,
+                           unsigned char* order, bool* used, int depth)
+{
+    if (depth == n) return true;
+    for (int c = 0; c < n; c++) {
+        if (used[c]) continue;
         if (depth > 0) {
-            const GemmDesc& pr = e.gemm[order[depth - 1]];
-            const GemmDesc& cu = e.gemm[g];
+            const int pr = order[depth - 1];
             bool clash = false;
             for (int s = 0; s < 2; s++)
-                for (int t = 0; t < 2; t++) clash = clash || gemm_slot(e.bd, pr, s) == gemm_slot(e.bd, cu, t);
+                for (int t = 0; t < 2; t++)
+                    if (((node_mask[pr] >> s) & 1) && ((node_mask[c] >> t) & 1))
+                        clash = clash || gemm_slot(e.bd, e.gemm[node_g[pr]], s) == gemm_slot(e.bd, e.gemm[node_g[c]], t);
             if (clash) continue;
         }
-        used[g] = true; order[depth] = (unsigned char)g;
-        if (fast_order_dfs(e, order, used, depth + 1)) return true;
-        used[g] = false;
+        used[c] = true; order[depth] = (unsigned char)c;
+        if (slot_order_dfs(e, node_g, node_mask, n, order, used, depth + 1)) return true;
+        used[c] = false;
     }
     return false;
 }
@@ -290,15 +312,46 @@ inline void make_fast_order(BlockTabEntry& e)
 {
     e.fast_ok = 0; e.pad_ = 0;
     for (int t = 0; t < MAX_GEMMS + 2; t++) { e.forder[t] = 0; e.ffirst[t] = 0; }
+    for (int c = 0; c < 2; c++)
+        for (int t = 0; t < SYM_GEMMS; t++) { e.sorder[c][t] = 0; e.sfirst[c][t] = 0; }
     if (e.bd.nslot != MAX_SLOTS || e.ngemm != MAX_GEMMS) return;
-    bool used[MAX_GEMMS] = {};
-    if (!fast_order_dfs(e, e.forder, used, 0)) return;
-    bool touched[MAX_SLOTS] = {};
-    for (int t = 0; t < e.ngemm; t++)
-        for (int s = 0; s < 2; s++) {
-            const int sl = gemm_slot(e.bd, e.gemm[e.forder[t]], s);
-            if (!touched[sl]) { e.ffirst[t] |= (unsigned char)(1 << s); touched[sl] = true; }
+    // all 18 GEMMs, both halves (triplets i > j > k)
+    {
+        unsigned char ng[MAX_GEMMS], nm[MAX_GEMMS], ord[MAX_GEMMS];
+        bool used[MAX_GEMMS] = {};
+        for (int g = 0; g < MAX_GEMMS; g++) { ng[g] = (unsigned char)g; nm[g] = 3; }
+        if (!slot_order_dfs(e, ng, nm, MAX_GEMMS, ord, used, 0)) return;
+        bool touched[MAX_SLOTS] = {};
+        for (int t = 0; t < MAX_GEMMS; t++) {
+            e.forder[t] = ng[ord[t]];
+            for (int s = 0; s < 2; s++) {
+                const int sl = gemm_slot(e.bd, e.gemm[e.forder[t]], s);
+                if (!touched[sl]) { e.ffirst[t] |= (unsigned char)(1 << s); touched[sl] = true; }
+            }
         }
+    }
+    // the 12 GEMMs of the two symmetric classes
+    for (int c = 0; c < 2; c++) {
+        unsigned char ng[SYM_GEMMS], nm[SYM_GEMMS], ord[SYM_GEMMS];
+        bool used[SYM_GEMMS] = {};
+        int n = 0;
+        for (int g = 0; g < MAX_GEMMS; g++) {
+            const int m = sym_emask(c, e.gemm[g].p);   // table entries hold positions 0/1/2 in p
+            if (m) { ng[n] = (unsigned char)g; nm[n] = (unsigned char)m; n++; }
+        }
+        if (n != SYM_GEMMS || !slot_order_dfs(e, ng, nm, SYM_GEMMS, ord, used, 0)) return;
+        bool touched[MAX_SLOTS] = {};
+        for (int t = 0; t < SYM_GEMMS; t++) {
+            e.sorder[c][t] = ng[ord[t]];
+            for (int s = 0; s < 2; s++) {
+                if (!((nm[ord[t]] >> s) & 1)) continue;
+                const int sl = gemm_slot(e.bd, e.gemm[e.sorder[c][t]], s);
+                if (!touched[sl]) { e.sfirst[c][t] |= (unsigned char)(1 << s); touched[sl] = true; }
+            }
+        }
+        for (int sl = 0; sl < MAX_SLOTS; sl++)
+            if (!touched[sl]) return;   // every slot must receive something (it does: three halves per slot)
+    }
     e.fast_ok = 1;
 }
 
@@ -411,7 +464,7 @@ FPT_HD double point_energy(const double* w, const double* vv, double Dd, int a, 
 
 // Energy contribution of point `pt` (linear index, c fastest) of the block held in the W slots `Wsm`:
 // V build ijk.jl:116 and the a>=b>=c body ijk.jl:127-133.  Returns 0 for padded or non-canonical points.
-FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int pt)
+FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm, int pt, int sym = 0)
 {
     const int TB = bd.ts[1], TC = bd.ts[2];
     const int v = P.v;
@@ -426,15 +479,24 @@ FPT_HD double block_point_energy(const Problem& P, const BlockDesc& bd, int i, i
     // OV2[(q,r)][y][z] = (qy|rz) = OV2[(r,q)][z][y]: always index so that the virtual that comes later in (a,b,c)
     // is the contiguous one -- lanes run over c, so every load is either coalesced or a broadcast.
     double w[6], vv[6];
+    for (int m = 0; m < 6; m++) {
+        const int c0 = perm3(m, 0), c1 = perm3(m, 1), c2 = perm3(m, 2);
+        const int lx = pick3(c0, al, bl, cl), ly = pick3(c1, al, bl, cl), lz = pick3(c2, al, bl, cl);
+        w[m] = Wsm[bd.slot_of_perm[m] * bd.slot_elems + slot_index(lx, ly, lz, bd.ts[c1], bd.ts[c2])];
+    }
+    if (sym == 1) {          // i = j: W[x,y,z] = T[x,y,z] + T[y,x,z]   (perm order: abc, acb, bac, bca, cab, cba)
+        const double s02 = w[0] + w[2], s14 = w[1] + w[4], s35 = w[3] + w[5];
+        w[0] = w[2] = s02; w[1] = w[4] = s14; w[3] = w[5] = s35;
+    } else if (sym == 2) {   // j = k: W[x,y,z] = T[x,y,z] + T[x,z,y]
+        const double s01 = w[0] + w[1], s23 = w[2] + w[3], s45 = w[4] + w[5];
+        w[0] = w[1] = s01; w[2] = w[3] = s23; w[4] = w[5] = s45;
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int m = 0; m < 6; m++) {
         const int c0 = perm3(m, 0), c1 = perm3(m, 1), c2 = perm3(m, 2);
         const int x = pick3(c0, a, b, c), y = pick3(c1, a, b, c), z = pick3(c2, a, b, c);
-        const int lx = pick3(c0, al, bl, cl), ly = pick3(c1, al, bl, cl), lz = pick3(c2, al, bl, cl);
-        const int off = bd.slot_of_perm[m] * bd.slot_elems + slot_index(lx, ly, lz, bd.ts[c1], bd.ts[c2]);
-        w[m] = Wsm[off];
         const double g_jk = (c2 > c1) ? P.OV2[ov2_idx(P, j, k, y, z)] : P.OV2[ov2_idx(P, k, j, z, y)];   // (jy|kz)
         const double g_ik = (c2 > c0) ? P.OV2[ov2_idx(P, i, k, x, z)] : P.OV2[ov2_idx(P, k, i, z, x)];   // (ix|kz)
         const double g_ij = (c1 > c0) ? P.OV2[ov2_idx(P, i, j, x, y)] : P.OV2[ov2_idx(P, j, i, y, x)];   // (ix|jy)
@@ -456,7 +518,7 @@ FPT_HD int ov_stage_off(int t) { return (t / OV_TILES_PER_STAGE) * OV_STAGE_STRI
 // shared memory by the producer (TMA) so that the a-loop has no global loads; see ov2_stage_src.
 template <bool ALL16>
 FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm,
-                                    const double* ovs, int bl, int cl, int al_begin, int al_end)
+                                    const double* ovs, int bl, int cl, int al_begin, int al_end, int sym = 0)
 {
     const int TA = ALL16 ? 16 : bd.ts[0], TB = ALL16 ? 16 : bd.ts[1], TC = ALL16 ? 16 : bd.ts[2];
     const int v = P.v;
@@ -495,12 +557,19 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
     for (int al = al_begin; al < al_end; al++) {
         const int a = a0 + al;
         const int ab = al << 4, ac = al << 4;
-        const double w0 = Wsm[s0 + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
-        const double w1 = Wsm[s1 + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
-        const double w2 = Wsm[s2 + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
-        const double w3 = Wsm[s3 + slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
-        const double w4 = Wsm[s4 + slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
-        const double w5 = Wsm[s5 + slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
+        double w0 = Wsm[s0 + slot_index(al, bl, cl, TB, TC)];   // W[a,b,c]
+        double w1 = Wsm[s1 + slot_index(al, cl, bl, TC, TB)];   // W[a,c,b]
+        double w2 = Wsm[s2 + slot_index(bl, al, cl, TA, TC)];   // W[b,a,c]
+        double w3 = Wsm[s3 + slot_index(bl, cl, al, TC, TA)];   // W[b,c,a]
+        double w4 = Wsm[s4 + slot_index(cl, al, bl, TA, TB)];   // W[c,a,b]
+        double w5 = Wsm[s5 + slot_index(cl, bl, al, TB, TA)];   // W[c,b,a]
+        if (sym == 1) {          // i = j: the slots hold T, W[x,y,z] = T[x,y,z] + T[y,x,z] (sym_emask)
+            const double s02 = w0 + w2, s14 = w1 + w4, s35 = w3 + w5;
+            w0 = w2 = s02; w1 = w4 = s14; w3 = w5 = s35;
+        } else if (sym == 2) {   // j = k: W[x,y,z] = T[x,y,z] + T[x,z,y]
+            const double s01 = w0 + w1, s23 = w2 + w3, s45 = w4 + w5;
+            w0 = w1 = s01; w2 = w3 = s23; w4 = w5 = s45;
+        }
         // V = W + D with D the disconnected term (ijk.jl:116); every product t1*g is consumed as soon as it is formed:
         //   X = sum_m W_m V_m = Xw + Xd,  Y = V0+V3+V4 = Ye + Yd,  Z = V1+V2+V5 = Zo + Zd
         const double Ye = w0 + w3 + w4, Zo = w1 + w2 + w5;
@@ -531,11 +600,11 @@ FPT_HD double block_column_energy_t(const Problem& P, const BlockDesc& bd, int i
 // so that one thread owns (b,c), hoists everything that does not depend on a and walks a with 12 loads per point, each
 // either contiguous in c across the lanes or a broadcast.  This is what the kernel runs; the emulator checks it.
 FPT_HD double block_column_energy(const Problem& P, const BlockDesc& bd, int i, int j, int k, const double* Wsm,
-                                  const double* ovs, int bl, int cl, int al_begin, int al_end)
+                                  const double* ovs, int bl, int cl, int al_begin, int al_end, int sym = 0)
 {
     if (bd.ts[0] == 16 && bd.ts[1] == 16 && bd.ts[2] == 16)
-        return block_column_energy_t<true>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end);
-    return block_column_energy_t<false>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end);
+        return block_column_energy_t<true>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end, sym);
+    return block_column_energy_t<false>(P, bd, i, j, k, Wsm, ovs, bl, cl, al_begin, al_end, sym);
 }
 
 // Source (offset into OV2) of staged tile t = 2*pair + col, pair in (jk,kj,ik,ki,ij,ji), col 0 = tile B, 1 = tile C,

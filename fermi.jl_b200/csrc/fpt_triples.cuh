@@ -114,10 +114,21 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
 // Producer: one thread.  Streams the Q chunks of every GEMM of every item through the ring.  Item n+1 is fetched and
 // decoded while the chunks of item n are still streaming (right after its first GEMM), so the ring never runs dry at an
 // item boundary.
-__device__ __forceinline__ bool item_is_fast(const Problem& P, const Ctl* ctl)
+// How an item updates the W slots.  0: accumulate path (RMW, twin-GEMM reuse).  Six-slot blocks: 1: load-accumulate-store over
+// all 18 GEMMs (i > j > k); 2 / 3: i = j / j = k -- the 12 GEMMs of BlockTabEntry::sorder[mode - 2], W completed by symmetry in
+// the energy stage (sym_emask).  dbg_flags 64 / 128 force the accumulate path for all items / for the symmetric classes.
+__device__ __forceinline__ int item_mode(const Problem& P, const Ctl* ctl)
 {
-    return ctl->ent.fast_ok && ctl->item.i != ctl->item.j && ctl->item.j != ctl->item.k && !(P.dbg_flags & 64);
+    if (!ctl->ent.fast_ok || (P.dbg_flags & 64)) return 0;
+    if (ctl->item.i == ctl->item.j) return (P.dbg_flags & 128) ? 0 : 2;
+    if (ctl->item.j == ctl->item.k) return (P.dbg_flags & 128) ? 0 : 3;
+    return 1;
 }
+// t-th GEMM of an item in mode >= 1, and which of its column halves are kept / which are first contributions
+__device__ __forceinline__ int seq_len(const Ctl* ctl, int mode) { return mode == 1 ? ctl->ent.ngemm : SYM_GEMMS; }
+__device__ __forceinline__ int seq_gemm(const Ctl* ctl, int mode, int t) { return mode == 1 ? ctl->ent.forder[t] : ctl->ent.sorder[mode - 2][t]; }
+__device__ __forceinline__ int seq_first(const Ctl* ctl, int mode, int t) { return mode == 1 ? ctl->ent.ffirst[t] : ctl->ent.sfirst[mode - 2][t]; }
+__device__ __forceinline__ int seq_emask(const Ctl* ctl, int mode, int g) { return mode == 1 ? 3 : sym_emask(mode - 2, ctl->ent.gemm[g].p); }
 
 template <bool FASTOK, class Tail>
 __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
@@ -134,11 +145,11 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
         const Ctl* ctl = &tail->ctl[slot];
         mbar_wait((uint64_t*)&tail->item_full[slot], (n >> 1) & 1);   // own TMA copy of the table entry has landed
         if (ctl->cur_item < 0) break;
-        const int ngemm = ctl->ent.ngemm;
-        const bool fast = FASTOK && item_is_fast(P, ctl);
+        const int mode = FASTOK ? item_mode(P, ctl) : 0;
+        const int ngemm = mode ? seq_len(ctl, mode) : ctl->ent.ngemm;
         for (int t = 0; t < ngemm; t++) {
-            const int g = fast ? ctl->ent.forder[t] : t;
-            if (!fast && gemm_is_dup(ctl->item, g)) continue;   // no k-loop for twin GEMMs (i == j or j == k)
+            const int g = mode ? seq_gemm(ctl, mode, t) : t;
+            if (!mode && gemm_is_dup(ctl->item, g)) continue;   // no k-loop for twin GEMMs (i == j or j == k)
             const GemmDesc& gd = ctl->ent.gemm[g];
             const uint32_t row_bytes = (uint32_t)gd.TZ * KGROUP * sizeof(double);
             const int q = occ_pick(ctl->item, gd.q), r = occ_pick(ctl->item, gd.r);
@@ -342,7 +353,7 @@ __device__ __forceinline__ void gemm_kloop(const Problem& P, const GemmDesc& gd,
 // MODE 2: store the accumulators.
 template <int MTW, int NT, int MODE>
 __device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs, double (&acc)[MTW][NT][2], double* Wsm, int lane,
-                                            int first_bits)
+                                            int first_bits, int emask = 3)
 {
     const int kk = lane & 3, r = lane >> 2;
     int xl[MTW], yl[MTW];
@@ -354,6 +365,15 @@ __device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs
     }
 #pragma unroll
     for (int e = 0; e < 2; e++) {
+        if (MODE != 0 && !((emask >> e) & 1)) {   // symmetric class: this column half is not kept
+            if (MODE == 1) {
+#pragma unroll
+                for (int mt = 0; mt < MTW; mt++)
+#pragma unroll
+                    for (int ct = 0; ct < NT; ct++) acc[mt][ct][e] = 0.0;
+            }
+            continue;
+        }
         // X and Z the same tile: D(s=0)[x=u,z=w] and D(s=1)[x=w,z=u] of different warps alias -> separate the column sets
         if (MODE == 0 && e == 1 && gd.diag_xz) consumer_bar();
         const int dbase = gd.dbase[e], sel = gd.dsel[e], Tb = gd.dTb[e], Tc = gd.dTc[e];
@@ -426,7 +446,7 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
 
 // load-accumulate-store form of one GEMM (see the comment at the top): g = forder[t], gnext = forder[t+1] or -1
 template <int MTW, int NT, bool PROF>
-__device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl, int g, int gnext, int first_bits, RowSet& rs,
+__device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl, int g, int gnext, int first_bits, int emask, RowSet& rs,
                                                double4x (&a)[ABUF][MTW_MAX], double* Wsm, const double* Qsm, SmemTail* tail,
                                                int& stage, uint32_t& sphase, uint32_t& gcount, int warp, int lane, long long* prof)
 {
@@ -438,8 +458,8 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
         mbar_wait((uint64_t*)&tail->rmw_done[gcount & 1], ((gcount - 2) >> 1) & 1);
     if (PROF) { t1 = clock64(); prof[6] += t1 - t0; }
     if constexpr (MTW > 0) {
-        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, first_bits);
-        else gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, 3);
+        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, first_bits, emask);
+        else gemm_wslots<MTW, NT, 1>(gd, rs, acc, Wsm, lane, 3, emask);
     }
     if (PROF) { t0 = clock64(); prof[7] += t0 - t1; }
     if constexpr (MTW > 0) gemm_kloop<MTW, NT, PROF, false>(P, gd, rs, a, acc, Qsm, tail, stage, sphase, lane, prof);
@@ -452,7 +472,7 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
         a_prologue2(P, rs, a);
     }
     if constexpr (MTW > 0) {
-        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 2>(gd, rs_cur, acc, Wsm, lane, 0);
+        if (!(P.dbg_flags & 1)) gemm_wslots<MTW, NT, 2>(gd, rs_cur, acc, Wsm, lane, 0, emask);
         else if (acc[0][0][0] == 1.2345e300) Wsm[0] = acc[0][0][1];
     }
     __syncwarp();
@@ -530,26 +550,28 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         if (PROF) { t1 = clock64(); prof[0] += t1 - t0; }
 
         const int ngemm = ctl->ent.ngemm;
-        const bool fast = item_is_fast(P, ctl);
-        const int gfirst = fast ? ctl->ent.forder[0] : 0;
+        const int mode = item_mode(P, ctl);
+        const int gfirst = mode ? seq_gemm(ctl, mode, 0) : 0;
         RowSet rs;
         rows_setup2(P, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
         a_prologue2(P, rs, a);
-        // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst / ffirst); the
-        // barrier at the end of the previous item's energy stage already ordered those stores after its reads
+        // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst / ffirst / sfirst);
+        // the barrier at the end of the previous item's energy stage already ordered those stores after its reads
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 
-        if (fast) {
-            for (int t = 0; t < ngemm; t++) {
-                const int g = ctl->ent.forder[t];
-                const int gnext = t + 1 < ngemm ? ctl->ent.forder[t + 1] : -1;
-                const int fbits = ctl->ent.ffirst[t];
+        if (mode) {
+            const int nseq = seq_len(ctl, mode);
+            for (int t = 0; t < nseq; t++) {
+                const int g = seq_gemm(ctl, mode, t);
+                const int gnext = t + 1 < nseq ? seq_gemm(ctl, mode, t + 1) : -1;
+                const int fbits = seq_first(ctl, mode, t);
+                const int emask = seq_emask(ctl, mode, g);
                 const int nt = ctl->ent.gemm[g].TZ >> 2;
                 // rs (set up during the previous GEMM) holds this warp's share of row tiles: 0, 1 or 2.  The broadcast tells the
                 // compiler that the value is warp-uniform: without it the k-loops are compiled as potentially divergent code
                 // (BSSY / WARPSYNC / BRA.DIV in the hot loop, no uniform-datapath instructions: -1.5 % on full-tile shapes)
                 const int nv = __shfl_sync(0xffffffffu, rs.nvalid, 0);
-                FPT_DISPATCH(nv, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                FPT_DISPATCH(nv, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, emask, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         } else {
             for (int g = 0; g < ngemm; g++) {
@@ -571,10 +593,10 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
             if (!(P.dbg_flags & 2)) {
                 if (bd.slot_elems == 4096)
                     esum += block_column_energy_t<true>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, Qsm, tt >> 4, tt & 15,
-                                                        half * 8, half * 8 + 8);
+                                                        half * 8, half * 8 + 8, mode >= 2 ? mode - 1 : 0);
                 else if (tt < bd.ts[1] * TC)
                     esum += block_column_energy_t<false>(P, bd, ctl->item.i, ctl->item.j, ctl->item.k, Wsm, Qsm, tt / TC, tt % TC,
-                                                         half * 8, half * 8 + 8);
+                                                         half * 8, half * 8 + 8, mode >= 2 ? mode - 1 : 0);
             }
         }
         if (PROF) t1 = clock64();

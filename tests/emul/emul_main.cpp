@@ -96,13 +96,13 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
         make_block(it.A, it.B, it.C, P.vp, bd);
         GemmDesc gd[MAX_GEMMS];
         const int ng = make_gemms(bd, 0, 1, 2, gd);   // positions, as in the device block table
+        BlockTabEntry ent{};
+        ent.bd = bd; ent.ngemm = ng;
+        for (int g = 0; g < ng; g++) ent.gemm[g] = gd[g];
+        make_fast_order(ent);
         for (int g = 0; g < ng; g++) { gd[g].p = occ_pick(it, gd[g].p); gd[g].q = occ_pick(it, gd[g].q); gd[g].r = occ_pick(it, gd[g].r); }
         {   // the load-accumulate-store order of the block table (BlockTabEntry::forder / ffirst) must be a permutation of the
             // GEMMs in which neighbours write different slots, with exactly the first contribution of every slot flagged
-            BlockTabEntry ent{};
-            ent.bd = bd; ent.ngemm = ng;
-            for (int g = 0; g < ng; g++) ent.gemm[g] = gd[g];
-            make_fast_order(ent);
             if ((bd.nslot == MAX_SLOTS) != (ent.fast_ok != 0)) { fprintf(stderr, "fast order missing for a six-slot block\n"); return 10; }
             if (ent.fast_ok) {
                 bool seen[MAX_GEMMS] = {}, touched[MAX_SLOTS] = {};
@@ -123,18 +123,46 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
                 }
             }
         }
+        // triplets with i = j or j = k in a six-slot block: only the 12 GEMMs of BlockTabEntry::sorder run, half of them keep
+        // one column half only, and the energy stage completes W by symmetry (sym_emask).  Check order, flags and energy.
+        const int cls = (it.i == it.j) ? 0 : ((it.j == it.k) ? 1 : -1);
+        const bool symmetric = ent.fast_ok && cls >= 0;
+        if (symmetric) {
+            bool seen[MAX_GEMMS] = {}, touched[MAX_SLOTS] = {};
+            for (int t = 0; t < SYM_GEMMS; t++) {
+                const int g = ent.sorder[cls][t];
+                const int em = sym_emask(cls, ent.gemm[g].p);
+                if (g >= ng || seen[g] || em == 0) { fprintf(stderr, "bad symmetric order\n"); return 15; }
+                seen[g] = true;
+                for (int s2 = 0; s2 < 2; s2++) {
+                    if (!((em >> s2) & 1)) continue;
+                    const int sl = gemm_slot(bd, gd[g], s2);
+                    if (t > 0) {
+                        const int gp = ent.sorder[cls][t - 1], emp = sym_emask(cls, ent.gemm[gp].p);
+                        for (int s3 = 0; s3 < 2; s3++)
+                            if (((emp >> s3) & 1) && sl == gemm_slot(bd, gd[gp], s3)) { fprintf(stderr, "symmetric neighbours share a slot\n"); return 16; }
+                    }
+                    const bool first = !touched[sl];
+                    if (first != (((ent.sfirst[cls][t] >> s2) & 1) != 0)) { fprintf(stderr, "wrong symmetric first flag\n"); return 17; }
+                    touched[sl] = true;
+                }
+            }
+        }
         std::fill(W.begin(), W.begin() + (size_t)bd.nslot * bd.slot_elems, 0.0);
         std::vector<int> hits((size_t)bd.nslot * bd.slot_elems, 0);
         std::vector<double> Dbuf;   // D of the last computed GEMM, [m][s][zl]
         for (int g = 0; g < ng; g++) {
             const GemmDesc& G = gd[g];
-            const bool dup = gemm_is_dup(it, g);   // twin GEMM: the kernel reuses the accumulators instead of recomputing
+            const int emask = symmetric ? sym_emask(cls, ent.gemm[g].p) : 3;
+            if (emask == 0) continue;   // symmetric class: this GEMM does not run
+            const bool dup = !symmetric && gemm_is_dup(it, g);   // twin GEMM: the kernel reuses the accumulators instead of recomputing
             if (!dup) Dbuf.assign((size_t)G.TX * G.TY * 2 * G.TZ, 0.0);
             for (int m = 0; m < G.TX * G.TY; m++) {
                 const int yl = m / G.TX, xl = m % G.TX;
                 const double* prow = P.Pt + pt_row(P, G.p, G.y0 + yl, G.x0 + xl);
                 for (int s = 0; s < 2; s++)
                     for (int zl = 0; zl < G.TZ; zl++) {
+                        if (!((emask >> s) & 1)) continue;   // symmetric class: this column half is not kept
                         double& d = Dbuf[((size_t)m * 2 + s) * G.TZ + zl];
                         if (!dup) {
                             d = 0.0;
@@ -154,15 +182,16 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
             }
         }
         for (size_t t = 0; t < hits.size(); t++)
-            if (hits[t] != 6) { fprintf(stderr, "slot element %zu received %d contributions (want 6)\n", t, hits[t]); return 4; }
+            if (hits[t] != (symmetric ? 3 : 6)) { fprintf(stderr, "slot element %zu received %d contributions\n", t, hits[t]); return 4; }
+        const int sym = symmetric ? cls + 1 : 0;
         std::vector<double> ovs((size_t)(OV_STAGE_TILES / OV_TILES_PER_STAGE) * OV_STAGE_STRIDE);
         for (int t = 0; t < OV_STAGE_TILES; t++)
             for (int e = 0; e < 256; e++) ovs[(size_t)ov_stage_off(t) + e] = P.OV2[ov2_stage_src(P, it, t) + e];
         double e_pt = 0.0, e_col = 0.0;
-        for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt);
+        for (int pt = 0; pt < bd.slot_elems; pt++) e_pt += block_point_energy(P, bd, it.i, it.j, it.k, W.data(), pt, sym);
         for (int bl = 0; bl < bd.ts[1]; bl++)
-            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 0, 8) +
-                         block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 8, 16);
+            for (int cl = 0; cl < bd.ts[2]; cl++) e_col += block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 0, 8, sym) +
+                         block_column_energy(P, bd, it.i, it.j, it.k, W.data(), ovs.data(), bl, cl, 8, 16, sym);
         if (std::fabs(e_pt - e_col) > 1e-13 * (1e-30 + std::fabs(e_pt)) + 1e-18) {
             fprintf(stderr, "column energy %.17g != point energy %.17g\n", e_col, e_pt);
             return 6;
