@@ -288,7 +288,7 @@ def test_nine_group_k_all_distinct_tile_triples(engine, o, v):
 
 def test_randomised_sweep(engine):
     """tools/gpu_fuzz.py: random shapes x routes (conventional / DF / AO / sparse AO) x item orders x kernel variants x
-    triplet windows x shard counts against the oracle (40 cases here; profiles/r01b_gpu_fuzz_150.json holds a 150-case run)."""
+    triplet windows x shard counts against the oracle (40 cases here; profiles/r01e_gpu_fuzz_250.json holds a 250-case run of the final build)."""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "40", "11"], capture_output=True, text=True, cwd=root)
