@@ -400,43 +400,11 @@ extern "C" int fpt_num_items(fpt_handle* h, long long* n)
     return 0;
 }
 
-// Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost; returns part `rank`.
-// In block-major order an item's cost depends on its block (diagonal and edge blocks are cheaper), so boundaries are
-// placed on the prefix sum of block_cost; in triplet-major order every stretch of nb items costs the same.
+// Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost (shard_items in fpt_layout.h,
+// shared with the CPU emulator so that the gloo tests exercise the very same split)
 static void shard_range(const fpt_handle* h, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
 {
-    const Problem& P = h->prob;
-    if (P.order != 1 || P.tw_count <= 0) {
-        *sb = b + (e - b) * rank / world;
-        *se = b + (e - b) * (rank + 1) / world;
-        return;
-    }
-    // cost of items [b, x): whole blocks plus a partial one
-    auto cost_upto = [&](i64 x) {
-        const i64 blk = x / P.tw_count, rem = x - blk * P.tw_count;
-        double c = 0.0;
-        for (i64 t = 0; t < blk; t++) c += h->block_cost[t] * (double)P.tw_count;
-        if (blk < P.nb) c += h->block_cost[blk] * (double)rem;
-        return c;
-    };
-    const double c0 = cost_upto(b), c1 = cost_upto(e);
-    auto boundary = [&](int r) -> i64 {
-        if (r <= 0) return b;
-        if (r >= world) return e;
-        const double target = c0 + (c1 - c0) * r / world;
-        double c = 0.0;
-        for (i64 blk = 0; blk < P.nb; blk++) {
-            const double cb = h->block_cost[blk] * (double)P.tw_count;
-            if (c + cb >= target) {
-                i64 x = blk * P.tw_count + (i64)((target - c) / h->block_cost[blk] + 0.5);
-                return x < b ? b : (x > e ? e : x);
-            }
-            c += cb;
-        }
-        return e;
-    };
-    *sb = boundary(rank);
-    *se = boundary(rank + 1);
+    shard_items(h->prob, h->block_cost.data(), b, e, rank, world, sb, se);
 }
 
 // launch the fused kernel + reduction for [item_begin, item_end) on h's device (asynchronous; result in h->out)

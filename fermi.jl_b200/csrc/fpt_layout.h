@@ -450,6 +450,44 @@ FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block)
     tetra_decode(block, it.A, it.B, it.C);
 }
 
+// Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost; part `rank` is [*sb, *se).
+// In block-major order an item's cost depends on its block (diagonal and edge blocks are cheaper), so boundaries are placed on
+// the prefix sum of block_cost (one entry per block); in triplet-major order every stretch of nb items costs the same.
+inline void shard_items(const Problem& P, const double* cost, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
+{
+    if (P.order != 1 || P.tw_count <= 0) {
+        *sb = b + (e - b) * rank / world;
+        *se = b + (e - b) * (rank + 1) / world;
+        return;
+    }
+    // cost of items [0, x): whole blocks plus a partial one
+    auto cost_upto = [&](i64 x) {
+        const i64 blk = x / P.tw_count, rem = x - blk * P.tw_count;
+        double c = 0.0;
+        for (i64 t = 0; t < blk; t++) c += cost[t] * (double)P.tw_count;
+        if (blk < P.nb) c += cost[blk] * (double)rem;
+        return c;
+    };
+    const double c0 = cost_upto(b), c1 = cost_upto(e);
+    auto boundary = [&](int r) -> i64 {
+        if (r <= 0) return b;
+        if (r >= world) return e;
+        const double target = c0 + (c1 - c0) * r / world;
+        double c = 0.0;
+        for (i64 blk = 0; blk < P.nb; blk++) {
+            const double cb = cost[blk] * (double)P.tw_count;
+            if (c + cb >= target) {
+                i64 x = blk * P.tw_count + (i64)((target - c) / cost[blk] + 0.5);
+                return x < b ? b : (x > e ? e : x);
+            }
+            c += cb;
+        }
+        return e;
+    };
+    *sb = boundary(rank);
+    *se = boundary(rank + 1);
+}
+
 // ---- energy of one (a,b,c) point, ijk.jl:127-133 ---------------------------------------------------------
 // w[m], vv[m] in perm order m: (abc),(acb),(bac),(bca),(cab),(cba)
 FPT_HD double point_energy(const double* w, const double* vv, double Dd, int a, int b, int c, double wijk)

@@ -201,3 +201,38 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
     *Et = E;
     return 0;
 }
+
+// The library's cost-weighted split of the work list (fpt_shard_items) for the CPU tests: same code (shard_items, block_cost,
+// make_gemms of fpt_layout.h), no GPU.  Returns the estimated cost share of the part in *cost_share (1/world when balanced).
+extern "C" int fpt_emul_shard(int o, int v, int order, int rank, int world, long long* item_begin, long long* item_end,
+                              double* cost_share)
+{
+    Problem P{};
+    P.o = o; P.v = v; P.vp = padded_v(v); P.nt = num_tiles(v);
+    P.Kp = roundup(v + o, KGROUP); P.G = P.Kp / KGROUP;
+    P.nb = num_blocks(P.nt);
+    P.order = order; P.tw_begin = 0; P.tw_count = num_triplets(o); P.nitems = P.nb * P.tw_count;
+    std::vector<double> cost((size_t)P.nb);
+    for (i64 b = 0; b < P.nb; b++) {
+        BlockTabEntry ent{};
+        int A, B, C;
+        tetra_decode(b, A, B, C);
+        make_block(A, B, C, P.vp, ent.bd);
+        ent.ngemm = make_gemms(ent.bd, 0, 1, 2, ent.gemm);
+        cost[(size_t)b] = block_cost(ent, P.G);
+    }
+    i64 sb, se;
+    shard_items(P, cost.data(), 0, P.nitems, rank, world, &sb, &se);
+    *item_begin = sb; *item_end = se;
+    if (cost_share) {
+        double tot = 0.0, mine = 0.0;
+        for (i64 it = 0; it < P.nitems; it++) {
+            const i64 blk = order == 1 ? it / P.tw_count : it % P.nb;
+            tot += cost[(size_t)blk];
+            if (it >= sb && it < se) mine += cost[(size_t)blk];
+        }
+        *cost_share = tot > 0 ? mine / tot : 0.0;
+    }
+    return 0;
+}
+

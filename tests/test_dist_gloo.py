@@ -32,7 +32,12 @@ def _worker(rank, world, port, out):
     dp = ctypes.POINTER(ctypes.c_double)
     L.fpt_emulate.argtypes = [ctypes.c_int, ctypes.c_int] + [dp] * 7 + [ctypes.c_int] + [ctypes.c_longlong] * 4 + [
         dp, ctypes.POINTER(ctypes.c_longlong)]
-    ib, ie = fb.host.shard_items(fb.host.num_items(o, v), rank, world)
+    # this rank's part of the work list: the library's own cost-weighted split (same code as fpt_shard_items)
+    L.fpt_emul_shard.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_longlong)] * 2 + [dp]
+    sb, se, share = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_double()
+    assert L.fpt_emul_shard(o, v, 1, rank, world, ctypes.byref(sb), ctypes.byref(se), ctypes.byref(share)) == 0
+    ib, ie = sb.value, se.value
+    assert abs(share.value - 1.0 / world) < 0.1
     e, n = ctypes.c_double(), ctypes.c_longlong()
     rc = L.fpt_emulate(o, v, *[bufs[k].ctypes.data_as(dp) for k in names], 1, 0, -1, ib, ie, ctypes.byref(e), ctypes.byref(n))
     assert rc == 0

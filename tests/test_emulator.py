@@ -56,3 +56,24 @@ def test_item_shards_add_up_and_match_triplet_ranges(emul, order):
     part2, _ = emul(x, order=order, tb=3, te=13)
     ref2 = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=3, t_end=13)
     assert abs(part2 - ref2) < 1e-14
+
+
+@pytest.mark.parametrize("o,v,world", [(4, 21, 3), (6, 50, 8), (24, 114, 8), (5, 19, 2)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_cost_weighted_shards_partition_the_work_list(built, o, v, world, order):
+    """fpt_shard_items' split (shard_items / block_cost in fpt_layout.h, run here on the CPU): the parts are contiguous,
+    cover [0, n_items) exactly once, and carry equal shares of the estimated cost."""
+    L = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "emul", "libfpt_emul.so"))
+    L.fpt_emul_shard.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_longlong)] * 2 + [_dp]
+    n = fb.host.num_items(o, v)
+    prev_end, shares = 0, []
+    for r in range(world):
+        b, e, sh = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_double()
+        assert L.fpt_emul_shard(o, v, order, r, world, ctypes.byref(b), ctypes.byref(e), ctypes.byref(sh)) == 0
+        assert b.value == prev_end and e.value >= b.value
+        prev_end = e.value
+        shares.append(sh.value)
+    assert prev_end == n
+    assert abs(sum(shares) - 1.0) < 1e-12
+    if n >= 50 * world:
+        assert max(shares) < 1.05 / world, shares
