@@ -106,14 +106,43 @@ class ClockSampler:
 
 
 def cpu_reference_sample(x, o, v, budget_s=15.0):
-    """Time the CPU restatement (oracle.pt_gemm, OpenMP) on a bounded sample of trailing (i,j) pairs."""
+    """Time the CPU restatement (oracle.pt_gemm, OpenMP over triplets, one single-threaded dgemm per contraction) on a bounded
+    sample of trailing (i,j) pairs.  The GEMMs run on the faster of the oracle's own kernel and the OpenBLAS bundled with scipy
+    (a short calibration on the last pair decides); the other one's calibration rate is reported beside it."""
     import oracle
     import fermi_jl_b200 as fb
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     threads = max(oracle.num_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    per_trip = algorithmic_flops(o, v, 1) / (threads * 12e9)      # guess: ~12 GFLOP/s per core
-    want = max(1, int(budget_s / max(per_trip, 1e-9)))
     npair = o * (o + 1) // 2
+    args = (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+
+    def count(tb, te):   # zero-weight i=j=k triplets inside the range do no work
+        ntr = 0
+        i = j = k = 0
+        for t in range(te):
+            if t >= tb and not (i == j == k):
+                ntr += 1
+            k += 1
+            if k > j:
+                k = 0; j += 1
+                if j > i:
+                    j = 0; i += 1
+        return ntr
+
+    # calibration: the last max(threads, 8) triplets with each BLAS
+    ntot = o * (o + 1) * (o + 2) // 6
+    cb = max(0, ntot - max(threads, 8) - 1)
+    rates = {}
+    for which in ("own", "openblas"):
+        if oracle.use_blas(which) != which:
+            continue
+        t0 = time.perf_counter()
+        oracle.pt_gemm(*args, t_begin=cb, t_end=ntot, nthreads=threads)
+        rates[which] = algorithmic_flops(o, v, count(cb, ntot)) / (time.perf_counter() - t0)
+    best = max(rates, key=rates.get)
+    oracle.use_blas(best)
+    per_trip = algorithmic_flops(o, v, 1) / rates[best]
+    want = max(1, int(budget_s / max(per_trip, 1e-9)))
     pr0 = npair
     while pr0 > 0:
         tb, te = fb.host.pair_range_triplets(o, pr0 - 1, npair)
@@ -122,21 +151,13 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
             break
     tb, te = fb.host.pair_range_triplets(o, pr0, npair)
     t0 = time.perf_counter()
-    e = oracle.pt_gemm(x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv, t_begin=tb, t_end=te, nthreads=threads)
+    e = oracle.pt_gemm(*args, t_begin=tb, t_end=te, nthreads=threads)
     dt = time.perf_counter() - t0
-    # zero-weight i=j=k triplets inside the range do no work
-    ntr = 0
-    i = j = k = 0
-    for t in range(te):
-        if t >= tb and not (i == j == k):
-            ntr += 1
-        k += 1
-        if k > j:
-            k = 0; j += 1
-            if j > i:
-                j = 0; i += 1
+    oracle.use_blas("own")
+    ntr = count(tb, te)
+    other = {k: {"value": r / 1e12, "unit": UNIT, "sample": f"calibration on the last {ntot - cb} triplets"} for k, r in rates.items() if k != best}
     return {"E": e, "seconds": dt, "triplets": ntr, "flops": algorithmic_flops(o, v, ntr), "threads": threads,
-            "triplet_range": (tb, te)}
+            "triplet_range": (tb, te), "blas": best, "other": other}
 
 
 def run_reference(args, name, o, v, naux):
@@ -159,9 +180,10 @@ def run_reference(args, name, o, v, naux):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
                        "o": o, "v": v},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "blas": s["blas"], "other_blas": s["other"], "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = CPU restatement of Fermi.jl ijk2.jl (oracle/pt_oracle.c, OpenMP); Julia is not available in this image"}
+            "note": "reference = CPU restatement of Fermi.jl ijk2.jl (oracle/pt_oracle.c: OpenMP over triplets, single-threaded dgemm per contraction "
+                    "from the faster of its own kernel and scipy's OpenBLAS, as ijk.jl:45-46 arranges it); Julia is not available in this image"}
     _emit(line)
 
 
@@ -213,21 +235,27 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"    # NCCL prints its version banner on stdout: keep stdout to the one JSON line
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"    # NCCL's default prints a version banner on stdout; stdout carries one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    eng = fb.Engine(local)
+    # The engine.  N = 1: a plain handle.  N > 1: one process per GPU, every process holds a *rank handle* (fpt_create_rank ->
+    # ncclCommInitRank); torch.distributed is the control plane only (it carries the 128-byte NCCL id here, and barriers / the
+    # max-over-ranks of the timings below); every byte of the data path -- sharded H2D, all-gather, all-reduce -- is the library's.
+    if world == 1:
+        eng = fb.Engine(local)
+    else:
+        box = [fb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng = fb.Engine(local, rank=rank, world=world, nccl_id=box[0])
 
-    # ---- synthetic inputs (same seed on every rank; only rank 0's host copy is used for the e2e leg) ----
+    # ---- synthetic inputs (same seed on every rank): ordinary pageable numpy arrays, column-major like the reference's ----
     x = fb.synth.make_inputs(o, v, naux=naux)
     names = ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv")
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(x, k).ravel(order="F"))).pin_memory() for k in names}
-    h2d_bytes = sum(t.numel() * 8 for t in host.values())
-    # column-major numpy views of the pinned buffers: what the reference-facing API (RCCSDpT) is handed
-    harr = {k: host[k].numpy().reshape(getattr(x, k).shape, order="F") for k in names}
+    harr = {k: np.asfortranarray(getattr(x, k), dtype=np.float64) for k in names}
+    h2d_bytes = sum(a.size * 8 for a in harr.values())
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,76 +270,77 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(val):
-        if dist is None:
-            return val
-        t = torch.tensor([val], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- leg 1: operands resident in HBM ----
-    eng.upload_conv(o, v, *[host[k] for k in names])
+    # ---- leg 1: operands resident in HBM (collective at N > 1: every rank computes its shard, one scalar all-reduce) ----
+    eng.upload_conv(o, v, *[harr[k] for k in names])
     n_items = eng.num_items()
-    ib, ie = eng.shard_items(rank, world)       # contiguous, equal estimated cost
     ntrip = n_triplets(o)
     flops = algorithmic_flops(o, v, ntrip)
     for _ in range(args.warmup):
-        eng.compute(ib, ie)
+        eng.compute(0, -1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev0.record()
-    kernel_ms, launches, e_part = 0.0, 0, 0.0
+    kernel_ms, launches, e_gpu = 0.0, 0, 0.0
     for _ in range(args.steps):
-        e_part, st = eng.compute(ib, ie)   # synchronous: returns after the result is on the host
+        e_gpu, st = eng.compute(0, -1)     # synchronous: returns after E(T) is on the host
         kernel_ms += st["kernel_ms"]
-        launches += 2                       # triples_kernel + reduce_partials
-    ev1.record()
+        launches += 2                       # triples_kernel + reduce_partials on this rank's GPU
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     step_ms = max_over_ranks(wall_ms / args.steps)
     kern_ms = max_over_ranks(kernel_ms / args.steps)
-    e_gpu = sum_over_ranks(e_part)
     value = flops / (step_ms * 1e-3) / 1e12
 
-    # ---- leg 2: end to end from pinned host buffers through the public API ----
-    def e2e_step():
-        if world == 1:
-            ccsd = fb.RCCSD(0.0, 0.0, 0.0, harr["T1"], harr["T2"])
-            moints = fb.IntegralHelper({"OVVV": harr["OVVV"], "OOOV": harr["OOOV"], "OVOV": harr["OVOV"],
-                                        "Fii": harr["fo"], "Faa": harr["fv"]})
-            return fb.RCCSDpT(ccsd, moints, fb.B200(), device=local).correction
-        # rank 0: H2D of the raw arrays; NCCL broadcast; every rank: prep + its shard; scalar all-reduce
-        raw = {}
-        for k in names:
-            raw[k] = host[k].to(dev, non_blocking=True) if rank == 0 else torch.empty(host[k].numel(), dtype=torch.float64, device=dev)
-        for k in names:
-            dist.broadcast(raw[k], src=0)
-        torch.cuda.synchronize()
-        eng.upload_conv(o, v, *[raw[k] for k in names])
-        e, st = eng.compute(ib, ie)
-        t = torch.tensor([e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
-        return float(t.item())
+    # ---- leg 2: end to end through the public API, from pageable host arrays (what a Julia ccall passes) ----
+    ccsd = fb.RCCSD(0.0, 0.0, 0.0, harr["T1"], harr["T2"])
+    moints = fb.IntegralHelper({"OVVV": harr["OVVV"], "OOOV": harr["OOOV"], "OVOV": harr["OVOV"], "Fii": harr["fo"], "Faa": harr["fv"]})
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e_e2e = 0.0
-    for _ in range(args.steps):
-        e_e2e = e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    def e2e_step(engine):
+        return fb.RCCSDpT(ccsd, moints, fb.B200(), engine=engine).correction
+
+    def time_e2e(engine, collective):
+        for _ in range(3):
+            e2e_step(engine)
+        if collective:
+            barrier()
+        t0 = time.perf_counter()
+        e = 0.0
+        tl = []
+        for _ in range(args.steps):
+            e = e2e_step(engine)
+            tl.append(engine.last_timeline())
+        if collective:
+            barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        br = {k: statistics.mean(t[k] for t in tl) for k in tl[0]}
+        return e, ms, br
+
+    e_e2e, e2e_ms, breakdown = time_e2e(eng, True)
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = flops / (e2e_ms * 1e-3) / 1e12
+
+    # ---- leg 3 (N > 1): the same call on ONE process driving all N GPUs (fpt_create(ngpu = N), what the Julia glue uses);
+    # the other ranks wait at the barrier ----
+    e2e_handle = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            try:
+                engh = fb.Engine(list(range(world)))
+                e_h, ms_h, br_h = time_e2e(engh, False)
+                engh.close()
+                e2e_handle = {"value": flops / (ms_h * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": ms_h, "E_T": e_h, "breakdown_ms": br_h,
+                              "what": f"fpt_triples_conv on a single-process handle over {world} GPUs (fpt_create(ngpu={world})), pageable host inputs"}
+            except fb.FermiException as ex:
+                e2e_handle = {"error": str(ex)}
+        barrier()
 
     if rank == 0:
         # ---- roofline denominator: FP64 tensor-pipe peak measured live (MEASURED_PEAKS.json has no FP64 entry) ----
-        peak = eng.fp64_peak(0, 300.0)
+        peak = fb.Engine(local).fp64_peak(0, 300.0) if world > 1 else eng.fp64_peak(0, 300.0)
         achieved = flops / world / (kern_ms * 1e-3) / 1e12   # per GPU: this rank's share of the flops / its kernel time
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
@@ -327,23 +356,28 @@ def main():
             eng.set_triplet_window(*s["triplet_range"])   # the same triplets on the GPU
             e_s, _ = eng.compute(0, -1)
             eng.set_triplet_window(0, -1)
-            cpu = {"value": s["flops"] / s["seconds"] / 1e12, "unit": UNIT, "cores": s["threads"], "kind": "port",
+            cpu = {"value": s["flops"] / s["seconds"] / 1e12, "unit": UNIT, "cores": s["threads"], "kind": "port", "blas": s["blas"],
                    "sample": f"triplets [{s['triplet_range'][0]},{s['triplet_range'][1]}) of the i>=j>=k list "
-                             f"({s['triplets']} non-zero-weight), {s['seconds']:.1f} s of oracle/pt_oracle.c (OpenMP)",
+                             f"({s['triplets']} non-zero-weight), {s['seconds']:.1f} s of oracle/pt_oracle.c (OpenMP, {s['blas']} dgemm)",
+                   "other_blas": s.get("other"),
                    "dE_gpu_minus_cpu_on_sample_Eh": e_s - s["E"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
                            "o": o, "v": v, "triplets": ntrip, "work_items": n_items,
-                           "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} rank(s)",
-                           "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 7) // 8 * 8) * 8 / 1e6)},
+                           "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} GPU(s)",
+                           "e2e_inputs": "pageable host arrays; sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)",
+                           "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 15) // 16 * 16) * 8 / 1e6)},
                 "triplets_per_s": ntrip / (step_ms * 1e-3), "E_T": e_gpu, "E_T_e2e": e_e2e,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                        "breakdown_ms": breakdown},
+                "e2e_handle": e2e_handle,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
         _emit(line)
     if dist is not None:
         dist.barrier()
+        eng.close()
         dist.destroy_process_group()
 
 

@@ -28,6 +28,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao", "fpt_triples_ao_sparse", "fpt_upload_ao_sparse",
+           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_gemm_bench", "fpt_last_timeline",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -68,8 +69,17 @@ def load_library():
     L.fpt_triples_ao_sparse.argtypes = ([vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_longlong, vp, ctypes.c_int]
                                         + [vp] * 5 + [_dp, ctypes.POINTER(Stats)])
     L.fpt_upload_ao_sparse.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_longlong, vp, ctypes.c_int] + [vp] * 5
-    for f in EXPORTS[:21]:
-        getattr(L, f).restype = ctypes.c_int
+    L.fpt_nccl_unique_id.argtypes = [vp]
+    L.fpt_create_rank.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
+    L.fpt_set_host_threads.argtypes = [vp, ctypes.c_int]
+    L.fpt_triples_conv_async.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7
+    L.fpt_triples_df_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
+    L.fpt_wait.argtypes = [vp, _dp, ctypes.POINTER(Stats)]
+    L.fpt_gemm_bench.argtypes = [vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp]
+    L.fpt_last_timeline.argtypes = [vp, _dp]
+    for f in EXPORTS:
+        if f not in ("fpt_last_error", "fpt_version"):
+            getattr(L, f).restype = ctypes.c_int
     _LIB = L
     return L
 
@@ -83,13 +93,28 @@ def _ptr(a):
     return ctypes.c_void_p(arr.ctypes.data), arr
 
 
-class Engine:
-    """Owns one fpt_handle (one GPU).  Thin, 1:1 over the C ABI."""
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id for `Engine(device, rank=..., world=..., nccl_id=...)`: rank 0 creates it, the launcher's control plane
+    (torch.distributed, MPI, a file ...) hands it to the other ranks."""
+    L = load_library()
+    buf = ctypes.create_string_buffer(128)
+    if L.fpt_nccl_unique_id(buf) != 0:
+        raise FermiException(L.fpt_last_error().decode())
+    return buf.raw
 
-    def __init__(self, device=None):
-        """device: None (current device), an int, or a list of ints (single-process multi-GPU handle)."""
+
+class Engine:
+    """Owns one fpt_handle.  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device=None, rank=None, world=None, nccl_id=None):
+        """device: None (current device), an int, or a list of ints (single-process multi-GPU handle).
+        rank / world / nccl_id: one process per GPU (fpt_create_rank); uploads and computes are then collective calls."""
         self._L = load_library()
         self._h = ctypes.c_void_p()
+        if rank is not None:
+            idbuf = ctypes.create_string_buffer(bytes(nccl_id), 128) if nccl_id is not None else None
+            self._check(self._L.fpt_create_rank(-1 if device is None else int(device), int(rank), int(world), idbuf, ctypes.byref(self._h)))
+            return
         if isinstance(device, (list, tuple)):
             devs = (ctypes.c_int * len(device))(*device)
             n = len(device)
@@ -118,6 +143,34 @@ class Engine:
         e, st = ctypes.c_double(), Stats()
         self._check(self._L.fpt_triples_conv(self._h, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
         return e.value, st.asdict()
+
+    def triples_conv_async(self, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv):
+        """Returns once the arrays have been consumed; `wait()` collects (E(T), stats)."""
+        ps = [_ptr(a) for a in (T1, T2, OVVV, OOOV, OVOV, fo, fv)]
+        self._check(self._L.fpt_triples_conv_async(self._h, o, v, *[p for p, _ in ps]))
+
+    def triples_df_async(self, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv):
+        ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
+        self._check(self._L.fpt_triples_df_async(self._h, o, v, naux, *[p for p, _ in ps]))
+
+    def wait(self):
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_wait(self._h, ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def set_host_threads(self, n: int):
+        self._check(self._L.fpt_set_host_threads(self._h, n))
+
+    def gemm_bench(self, M: int, N: int, K: int, reps: int = 5) -> float:
+        t = ctypes.c_double()
+        self._check(self._L.fpt_gemm_bench(self._h, M, N, K, reps, ctypes.byref(t)))
+        return t.value
+
+    def last_timeline(self) -> dict:
+        buf = (ctypes.c_double * 8)()
+        self._check(self._L.fpt_last_timeline(self._h, buf))
+        names = ["host_stage_ms", "h2d_done_ms", "operands_ready_ms", "kernel_begin_ms", "kernel_end_ms", "result_sent_ms"]
+        return dict(zip(names, list(buf)[:6]))
 
     def triples_df(self, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv):
         ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]

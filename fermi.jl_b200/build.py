@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfermi_pt_b200.so")
 SOURCES = ["fpt_api.cu"]
-HEADERS = ["fpt_triples.cuh", "fpt_triples2.cuh", "fpt_aux_kernels.cuh", "fpt_ptx.cuh", "fpt_layout.h", os.path.join("..", "..", "include", "fermi_pt_b200.h")]
+HEADERS = ["fpt_triples.cuh", "fpt_triples2.cuh", "fpt_aux_kernels.cuh", "fpt_gemm.cuh", "fpt_internal.h", "fpt_stage.h", "fpt_ptx.cuh", "fpt_layout.h",
+           os.path.join("..", "..", "include", "fermi_pt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -29,10 +30,35 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+LAUNCH_REGS = 96   # fpt_triples.cuh: the setmaxnreg budget (512 x 112 + 128 x 24 <= 640 x 96) assumes this launch allocation
+
+
+def check_register_budget() -> None:
+    """The fused kernel redistributes its launch-time register allocation with setmaxnreg; a different allocation would make
+    the consumers' setmaxnreg.inc spin forever.  ptxas settles on 96 by itself (launch bound 640 threads, 1 CTA/SM), but
+    nothing in the source pins it, so the built library is checked."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    out = subprocess.run([cuobjdump, "-res-usage", LIB], capture_output=True, text=True).stdout.splitlines()
+    seen = 0
+    for n, line in enumerate(out):
+        if "triples_kernelILb" in line and n + 1 < len(out):
+            regs = int(out[n + 1].split("REG:")[1].split()[0])
+            seen += 1
+            if regs != LAUNCH_REGS:
+                os.remove(LIB)
+                raise RuntimeError(f"triples_kernel was compiled with {regs} registers per thread, the setmaxnreg budget needs {LAUNCH_REGS}")
+    if seen == 0:
+        raise RuntimeError("triples_kernel not found in the built library")
+
+
+def build(force: bool = False, verbose: bool = False, defines=()) -> str:
     if force or needs_build():
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        cmd = ([_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB]
+               + [os.path.join(CSRC, s) for s in SOURCES])
         subprocess.check_call(cmd)
+        check_register_budget()
     return LIB
 
 

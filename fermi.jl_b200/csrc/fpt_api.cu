@@ -1,132 +1,85 @@
 // C-ABI of libfermi_pt_b200.so (declared in include/fermi_pt_b200.h) and the host-side driver of the (T) path:
-// device buffer pool, host->device staging, layout prep / DF assembly launches, the persistent fused kernel launch
-// and the final reduction.  Replaces the driver loop + accumulation of
+// device buffer pool, sharded host->device staging (pinned bounce ring, one PCIe link per GPU), NCCL all-gather of the raw
+// arrays over NVLink, layout prep / DF assembly launches, the persistent fused kernel, the scalar all-reduce of E(T).
+// Replaces the driver loop + accumulation of
 //   src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:20-150 (reference, Julia threads)
 // No CPU fallback: every entry point fails loudly without a CUDA device.
 #include <cuda_runtime.h>
-#include <dlfcn.h>
-#include <nccl.h>
+#include <sched.h>
 #include <algorithm>
 #include <chrono>
-#include <cstdarg>
-#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "../../include/fermi_pt_b200.h"
+#include "fpt_internal.h"
 #include "fpt_aux_kernels.cuh"
+#include "fpt_gemm.cuh"
 #include "fpt_triples.cuh"
+#ifdef FPT_WITH_VARIANT2
 #include "fpt_triples2.cuh"
+#endif
 
 using namespace fpt;
+typedef std::chrono::steady_clock wall;
+static double ms_since(wall::time_point t0) { return std::chrono::duration<double, std::milli>(wall::now() - t0).count(); }
 
-static thread_local std::string g_err;
-static int fail(const char* fmt, ...)
+extern "C" const char* fpt_last_error(void) { return err_text().c_str(); }
+extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.4 (sm_100a)"; }
+
+// ---- handle life cycle -----------------------------------------------------------------------------------------------------
+static void dev_destroy(Dev* d)
 {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return 1;
+    if (!d) return;
+    cudaSetDevice(d->dev);
+    if (d->comm) nccl_api().CommDestroy(d->comm);
+    DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
+                      &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
+    for (DevBuf* b : bufs) b->release();
+    cudaEvent_t evs[] = {d->ev0, d->ev1, d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : d->tl)
+        if (e) cudaEventDestroy(e);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    if (d->copy) cudaStreamDestroy(d->copy);
+    delete d;
 }
-#define CK(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e_ = (call);                                                                          \
-        if (e_ != cudaSuccess) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
-    } while (0)
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        cap = bytes;
-        return 0;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    double* d() const { return (double*)p; }
-};
-
-struct fpt_handle {
-    int dev = 0;
-    int n_sm = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // resident operands
-    DevBuf Pt, Qt, OV2, T1d, fo, fv, prefix, partials, counter, out, prof, blocktab;
-    // staging for raw inputs
-    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk, sBOO, sBOV, sBVV;
-    // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
-    DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV;
-    Problem prob{};
-    bool loaded = false;
-    fpt_stats last{};
-    int launches = 0;
-    int last_grid = 0;
-    bool profiling = false;
-    int dbg_flags = 0;
-    int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
-    std::vector<double> block_cost;
-    int kernel_variant = 1;   // 1: DMMA warps add their own accumulators into the W slots (fpt_triples.cuh, default);
-                              // 2: experimental epilogue-warp kernel with TMEM parking (fpt_triples2.cuh)
-    bool last_profiled = false;
-    // multi-GPU (single process): this handle drives devices[0]; peers[] drive the others; one NCCL clique
-    std::vector<fpt_handle*> peers;
-    std::vector<ncclComm_t> comms;   // comms[0] = this device, comms[1+k] = peers[k]
-};
-
-// ---- NCCL, resolved at run time (only handles with ngpu > 1 need it) ---------------------------------------------------
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
-static NcclApi g_nccl;
-static int nccl_load()
+static int dev_init(Dev* d)
 {
-    if (g_nccl.lib) return 0;
-    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return fail("multi-GPU handle: cannot load libnccl.so.2 (%s)", dlerror());
-#define FPT_SYM(field, name)                                                            \
-    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));          \
-    if (!g_nccl.field) return fail("multi-GPU handle: libnccl lacks %s", name)
-    FPT_SYM(CommInitAll, "ncclCommInitAll");
-    FPT_SYM(CommDestroy, "ncclCommDestroy");
-    FPT_SYM(GroupStart, "ncclGroupStart");
-    FPT_SYM(GroupEnd, "ncclGroupEnd");
-    FPT_SYM(Broadcast, "ncclBroadcast");
-    FPT_SYM(AllReduce, "ncclAllReduce");
-    FPT_SYM(GetErrorString, "ncclGetErrorString");
-#undef FPT_SYM
-    g_nccl.lib = lib;
+    cudaDeviceProp prop;
+    CK(cudaSetDevice(d->dev));
+    CK(cudaGetDeviceProperties(&prop, d->dev));
+    if (prop.major < 10)
+        return fail("fpt_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", d->dev, prop.major, prop.minor);
+    d->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&d->ev0));
+    CK(cudaEventCreate(&d->ev1));
+    CK(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->ev_free[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->ev_free[1], cudaEventDisableTiming));
+    for (int t = 0; t < NTL; t++) CK(cudaEventCreate(&d->tl[t]));
+    CK(cudaFuncSetAttribute(triples_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+#ifdef FPT_WITH_VARIANT2
+    CK(cudaFuncSetAttribute(triples_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
+#endif
+    CK(gemm_tn_set_attributes<EPI_COLMAJOR>());
+    CK(gemm_tn_set_attributes<EPI_PT>());
+    CK(gemm_tn_set_attributes<EPI_QT_HOLE>());
+    CK(gemm_tn_set_attributes<EPI_OV2>());
     return 0;
 }
-#define NCK(call)                                                                                              \
-    do {                                                                                                       \
-        ncclResult_t r_ = (call);                                                                              \
-        if (r_ != ncclSuccess) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
-    } while (0)
 
-static int broadcast_operands(fpt_handle* h);
-
-extern "C" const char* fpt_last_error(void) { return g_err.c_str(); }
-extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.3 (sm_100a)"; }
-
-static int create_one(int dev, fpt_handle** out)
+static int dev_create(int dev, int idx, Dev** out)
 {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -134,22 +87,51 @@ static int create_one(int dev, fpt_handle** out)
         return fail("fpt_create: no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString(e));
     if (dev < 0) CK(cudaGetDevice(&dev));
     if (dev >= ndev) return fail("fpt_create: device %d out of range (have %d)", dev, ndev);
-    CK(cudaSetDevice(dev));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10)
-        return fail("fpt_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
-    fpt_handle* h = new fpt_handle();
-    h->dev = dev;
-    h->n_sm = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&h->ev0));
-    CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(triples_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(triples_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(triples_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(triples_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
-    *out = h;
+    Dev* d = new Dev();
+    d->dev = dev;
+    d->idx = idx;
+    if (dev_init(d)) { dev_destroy(d); return 1; }
+    *out = d;
+    return 0;
+}
+
+static int default_host_threads(int share)
+{
+    if (const char* s = getenv("FERMI_PT_B200_THREADS")) {
+        const int n = atoi(s);
+        if (n >= 1) return n > 64 ? 64 : n;
+    }
+    int n = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);
+    n /= (share > 0 ? share : 1);
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+// pool of staging threads, pinned bounce ring, pinned result word
+static int handle_finish(fpt_handle* h)
+{
+    CK(cudaSetDevice(h->devs[0]->dev));
+    h->pool.start(default_host_threads(h->rank_mode ? h->world : 1));
+    const int nslots = std::max(8, 2 * (int)h->devs.size());
+    CK(h->ring.init(nslots, (int)h->devs.size()));
+    CK(cudaHostAlloc((void**)&h->res_pinned, 64, cudaHostAllocPortable));
+    return 0;
+}
+
+extern "C" int fpt_destroy(fpt_handle* h)
+{
+    if (!h) return 0;
+    DeviceGuard guard;
+    for (Dev* d : h->devs) {
+        cudaSetDevice(d->dev);
+        cudaDeviceSynchronize();
+    }
+    h->pool.stop();
+    h->ring.release();
+    if (h->res_pinned) cudaFreeHost(h->res_pinned);
+    for (Dev* d : h->devs) dev_destroy(d);
+    delete h;
     return 0;
 }
 
@@ -159,70 +141,230 @@ extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
     *out = nullptr;
     if (ngpu < 1 || ngpu > 16) return fail("fpt_create: ngpu=%d out of range", ngpu);
     if (ngpu > 1 && !devices) return fail("fpt_create: a device list is required for ngpu > 1");
-    fpt_handle* h = nullptr;
-    if (create_one(devices ? devices[0] : -1, &h)) return 1;
+    DeviceGuard guard;
+    fpt_handle* h = new fpt_handle();
+    for (int k = 0; k < ngpu; k++) {
+        Dev* d = nullptr;
+        if (dev_create(devices ? devices[k] : -1, k, &d)) { fpt_destroy(h); return 1; }
+        d->grank = k;
+        h->devs.push_back(d);
+    }
+    h->world = ngpu;
     if (ngpu > 1) {
-        // single-process multi-GPU: one NCCL clique over NVLink, operands broadcast once per upload, one scalar all-reduce
+        // single-process multi-GPU: one NCCL clique over NVLink
         if (nccl_load()) { fpt_destroy(h); return 1; }
-        for (int k = 1; k < ngpu; k++) {
-            fpt_handle* p = nullptr;
-            if (create_one(devices[k], &p)) { fpt_destroy(h); return 1; }
-            h->peers.push_back(p);
-        }
-        h->comms.resize(ngpu);
-        ncclResult_t r = g_nccl.CommInitAll(h->comms.data(), ngpu, devices);
+        std::vector<ncclComm_t> comms(ngpu);
+        std::vector<int> devs(ngpu);
+        for (int k = 0; k < ngpu; k++) devs[k] = h->devs[k]->dev;
+        ncclResult_t r = nccl_api().CommInitAll(comms.data(), ngpu, devs.data());
         if (r != ncclSuccess) {
-            h->comms.clear();
-            fail("ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+            fail("ncclCommInitAll failed: %s", nccl_api().GetErrorString(r));
             fpt_destroy(h);
             return 1;
         }
-        CK(cudaSetDevice(h->dev));
+        for (int k = 0; k < ngpu; k++) h->devs[k]->comm = comms[k];
     }
+    if (handle_finish(h)) { fpt_destroy(h); return 1; }
     *out = h;
     return 0;
 }
 
-extern "C" int fpt_destroy(fpt_handle* h)
+extern "C" int fpt_nccl_unique_id(void* id128)
 {
-    if (!h) return 0;
-    for (ncclComm_t c : h->comms) g_nccl.CommDestroy(c);
-    h->comms.clear();
-    for (fpt_handle* p : h->peers) fpt_destroy(p);
-    h->peers.clear();
-    cudaSetDevice(h->dev);
-    DevBuf* bufs[] = {&h->Pt, &h->Qt, &h->OV2, &h->T1d, &h->fo, &h->fv, &h->prefix, &h->partials, &h->counter, &h->out, &h->prof, &h->blocktab,
-                      &h->sCo, &h->sCv, &h->aoDense, &h->sIdx, &h->sVals, &h->aoQ1, &h->aoQ2v, &h->aoQ2o, &h->aoQ3vv, &h->aoQ3vo, &h->aoQ3oo, &h->aoOVVV, &h->aoOOOV, &h->aoOVOV, &h->sT1, &h->sT2, &h->sOOOV, &h->sOVOV, &h->sChunk, &h->sBOO, &h->sBOV, &h->sBVV};
-    for (DevBuf* b : bufs) b->release();
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    delete h;
+    if (!id128) return fail("fpt_nccl_unique_id: NULL argument");
+    if (nccl_load()) return 1;
+    static_assert(sizeof(ncclUniqueId) == 128, "the ABI carries the NCCL id as 128 bytes");
+    ncclUniqueId id;
+    NCK(nccl_api().GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
     return 0;
 }
 
-static bool is_device_ptr(const void* p)
+extern "C" int fpt_create_rank(int device, int rank, int world, const void* id128, fpt_handle** out)
+{
+    if (!out) return fail("fpt_create_rank: out is NULL");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return fail("fpt_create_rank: invalid rank %d of %d", rank, world);
+    if (world > 1 && !id128) return fail("fpt_create_rank: the NCCL id is required for world > 1");
+    DeviceGuard guard;
+    fpt_handle* h = new fpt_handle();
+    Dev* d = nullptr;
+    if (dev_create(device, 0, &d)) { fpt_destroy(h); return 1; }
+    d->grank = rank;
+    h->devs.push_back(d);
+    h->world = world;
+    h->rank_mode = true;
+    if (world > 1) {
+        if (nccl_load()) { fpt_destroy(h); return 1; }
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        cudaSetDevice(d->dev);
+        ncclResult_t r = nccl_api().CommInitRank(&d->comm, world, id, rank);
+        if (r != ncclSuccess) {
+            d->comm = nullptr;
+            fail("ncclCommInitRank failed: %s", nccl_api().GetErrorString(r));
+            fpt_destroy(h);
+            return 1;
+        }
+    }
+    if (handle_finish(h)) { fpt_destroy(h); return 1; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int fpt_set_host_threads(fpt_handle* h, int n)
+{
+    if (!h) return fail("fpt_set_host_threads: NULL handle");
+    if (n < 1 || n > 64) return fail("fpt_set_host_threads: n=%d out of range (1..64)", n);
+    h->pool.start(n);
+    return 0;
+}
+
+// ---- where does a caller's pointer live ------------------------------------------------------------------------------------
+enum PtrKind { PK_PAGEABLE = 0, PK_PINNED = 1, PK_DEVICE = 2 };
+static PtrKind classify(const void* p, int* device = nullptr)
 {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return PK_PAGEABLE; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+        if (device) *device = at.device;
+        return PK_DEVICE;
+    }
+    return at.type == cudaMemoryTypeHost ? PK_PINNED : PK_PAGEABLE;
 }
 
-// Returns a device pointer for `src` (n doubles): src itself if already on the device, else a staged copy.
-static int stage_in(fpt_handle* h, DevBuf& buf, const double* src, size_t n, const double** dptr, double* h2d_bytes)
+// Device-resident inputs are consumed in place on the handle's own streams.  They must live on the handle's (first) GPU, and
+// whatever stream produced them is ordered before the first read by one device-wide synchronisation.
+static int admit_device_inputs(fpt_handle* h, const char* who, std::initializer_list<const void*> ptrs)
 {
-    if (is_device_ptr(src)) { *dptr = src; return 0; }
-    if (buf.ensure(n * sizeof(double))) return 1;
-    CK(cudaMemcpyAsync(buf.p, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    *h2d_bytes += (double)n * sizeof(double);
-    *dptr = buf.d();
+    bool any = false;
+    for (const void* p : ptrs) {
+        int dev = -1;
+        if (p && classify(p, &dev) == PK_DEVICE) {
+            if (dev != h->devs[0]->dev)
+                return fail("%s: a device-resident input lives on GPU %d, the handle's GPU is %d", who, dev, h->devs[0]->dev);
+            any = true;
+        }
+    }
+    if (any) {
+        CK(cudaSetDevice(h->devs[0]->dev));
+        CK(cudaDeviceSynchronize());
+    }
     return 0;
 }
 
+// ---- staging ---------------------------------------------------------------------------------------------------------------
+// enqueue the copy of `bytes` from host `src` to `dst` on GPU d (its copy stream)
+static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, size_t bytes, PtrKind kind)
+{
+    if (bytes == 0) return 0;
+    CK(cudaSetDevice(d.dev));
+    h->h2d += (double)bytes;
+    if (kind == PK_PINNED || bytes <= ((size_t)64 << 10)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.copy));
+        return 0;
+    }
+    const auto t0 = wall::now();
+    for (size_t off = 0; off < bytes; off += PinnedRing::SLOT_BYTES) {
+        const size_t nb = std::min(PinnedRing::SLOT_BYTES, bytes - off);
+        PinnedRing::Slot* s = nullptr;
+        CK(h->ring.acquire(&s));
+        h->pool.copy(s->p, (const char*)src + off, nb);
+        CK(cudaMemcpyAsync((char*)dst + off, s->p, nb, cudaMemcpyHostToDevice, d.copy));
+        CK(h->ring.sent(s, d.idx, d.copy));
+    }
+    h->stage_host_ms += ms_since(t0);
+    return 0;
+}
+
+// the copy stream's work so far is what the compute stream continues from
+static int copy_then_stream(Dev& d)
+{
+    CK(cudaSetDevice(d.dev));
+    CK(cudaEventRecord(d.ev_copy, d.copy));
+    CK(cudaStreamWaitEvent(d.stream, d.ev_copy, 0));
+    return 0;
+}
+
+constexpr size_t SHARD_MIN_BYTES = (size_t)1 << 20;
+
+// Makes the array `src` (n doubles; host or device memory) resident on every GPU of the handle, ordered on each GPU's compute
+// stream; out[i] = its address on devs[i].  `bufof(d)` names the staging buffer to use on GPU d.
+//  * host memory, world > 1, >= 1 MB: GPU g pulls only part g of `world` over its own PCIe link, then one in-place ncclAllGather
+//    over NVLink completes the array everywhere (in rank mode every process passes the same array and pulls its own part);
+//  * host memory otherwise: every GPU of this process pulls the whole array;
+//  * device memory (on devs[0]): used in place; the other GPUs of a single-process handle receive it by ncclBroadcast.
+template <class BufOf>
+static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, std::vector<const double*>& out)
+{
+    const int L = (int)h->devs.size(), W = h->world;
+    out.assign(L, nullptr);
+    const PtrKind kind = classify(src);
+    if (kind == PK_DEVICE) {
+        out[0] = src;
+        if (L > 1) {
+            for (int i = 1; i < L; i++) {
+                Dev& d = *h->devs[i];
+                CK(cudaSetDevice(d.dev));
+                if (bufof(d).ensure(n * sizeof(double))) return 1;
+                out[i] = bufof(d).d();
+            }
+            NCK(nccl_api().GroupStart());
+            for (int i = 0; i < L; i++) {
+                Dev& d = *h->devs[i];
+                NCK(nccl_api().Broadcast(out[i], (void*)out[i], n, ncclDouble, 0, d.comm, d.stream));
+            }
+            NCK(nccl_api().GroupEnd());
+        }
+        return 0;
+    }
+    const bool shard = W > 1 && n * sizeof(double) >= SHARD_MIN_BYTES;
+    if (!shard) {
+        for (int i = 0; i < L; i++) {
+            Dev& d = *h->devs[i];
+            CK(cudaSetDevice(d.dev));
+            if (bufof(d).ensure(n * sizeof(double))) return 1;
+            out[i] = bufof(d).d();
+            if (stage_to(h, d, bufof(d).p, src, n * sizeof(double), kind)) return 1;
+            if (copy_then_stream(d)) return 1;
+        }
+        return 0;
+    }
+    const size_t part = ((n + W - 1) / W + 511) & ~(size_t)511;
+    for (int i = 0; i < L; i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        if (bufof(d).ensure((size_t)W * part * sizeof(double))) return 1;
+        out[i] = bufof(d).d();
+        const size_t b = std::min(n, (size_t)d.grank * part), e = std::min(n, (size_t)(d.grank + 1) * part);
+        if (stage_to(h, d, bufof(d).d() + b, src + b, (e - b) * sizeof(double), kind)) return 1;
+        if (copy_then_stream(d)) return 1;
+    }
+    NCK(nccl_api().GroupStart());
+    for (int i = 0; i < L; i++) {
+        Dev& d = *h->devs[i];
+        NCK(nccl_api().AllGather(bufof(d).d() + (size_t)d.grank * part, bufof(d).p, part, ncclDouble, d.comm, d.stream));
+    }
+    NCK(nccl_api().GroupEnd());
+    return 0;
+}
+
+// ---- problem set-up --------------------------------------------------------------------------------------------------------
+static int grid1d(i64 n, int block = 256) { i64 g = (n + block - 1) / block; if (g > 148 * 32) g = 148 * 32; if (g < 1) g = 1; return (int)g; }
+
+static int check_idle(fpt_handle* h, const char* who)
+{
+    if (!h) return fail("%s: NULL handle", who);
+    if (h->pending) return fail("%s: an asynchronous call is in flight on this handle; collect it with fpt_wait first", who);
+    return 0;
+}
+
+// Dimensions, work list and device buffers of a new problem on every GPU of the handle; the copy streams are ordered after
+// whatever the compute streams still have in flight (the previous problem's kernels read the buffers about to be overwritten).
 static int setup_problem(fpt_handle* h, int o, int v)
 {
     if (o < 1 || v < 1) return fail("invalid dimensions o=%d v=%d", o, v);
-    Problem& P = h->prob;
+    Problem P{};
     P.o = o; P.v = v;
     P.vp = padded_v(v);
     P.nt = num_tiles(v);
@@ -234,161 +376,247 @@ static int setup_problem(fpt_handle* h, int o, int v)
     P.tw_begin = 0;
     P.tw_count = num_triplets(o);   // a new problem starts with the full triplet list
     P.nitems = P.nb * P.tw_count;
-    if (h->Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
-    if (h->Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
-    if (h->OV2.ensure((size_t)ov2_elems(P) * sizeof(double))) return 1;
-    if (h->T1d.ensure((size_t)o * v * sizeof(double))) return 1;
-    if (h->fo.ensure((size_t)o * sizeof(double))) return 1;
-    if (h->fv.ensure((size_t)v * sizeof(double))) return 1;
-    if (h->partials.ensure((size_t)h->n_sm * 4 * sizeof(double))) return 1;
-    if (h->counter.ensure(sizeof(unsigned long long))) return 1;
-    if (h->out.ensure(sizeof(double))) return 1;
-    if (h->prof.ensure((size_t)h->n_sm * NPROF * sizeof(long long))) return 1;
-    // block descriptor table (positions in (i,j,k) instead of orbital numbers)
-    std::vector<BlockTabEntry> tab((size_t)P.nb);
-    for (i64 b = 0; b < P.nb; b++) {
-        int A, B, C;
-        tetra_decode(b, A, B, C);
-        make_block(A, B, C, P.vp, tab[b].bd);
-        tab[b].ngemm = make_gemms(tab[b].bd, 0, 1, 2, tab[b].gemm);
-        make_fast_order(tab[b]);
+    h->o = o; h->v = v;
+    h->tw_begin = 0; h->tw_count = P.tw_count; h->nitems = P.nitems;
+    // block descriptor table (positions in (i,j,k) instead of orbital numbers): depends on the tiling of the virtual range only,
+    // kept across calls of the same shape (the 6 N_atoms calls of a finite-difference gradient)
+    if (h->tab_vp != P.vp) {
+        h->tab.assign((size_t)P.nb, BlockTabEntry{});
+        for (i64 b = 0; b < P.nb; b++) {
+            int A, B, C;
+            tetra_decode(b, A, B, C);
+            make_block(A, B, C, P.vp, h->tab[b].bd);
+            h->tab[b].ngemm = make_gemms(h->tab[b].bd, 0, 1, 2, h->tab[b].gemm);
+            make_fast_order(h->tab[b]);
+        }
+        h->tab_vp = P.vp;
     }
-    if (h->blocktab.ensure(tab.size() * sizeof(BlockTabEntry))) return 1;
-    CK(cudaMemcpyAsync(h->blocktab.p, tab.data(), tab.size() * sizeof(BlockTabEntry), cudaMemcpyHostToDevice, h->stream));
-    P.blocktab = (const BlockTabEntry*)h->blocktab.p;
-    CK(cudaStreamSynchronize(h->stream));   // `tab` is a local
     h->block_cost.resize((size_t)P.nb);
-    for (i64 b = 0; b < P.nb; b++) h->block_cost[b] = block_cost(tab[b], P.G);
-    P.Pt = h->Pt.d(); P.Qt = h->Qt.d(); P.OV2 = h->OV2.d(); P.T1d = h->T1d.d();
-    P.fo = h->fo.d(); P.fv = h->fv.d();
+    for (i64 b = 0; b < P.nb; b++) h->block_cost[b] = block_cost(h->tab[b], P.G);
+    for (Dev* dp : h->devs) {
+        Dev& d = *dp;
+        CK(cudaSetDevice(d.dev));
+        if (d.Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
+        if (d.Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
+        if (d.OV2.ensure((size_t)ov2_elems(P) * sizeof(double))) return 1;
+        if (d.T1d.ensure((size_t)o * v * sizeof(double))) return 1;
+        if (d.fo.ensure((size_t)o * sizeof(double))) return 1;
+        if (d.fv.ensure((size_t)v * sizeof(double))) return 1;
+        if (d.partials.ensure((size_t)d.n_sm * 4 * sizeof(double))) return 1;
+        if (d.counter.ensure(sizeof(unsigned long long))) return 1;
+        if (d.out.ensure(sizeof(double))) return 1;
+        if (d.prof.ensure((size_t)d.n_sm * NPROF * sizeof(long long))) return 1;
+        if (d.blocktab.ensure(h->tab.size() * sizeof(BlockTabEntry))) return 1;
+        if (d.tab_vp != P.vp) {
+            CK(cudaMemcpyAsync(d.blocktab.p, h->tab.data(), h->tab.size() * sizeof(BlockTabEntry), cudaMemcpyHostToDevice, d.stream));
+            d.tab_vp = P.vp;
+        }
+        d.prob = P;
+        d.prob.blocktab = (const BlockTabEntry*)d.blocktab.p;
+        d.prob.Pt = d.Pt.d(); d.prob.Qt = d.Qt.d(); d.prob.OV2 = d.OV2.d(); d.prob.T1d = d.T1d.d();
+        d.prob.fo = d.fo.d(); d.prob.fv = d.fv.d();
+        CK(cudaEventRecord(d.ev_start, d.stream));
+        CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));
+        if (dp == h->devs[0]) CK(cudaEventRecord(d.tl[0], d.copy));
+    }
     return 0;
 }
 
-static int grid1d(i64 n, int block = 256) { i64 g = (n + block - 1) / block; if (g > 148 * 32) g = 148 * 32; if (g < 1) g = 1; return (int)g; }
-
-// the parts common to conventional and DF uploads: T1, T2 -> T1d, Pt hole part, Qt particle part; fo, fv
-static int upload_common(fpt_handle* h, const double* T1, const double* T2, const double* fo, const double* fv,
-                         const double** dT2, double* h2d)
+// Pt's padding (rows x,y >= v and kappa >= v+o) must read as zero.  The prep kernels only ever write real entries, so after one
+// memset a buffer stays clean for every later problem of the same shape.
+static int pt_zero_padding(Dev& d)
 {
-    const Problem& P = h->prob;
-    const int o = P.o, v = P.v;
-    const double* dT1;
-    if (stage_in(h, h->sT1, T1, (size_t)o * v, &dT1, h2d)) return 1;
-    if (stage_in(h, h->sT2, T2, (size_t)o * o * v * v, dT2, h2d)) return 1;
-    CK(cudaMemcpyAsync(h->fo.p, fo, o * sizeof(double), cudaMemcpyDefault, h->stream));
-    CK(cudaMemcpyAsync(h->fv.p, fv, v * sizeof(double), cudaMemcpyDefault, h->stream));
-    if (!is_device_ptr(fo)) *h2d += (o + v) * sizeof(double);
-    CK(cudaMemsetAsync(h->Pt.p, 0, (size_t)o * P.vp * P.vp * P.Kp * sizeof(double), h->stream));
-    prep_t1<<<grid1d(o * v), 256, 0, h->stream>>>(P, h->T1d.d(), dT1);
-    prep_pt_hole<<<grid1d((i64)o * o * v * v), 256, 0, h->stream>>>(P, h->Pt.d(), *dT2);
-    h->launches += 2;
-    CK(cudaGetLastError());
+    const Problem& P = d.prob;
+    if (d.clean_o == P.o && d.clean_v == P.v && d.clean_ptr == d.Pt.p) return 0;
+    CK(cudaMemsetAsync(d.Pt.p, 0, (size_t)P.o * P.vp * P.vp * P.Kp * sizeof(double), d.stream));
     return 0;
+}
+static void upload_begin(fpt_handle* h)
+{
+    h->loaded = false;
+    h->launches = 0;
+    h->h2d = 0.0;
+    h->stage_host_ms = 0.0;
+    for (Dev* d : h->devs) d->clean_o = -1;
+}
+static int upload_end(fpt_handle* h, bool sync)
+{
+    for (Dev* dp : h->devs) {
+        Dev& d = *dp;
+        CK(cudaSetDevice(d.dev));
+        if (dp == h->devs[0]) {
+            CK(cudaEventRecord(d.tl[1], d.copy));
+            CK(cudaEventRecord(d.tl[2], d.stream));
+        }
+        if (sync) {
+            CK(cudaStreamSynchronize(d.copy));
+            CK(cudaStreamSynchronize(d.stream));
+        }
+        d.clean_o = d.prob.o; d.clean_v = d.prob.v; d.clean_ptr = d.Pt.p;
+    }
+    h->loaded = true;
+    return 0;
+}
+
+// the parts common to all routes: T1, T2 -> T1d, Pt hole part; fo, fv.  dT2[i] = T2 on GPU i for the route's own Qt build.
+static int upload_common(fpt_handle* h, const double* T1, const double* T2, const double* fo, const double* fv,
+                         std::vector<const double*>& dT2)
+{
+    const int o = h->o, v = h->v;
+    std::vector<const double*> dT1, dfo, dfv;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sT1; }, T1, (size_t)o * v, dT1)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sT2; }, T2, (size_t)o * o * v * v, dT2)) return 1;
+    for (size_t i = 0; i < h->devs.size(); i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        const bool dev_in = classify(fo) == PK_DEVICE;
+        CK(cudaMemcpyAsync(d.fo.p, fo, o * sizeof(double), cudaMemcpyDefault, d.stream));
+        CK(cudaMemcpyAsync(d.fv.p, fv, v * sizeof(double), cudaMemcpyDefault, d.stream));
+        if (!dev_in) h->h2d += (o + v) * sizeof(double);
+        if (pt_zero_padding(d)) return 1;
+        prep_t1<<<grid1d(o * v), 256, 0, d.stream>>>(d.prob, d.T1d.d(), dT1[i]);
+        prep_pt_hole<<<grid1d((i64)o * o * v * v), 256, 0, d.stream>>>(d.prob, d.Pt.d(), dT2[i]);
+        CK(cudaGetLastError());
+    }
+    h->launches += 2;
+    return 0;
+}
+
+static int upload_conv_impl(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                            const double* OOOV, const double* OVOV, const double* fo, const double* fv, bool sync)
+{
+    if (setup_problem(h, o, v)) return 1;
+    const int L = (int)h->devs.size(), W = h->world;
+    std::vector<const double*> dT2, dOOOV, dOVOV, dChunk;
+    if (upload_common(h, T1, T2, fo, fv, dT2)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOOOV; }, OOOV, (size_t)o * o * o * v, dOOOV)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOVOV; }, OVOV, (size_t)o * v * o * v, dOVOV)) return 1;
+    for (int i = 0; i < L; i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        const Problem& P = d.prob;
+        prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], dOOOV[i]);
+        prep_ov2<<<grid1d(ov2_elems(P)), 256, 0, d.stream>>>(P, d.OV2.d(), dOVOV[i]);
+        CK(cudaGetLastError());
+    }
+    h->launches += 2;
+    // OVVV -> Pt particle part, in chunks over the slowest index d: chunk c is staged (and gathered) into buffer c & 1 while the
+    // prep kernel of chunk c-1 runs out of the other one
+    const size_t slab = (size_t)o * v * v;   // doubles per d
+    const bool on_dev = classify(OVVV) == PK_DEVICE;
+    int dchunk = v;
+    if (!on_dev || L > 1) {
+        const size_t budget = (size_t)64 << 20;
+        dchunk = (int)std::max<size_t>(1, budget / (slab * sizeof(double)));
+        if (dchunk > v) dchunk = v;
+    }
+    int c = 0;
+    for (int d0 = 0; d0 < v; d0 += dchunk, c++) {
+        const int dn = std::min(dchunk, v - d0);
+        const int bsel = c & 1;
+        if (c >= 2)
+            for (Dev* dp : h->devs) {   // the buffer's previous content has been consumed
+                CK(cudaSetDevice(dp->dev));
+                CK(cudaStreamWaitEvent(dp->copy, dp->ev_free[bsel], 0));
+            }
+        if (distribute(h, [bsel](Dev& d) -> DevBuf& { return d.sChunk[bsel]; }, OVVV + (size_t)d0 * slab, (size_t)dn * slab, dChunk)) return 1;
+        for (int i = 0; i < L; i++) {
+            Dev& d = *h->devs[i];
+            CK(cudaSetDevice(d.dev));
+            dim3 grid((unsigned)(((size_t)o * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
+            prep_pt_particle<<<grid, dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], d0, dn);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(d.ev_free[bsel], d.stream));
+        }
+        h->launches += 1;
+    }
+    (void)W;
+    return upload_end(h, sync);
 }
 
 extern "C" int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
                                const double* OOOV, const double* OVOV, const double* fo, const double* fv)
 {
-    if (!h) return fail("fpt_upload_conv: NULL handle");
+    if (check_idle(h, "fpt_upload_conv")) return 1;
     if (!T1 || !T2 || !OVVV || !OOOV || !OVOV || !fo || !fv) return fail("fpt_upload_conv: NULL array argument");
-    CK(cudaSetDevice(h->dev));
-    auto t0 = std::chrono::steady_clock::now();
-    h->loaded = false;
-    h->launches = 0;
-    if (setup_problem(h, o, v)) return 1;
-    const Problem& P = h->prob;
-    double h2d = 0.0;
-    const double* dT2;
-    if (upload_common(h, T1, T2, fo, fv, &dT2, &h2d)) return 1;
-    const double *dOOOV, *dOVOV;
-    if (stage_in(h, h->sOOOV, OOOV, (size_t)o * o * o * v, &dOOOV, &h2d)) return 1;
-    if (stage_in(h, h->sOVOV, OVOV, (size_t)o * v * o * v, &dOVOV, &h2d)) return 1;
-    prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, h->stream>>>(P, h->Qt.d(), dT2, dOOOV);
-    prep_ov2<<<grid1d(ov2_elems(P)), 256, 0, h->stream>>>(P, h->OV2.d(), dOVOV);
-    h->launches += 2;
-    CK(cudaGetLastError());
-    // OVVV -> Pt particle part, in chunks over the slowest index d
-    const size_t slab = (size_t)o * v * v;   // doubles per d
-    const bool on_dev = is_device_ptr(OVVV);
-    int dchunk = v;
-    if (!on_dev) {
-        const size_t budget = (size_t)512 << 20;
-        dchunk = (int)(budget / (slab * sizeof(double)));
-        if (dchunk < 1) dchunk = 1;
-        if (dchunk > v) dchunk = v;
-        if (h->sChunk.ensure((size_t)dchunk * slab * sizeof(double))) return 1;
-    }
-    for (int d0 = 0; d0 < v; d0 += dchunk) {
-        const int dn = (v - d0 < dchunk) ? v - d0 : dchunk;
-        const double* src = OVVV + (size_t)d0 * slab;
-        if (!on_dev) {
-            CK(cudaMemcpyAsync(h->sChunk.p, src, (size_t)dn * slab * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            h2d += (double)dn * slab * sizeof(double);
-            src = h->sChunk.d();
-        }
-        dim3 grid((unsigned)(((size_t)o * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
-        prep_pt_particle<<<grid, dim3(32, 8), 0, h->stream>>>(P, h->Pt.d(), src, d0, dn);
-        h->launches += 1;
-        CK(cudaGetLastError());
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    h->loaded = true;
-    if (!h->peers.empty() && broadcast_operands(h)) return 1;
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_upload_conv", {T1, T2, OVVV, OOOV, OVOV, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_conv_impl(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, true)) return 1;
     h->last = fpt_stats{};
-    h->last.h2d_bytes = h2d;
-    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->last.h2d_bytes = h->h2d;
+    h->last.upload_ms = ms_since(t0);
     return 0;
+}
+
+// DF route: the (ia|bd), (ij|ka), (ia|jb) blocks that DFERI.jl:88-180 would materialise on the host are assembled on the GPU
+// from the B factors, straight into the fused kernel's layouts.  With several GPUs the big one -- Pt's particle part,
+// 2 naux o v^3 flops -- is assembled in slices over the occupied index p, one slice per GPU, and the slices are exchanged over
+// NVLink (one broadcast per owner, grouped); the two small ones are built redundantly everywhere.
+static int upload_df_impl(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                          const double* BOV, const double* BVV, const double* fo, const double* fv, bool sync)
+{
+    if (setup_problem(h, o, v)) return 1;
+    const int L = (int)h->devs.size(), W = h->world;
+    std::vector<const double*> dT2, dBOO, dBOV, dBVV;
+    if (upload_common(h, T1, T2, fo, fv, dT2)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOO; }, BOO, (size_t)naux * o * o, dBOO)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOV; }, BOV, (size_t)naux * o * v, dBOV)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBVV; }, BVV, (size_t)naux * v * v, dBVV)) return 1;
+    for (int i = 0; i < L; i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        const Problem& P = d.prob;
+        GemmOut out{};
+        out.P = P;
+        // Qt: particle part from T2, hole part OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z]          (DFERI.jl:88-112)
+        prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], nullptr);
+        CK(cudaGetLastError());
+        out.C = d.Qt.d();
+        CK(gemm_tn_launch<EPI_QT_HOLE>(d.stream, dBOO[i], rowmap_identity(), dBOV[i], rowmap_identity(), (i64)o * o, o * v, naux, out));
+        // OV2: OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z]                                            (DFERI.jl:139-154)
+        CK(cudaMemsetAsync(d.OV2.p, 0, (size_t)ov2_elems(P) * sizeof(double), d.stream));
+        out.C = d.OV2.d();
+        CK(gemm_tn_launch<EPI_OV2>(d.stream, dBOV[i], rowmap_identity(), dBOV[i], rowmap_identity(), (i64)o * v, o * v, naux, out));
+        // Pt particle part, this GPU's slice of p: OVVV[p,y,x,d] = sum_Q BOV[Q,p,y] BVV[Q,x,d]       (DFERI.jl:156-180)
+        const int p0 = (int)((i64)o * d.grank / W), p1 = (int)((i64)o * (d.grank + 1) / W);
+        out.C = d.Pt.d();
+        out.p0 = p0;
+        const RowMap mA{p0, o, 1, v};   // m = y + v*pl  ->  BOV row (p0+pl) + o*y
+        const RowMap mB{0, v, 1, v};    // n = d + v*x   ->  BVV row x + v*d
+        CK(gemm_tn_launch<EPI_PT>(d.stream, dBOV[i], mA, dBVV[i], mB, (i64)(p1 - p0) * v, v * v, naux, out));
+    }
+    h->launches += 4;
+    if (W > 1) {
+        const size_t pslab = (size_t)h->devs[0]->prob.vp * h->devs[0]->prob.vp * h->devs[0]->prob.Kp;
+        NCK(nccl_api().GroupStart());
+        for (int i = 0; i < L; i++) {
+            Dev& d = *h->devs[i];
+            for (int g = 0; g < W; g++) {
+                const int p0 = (int)((i64)o * g / W), p1 = (int)((i64)o * (g + 1) / W);
+                if (p1 > p0) NCK(nccl_api().Broadcast(d.Pt.d() + p0 * pslab, d.Pt.d() + p0 * pslab, (p1 - p0) * pslab, ncclDouble, g, d.comm, d.stream));
+            }
+        }
+        NCK(nccl_api().GroupEnd());
+    }
+    return upload_end(h, sync);
 }
 
 extern "C" int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
                              const double* BOV, const double* BVV, const double* fo, const double* fv)
 {
-    if (!h) return fail("fpt_upload_df: NULL handle");
+    if (check_idle(h, "fpt_upload_df")) return 1;
     if (!T1 || !T2 || !BOO || !BOV || !BVV || !fo || !fv) return fail("fpt_upload_df: NULL array argument");
     if (naux < 1) return fail("fpt_upload_df: invalid naux=%d", naux);
-    CK(cudaSetDevice(h->dev));
-    auto t0 = std::chrono::steady_clock::now();
-    h->loaded = false;
-    h->launches = 0;
-    if (setup_problem(h, o, v)) return 1;
-    const Problem& P = h->prob;
-    double h2d = 0.0;
-    const double* dT2;
-    if (upload_common(h, T1, T2, fo, fv, &dT2, &h2d)) return 1;
-    const double *dBOO, *dBOV, *dBVV;
-    if (stage_in(h, h->sBOO, BOO, (size_t)naux * o * o, &dBOO, &h2d)) return 1;
-    if (stage_in(h, h->sBOV, BOV, (size_t)naux * o * v, &dBOV, &h2d)) return 1;
-    if (stage_in(h, h->sBVV, BVV, (size_t)naux * v * v, &dBVV, &h2d)) return 1;
-    // Qt: T2 part by the gather kernel (OOOV argument unused for kappa >= v when we overwrite below) -> pass a
-    // zero-filled dummy?  Instead: prep_qt with OOOV = nullptr is not allowed, so build the T2 part with a DF-aware call:
-    // stage 1 fills everything (hole part from a temporary zero source is avoided by the kernel's branch order).
-    if (h->sOOOV.ensure((size_t)o * o * o * v * sizeof(double))) return 1;
-    CK(cudaMemsetAsync(h->sOOOV.p, 0, (size_t)o * o * o * v * sizeof(double), h->stream));
-    prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, h->stream>>>(P, h->Qt.d(), dT2, h->sOOOV.d());
-    {   // OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z]  -> Qt hole part        (DFERI.jl:88-112)
-        const int M = o * o, N = o * v;
-        dim3 grid((M + 63) / 64, (N + 63) / 64);
-        df_gemm_kernel<1><<<grid, 128, 0, h->stream>>>(P, h->Qt.d(), dBOO, dBOV, M, N, naux);
-    }
-    CK(cudaMemsetAsync(h->OV2.p, 0, (size_t)ov2_elems(P) * sizeof(double), h->stream));
-    {   // OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z]  -> OV2                 (DFERI.jl:139-154)
-        const int M = o * v, N = o * v;
-        dim3 grid((M + 63) / 64, (N + 63) / 64);
-        df_gemm_kernel<2><<<grid, 128, 0, h->stream>>>(P, h->OV2.d(), dBOV, dBOV, M, N, naux);
-    }
-    {   // OVVV[p,y,x,d] = sum_Q BOV[Q,p,y] BVV[Q,x,d]  -> Pt particle part    (DFERI.jl:156-180, never on the host)
-        const int M = o * v, N = v * v;
-        dim3 grid((M + 63) / 64, (N + 63) / 64);
-        df_gemm_kernel<0><<<grid, 128, 0, h->stream>>>(P, h->Pt.d(), dBOV, dBVV, M, N, naux);
-    }
-    h->launches += 4;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
-    h->loaded = true;
-    if (!h->peers.empty() && broadcast_operands(h)) return 1;
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_upload_df", {T1, T2, BOO, BOV, BVV, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_df_impl(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, true)) return 1;
     h->last = fpt_stats{};
-    h->last.h2d_bytes = h2d;
-    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->last.h2d_bytes = h->h2d;
+    h->last.upload_ms = ms_since(t0);
     return 0;
 }
 
@@ -396,278 +624,430 @@ extern "C" int fpt_num_items(fpt_handle* h, long long* n)
 {
     if (!h || !n) return fail("fpt_num_items: NULL argument");
     if (!h->loaded) return fail("fpt_num_items: no problem uploaded");
-    *n = h->prob.nitems;
+    *n = h->nitems;
     return 0;
+}
+
+// ---- compute ---------------------------------------------------------------------------------------------------------------
+static Problem current_problem(const fpt_handle* h, const Dev& d)
+{
+    Problem P = d.prob;
+    P.order = h->item_order;
+    P.dbg_flags = h->dbg_flags;
+    P.tw_begin = h->tw_begin;
+    P.tw_count = h->tw_count;
+    P.nitems = h->nitems;
+    return P;
 }
 
 // Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost (shard_items in fpt_layout.h,
 // shared with the CPU emulator so that the gloo tests exercise the very same split)
 static void shard_range(const fpt_handle* h, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
 {
-    shard_items(h->prob, h->block_cost.data(), b, e, rank, world, sb, se);
+    shard_items(current_problem(h, *h->devs[0]), h->block_cost.data(), b, e, rank, world, sb, se);
 }
 
-// launch the fused kernel + reduction for [item_begin, item_end) on h's device (asynchronous; result in h->out)
-static int compute_launch(fpt_handle* h, i64 item_begin, i64 item_end)
+// launch the fused kernel + reduction for [item_begin, item_end) on one GPU (asynchronous; result in d.out)
+static int compute_launch(fpt_handle* h, Dev& d, i64 item_begin, i64 item_end)
 {
-    CK(cudaSetDevice(h->dev));
-    const Problem& P = h->prob;
+    CK(cudaSetDevice(d.dev));
+    const Problem P = current_problem(h, d);
     const i64 n = item_end - item_begin;
-    int grid = h->n_sm;
+    int grid = d.n_sm;
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
-    CK(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
+    CK(cudaEventRecord(d.ev0, d.stream));
+    unsigned long long* ctr = (unsigned long long*)d.counter.p;
+#ifdef FPT_WITH_VARIANT2
     if (h->kernel_variant == 2) {
-        if (h->profiling)
-            triples_kernel2<true><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, h->stream>>>(
-                P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
-        else
-            triples_kernel2<false><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, h->stream>>>(
-                P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
-    } else if (h->profiling)
-        triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(
-            P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
+        if (h->profiling) triples_kernel2<true><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
+        else triples_kernel2<false><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
+    } else
+#endif
+    if (h->profiling)
+        triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
     else
-        triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, h->stream>>>(
-            P, item_begin, item_end, (unsigned long long*)h->counter.p, h->partials.d(), (long long*)h->prof.p);
-    h->last_grid = grid;
+        triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
+    d.last_grid = grid;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev1, d.stream));
+    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d());
+    CK(cudaGetLastError());
+    d.shard_b = item_begin;
+    d.shard_e = item_end;
+    return 0;
+}
+
+// Enqueue the evaluation of [item_begin, item_end): every GPU of the communicator takes its static, cost-weighted shard, E(T) is
+// one scalar all-reduce, and the 8-byte result is sent to the host.  Nothing here waits for the GPU.
+static int compute_enqueue(fpt_handle* h, i64 item_begin, i64 item_end)
+{
+    if (item_end < 0 || item_end > h->nitems) item_end = h->nitems;
+    if (item_begin < 0) item_begin = 0;
+    if (item_begin > item_end) item_begin = item_end;
+    const int W = h->world;
+    for (Dev* dp : h->devs) {
+        i64 sb, se;
+        shard_range(h, item_begin, item_end, dp->grank, W, &sb, &se);
+        if (compute_launch(h, *dp, sb, se)) return 1;
+    }
     h->last_profiled = h->profiling;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, h->stream));
-    reduce_partials<<<1, 32, 0, h->stream>>>(h->partials.d(), grid, h->out.d());
-    CK(cudaGetLastError());
+    if (W > 1) {   // the single scalar all-reduce of E(T)
+        NCK(nccl_api().GroupStart());
+        for (Dev* dp : h->devs) NCK(nccl_api().AllReduce(dp->out.p, dp->out.p, 1, ncclDouble, ncclSum, dp->comm, dp->stream));
+        NCK(nccl_api().GroupEnd());
+    }
+    Dev& d0 = *h->devs[0];
+    CK(cudaSetDevice(d0.dev));
+    CK(cudaMemcpyAsync(h->res_pinned, d0.out.p, sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CK(cudaEventRecord(d0.tl[5], d0.stream));
+    h->pend_items = item_end - item_begin;
+    return 0;
+}
+
+static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
+{
+    float ms_max = 0.f;
+    for (Dev* dp : h->devs) {
+        CK(cudaSetDevice(dp->dev));
+        CK(cudaStreamSynchronize(dp->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, dp->ev0, dp->ev1));
+        if (ms > ms_max) ms_max = ms;
+    }
+    if (Et) *Et = *h->res_pinned;
+    // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
+    const double ntrip = (double)h->tw_count;
+    const int v = h->v, o = h->o;
+    h->last.kernel_ms = ms_max;
+    h->last.n_items = h->pend_items;
+    h->last.n_triplets = (long long)ntrip;
+    h->last.flops = 12.0 * v * (double)v * v * (v + o) * ntrip * (h->nitems ? (double)h->pend_items / (double)h->nitems : 0.0);
+    h->last.n_launches = h->launches + 2 * (int)h->devs.size();
+    h->last.n_sm = h->devs[0]->n_sm;
+    // timeline of the first GPU, milliseconds since the upload began (entries stay 0 when the compute followed an older upload)
+    Dev& d0 = *h->devs[0];
+    CK(cudaSetDevice(d0.dev));
+    for (double& t : h->timeline) t = 0.0;
+    h->timeline[0] = h->stage_host_ms;
+    cudaEvent_t marks[5] = {d0.tl[1], d0.tl[2], d0.ev0, d0.ev1, d0.tl[5]};
+    for (int t = 0; t < 5; t++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, d0.tl[0], marks[t]) == cudaSuccess) h->timeline[1 + t] = ms;
+        else cudaGetLastError();
+    }
+    if (st) *st = h->last;
     return 0;
 }
 
 extern "C" int fpt_compute(fpt_handle* h, long long item_begin, long long item_end, double* Et, fpt_stats* st)
 {
     if (!h || !Et) return fail("fpt_compute: NULL argument");
+    if (check_idle(h, "fpt_compute")) return 1;
     if (!h->loaded) return fail("fpt_compute: no problem uploaded");
-    const Problem& P = h->prob;
-    if (item_end < 0 || item_end > P.nitems) item_end = P.nitems;
-    if (item_begin < 0) item_begin = 0;
-    if (item_begin > item_end) item_begin = item_end;
-    const i64 n = item_end - item_begin;
-    const int ng = 1 + (int)h->peers.size();
-    std::vector<fpt_handle*> hs(1, h);
-    for (fpt_handle* p : h->peers) hs.push_back(p);
-    // static contiguous shards of the range, one per GPU (equal estimated cost)
-    for (int d = 0; d < ng; d++) {
-        hs[d]->profiling = h->profiling;
-        hs[d]->kernel_variant = h->kernel_variant;
-        hs[d]->prob.order = P.order; hs[d]->prob.tw_begin = P.tw_begin; hs[d]->prob.tw_count = P.tw_count; hs[d]->prob.nitems = P.nitems;
-        i64 sb, se;
-        shard_range(h, item_begin, item_end, d, ng, &sb, &se);
-        if (compute_launch(hs[d], sb, se)) return 1;
+    DeviceGuard guard;
+    if (compute_enqueue(h, item_begin, item_end)) return 1;
+    return compute_finish(h, Et, st);
+}
+
+// Milliseconds since the start of the last upload, on the first GPU's clock: out8 = {host time spent copying pageable memory into
+// the pinned ring (wall, overlaps the DMAs), last H2D done, operands ready (gathers + prep done), kernel begin, kernel end,
+// result on its way to the host, 0, 0}.
+extern "C" int fpt_last_timeline(fpt_handle* h, double* out8)
+{
+    if (!h || !out8) return fail("fpt_last_timeline: NULL argument");
+    for (int t = 0; t < 8; t++) out8[t] = h->timeline[t];
+    return 0;
+}
+
+// ---- one-call forms ----------------------------------------------------------------------------------------------------------
+// upload and compute are enqueued back to back (no host synchronisation in between); `async` returns as soon as the caller's
+// arrays have been consumed, fpt_wait collects the result.
+static int finish_call(fpt_handle* h, bool async, wall::time_point t0, double* Et, fpt_stats* st)
+{
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h->h2d;
+    if (compute_enqueue(h, 0, -1)) return 1;
+    if (async) {
+        for (Dev* dp : h->devs) {   // inputs in pinned memory are read by the DMA engines directly: wait for those reads
+            CK(cudaSetDevice(dp->dev));
+            CK(cudaStreamSynchronize(dp->copy));
+        }
+        h->last.upload_ms = ms_since(t0);
+        h->pending = true;
+        return 0;
     }
-    if (ng > 1) {   // the single scalar all-reduce of E(T)
-        NCK(g_nccl.GroupStart());
-        for (int d = 0; d < ng; d++)
-            NCK(g_nccl.AllReduce(hs[d]->out.p, hs[d]->out.p, 1, ncclDouble, ncclSum, h->comms[d], hs[d]->stream));
-        NCK(g_nccl.GroupEnd());
-    }
-    double e = 0.0;
-    float ms_max = 0.f;
-    CK(cudaSetDevice(h->dev));
-    CK(cudaMemcpyAsync(&e, h->out.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    for (int d = 0; d < ng; d++) {
-        CK(cudaSetDevice(hs[d]->dev));
-        CK(cudaStreamSynchronize(hs[d]->stream));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, hs[d]->ev0, hs[d]->ev1));
-        if (ms > ms_max) ms_max = ms;
-    }
-    CK(cudaSetDevice(h->dev));
-    *Et = e;
-    // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
-    const double ntrip = (double)P.tw_count;
-    h->last.kernel_ms = ms_max;
-    h->last.n_items = n;
-    h->last.n_triplets = (long long)ntrip;
-    h->last.flops = 12.0 * P.v * (double)P.v * P.v * (P.v + P.o) * ntrip * (P.nitems ? (double)n / (double)P.nitems : 0.0);
-    h->last.n_launches = h->launches + 2 * ng;
-    h->last.n_sm = h->n_sm;
+    if (compute_finish(h, Et, nullptr)) return 1;
+    h->last.total_ms = ms_since(t0);
+    h->last.upload_ms = h->timeline[2];
     if (st) *st = h->last;
     return 0;
 }
 
-// multi-GPU handle: make the prepared operands resident on every peer (one NCCL broadcast per buffer, root = device 0)
-static int broadcast_operands(fpt_handle* h)
+static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
+                        const double* OVOV, const double* fo, const double* fv, double* Et, fpt_stats* st, bool async, const char* who)
 {
-    const Problem& P = h->prob;
-    const int ng = 1 + (int)h->peers.size();
-    for (fpt_handle* p : h->peers) {
-        CK(cudaSetDevice(p->dev));
-        p->dbg_flags = h->dbg_flags;
-        p->item_order = h->item_order;
-        p->loaded = false;
-        if (setup_problem(p, P.o, P.v)) return 1;
-    }
-    const size_t counts[6] = {(size_t)P.o * P.vp * P.vp * P.Kp, (size_t)P.o * P.o * P.G * P.vp * KGROUP, (size_t)ov2_elems(P),
-                              (size_t)P.o * P.v, (size_t)P.o, (size_t)P.v};
-    NCK(g_nccl.GroupStart());
-    for (int d = 0; d < ng; d++) {
-        fpt_handle* hd = d ? h->peers[d - 1] : h;
-        void* bufs[6] = {hd->Pt.p, hd->Qt.p, hd->OV2.p, hd->T1d.p, hd->fo.p, hd->fv.p};
-        for (int b = 0; b < 6; b++)
-            NCK(g_nccl.Broadcast(bufs[b], bufs[b], counts[b], ncclDouble, 0, h->comms[d], hd->stream));
-    }
-    NCK(g_nccl.GroupEnd());
-    for (int d = 0; d < ng; d++) {
-        fpt_handle* hd = d ? h->peers[d - 1] : h;
-        CK(cudaSetDevice(hd->dev));
-        CK(cudaStreamSynchronize(hd->stream));
-        hd->loaded = true;
-    }
-    CK(cudaSetDevice(h->dev));
-    return 0;
+    if (check_idle(h, who)) return 1;
+    if (!T1 || !T2 || !OVVV || !OOOV || !OVOV || !fo || !fv || (!async && !Et)) return fail("%s: NULL argument", who);
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, who, {T1, T2, OVVV, OOOV, OVOV, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_conv_impl(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, false)) return 1;
+    return finish_call(h, async, t0, Et, st);
+}
+
+static int triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO, const double* BOV,
+                      const double* BVV, const double* fo, const double* fv, double* Et, fpt_stats* st, bool async, const char* who)
+{
+    if (check_idle(h, who)) return 1;
+    if (!T1 || !T2 || !BOO || !BOV || !BVV || !fo || !fv || (!async && !Et)) return fail("%s: NULL argument", who);
+    if (naux < 1) return fail("%s: invalid naux=%d", who, naux);
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, who, {T1, T2, BOO, BOV, BVV, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_df_impl(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, false)) return 1;
+    return finish_call(h, async, t0, Et, st);
 }
 
 extern "C" int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
-                                const double* OOOV, const double* OVOV, const double* fo, const double* fv, double* Et,
-                                fpt_stats* st)
+                                const double* OOOV, const double* OVOV, const double* fo, const double* fv, double* Et, fpt_stats* st)
 {
-    auto t0 = std::chrono::steady_clock::now();
-    if (fpt_upload_conv(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv)) return 1;
-    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
-    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (st) *st = h->last;
-    return 0;
+    return triples_conv(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, Et, st, false, "fpt_triples_conv");
+}
+extern "C" int fpt_triples_conv_async(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                                      const double* OOOV, const double* OVOV, const double* fo, const double* fv)
+{
+    return triples_conv(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, nullptr, nullptr, true, "fpt_triples_conv_async");
+}
+extern "C" int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                              const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et, fpt_stats* st)
+{
+    return triples_df(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, Et, st, false, "fpt_triples_df");
+}
+extern "C" int fpt_triples_df_async(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                                    const double* BOV, const double* BVV, const double* fo, const double* fv)
+{
+    return triples_df(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, nullptr, nullptr, true, "fpt_triples_df_async");
 }
 
-extern "C" int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
-                              const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
-                              fpt_stats* st)
+extern "C" int fpt_wait(fpt_handle* h, double* Et, fpt_stats* st)
 {
-    auto t0 = std::chrono::steady_clock::now();
-    if (fpt_upload_df(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)) return 1;
-    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
-    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!h || !Et) return fail("fpt_wait: NULL argument");
+    if (!h->pending) return fail("fpt_wait: no asynchronous call is in flight");
+    DeviceGuard guard;
+    h->pending = false;
+    const auto t0 = wall::now();
+    if (compute_finish(h, Et, nullptr)) return 1;
+    h->last.total_ms = h->last.upload_ms + ms_since(t0);   // host time inside the two calls
     if (st) *st = h->last;
     return 0;
 }
 
 // ---- AO -> MO route (replaces Chonky.jl:28-114 for the three blocks the (T) path reads) --------------------------
-static int quarter(fpt_handle* h, double* C, const double* A, const double* B, i64 M, int N, int Q, i64 ldc = 0)
+// C[m + ldc*n] = sum_q A[q + Q*m] B[q + Q*n]
+static int quarter(fpt_handle* h, Dev& d, double* C, const double* A, const double* B, i64 M, int N, int Q, i64 ldc = 0)
 {
-    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
-    quarter_gemm_kernel<<<grid, 128, 0, h->stream>>>(C, A, B, M, N, Q, ldc ? ldc : M);
+    GemmOut out{};
+    out.C = C;
+    out.ldc = ldc ? ldc : M;
+    CK(gemm_tn_launch<EPI_COLMAJOR>(d.stream, A, rowmap_identity(), B, rowmap_identity(), M, N, Q, out));
     h->launches += 1;
-    CK(cudaGetLastError());
     return 0;
 }
 
 // AOERI[mu,nu,rho,sigma] (nbf^4, column-major, chemist notation as in aoints["ERI"]), Co = C[:, occupied] (nbf x o),
 // Cv = C[:, virtual] (nbf x v): the frozen-core / dropped-virtual slices the reference takes in Chonky.jl:38-41.
-extern "C" int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
-                             const double* Co, const double* Cv, const double* fo, const double* fv)
+// The transformation runs on the handle's first GPU; the MO blocks then take the conventional route from device memory (a
+// multi-GPU handle broadcasts them over NVLink; in rank mode every process transforms its own copy).
+static int upload_ao_impl(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                          const double* Co, const double* Cv, const double* fo, const double* fv, bool sync)
 {
-    if (!h) return fail("fpt_upload_ao: NULL handle");
-    if (!T1 || !T2 || !AOERI || !Co || !Cv || !fo || !fv) return fail("fpt_upload_ao: NULL array argument");
-    if (nbf < 1 || o < 1 || v < 1 || o + v > nbf) return fail("fpt_upload_ao: invalid dimensions nbf=%d o=%d v=%d", nbf, o, v);
-    CK(cudaSetDevice(h->dev));
-    auto t0 = std::chrono::steady_clock::now();
-    h->loaded = false;
-    h->launches = 0;
-    double h2d = 0.0;
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
     const i64 n1 = nbf, n2 = n1 * nbf, n3 = n2 * nbf;
-    const double *dCo, *dCv;
-    if (stage_in(h, h->sCo, Co, (size_t)nbf * o, &dCo, &h2d)) return 1;
-    if (stage_in(h, h->sCv, Cv, (size_t)nbf * v, &dCv, &h2d)) return 1;
-    if (h->aoQ1.ensure((size_t)n3 * o * sizeof(double))) return 1;
+    // the copy stream continues from whatever the compute stream still has in flight
+    CK(cudaEventRecord(d.ev_start, d.stream));
+    CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));
+    const double *dCo = Co, *dCv = Cv;
+    if (classify(Co) != PK_DEVICE) {
+        if (d.sCo.ensure((size_t)nbf * o * sizeof(double))) return 1;
+        if (stage_to(h, d, d.sCo.p, Co, (size_t)nbf * o * sizeof(double), classify(Co))) return 1;
+        dCo = d.sCo.d();
+    }
+    if (classify(Cv) != PK_DEVICE) {
+        if (d.sCv.ensure((size_t)nbf * v * sizeof(double))) return 1;
+        if (stage_to(h, d, d.sCv.p, Cv, (size_t)nbf * v * sizeof(double), classify(Cv))) return 1;
+        dCv = d.sCv.d();
+    }
+    if (copy_then_stream(d)) return 1;
+    if (d.aoQ1.ensure((size_t)n3 * o * sizeof(double))) return 1;
     // quarter 1: Q1[(nu,rho,sigma), i] = sum_mu AOERI[mu,(nu,rho,sigma)] Co[mu,i], streamed over sigma slabs of the AO tensor
     {
-        const bool on_dev = is_device_ptr(AOERI);
+        const PtrKind kind = classify(AOERI);
         int schunk = nbf;
-        if (!on_dev) {
-            const size_t budget = (size_t)512 << 20;
-            schunk = (int)(budget / ((size_t)n3 * sizeof(double)));
-            if (schunk < 1) schunk = 1;
+        if (kind != PK_DEVICE) {
+            const size_t budget = (size_t)128 << 20;
+            schunk = (int)std::max<size_t>(1, budget / ((size_t)n3 * sizeof(double)));
             if (schunk > nbf) schunk = nbf;
-            if (h->sChunk.ensure((size_t)schunk * n3 * sizeof(double))) return 1;
+            for (int b = 0; b < 2; b++)
+                if (d.sChunk[b].ensure((size_t)schunk * n3 * sizeof(double))) return 1;
         }
-        for (int s0 = 0; s0 < nbf; s0 += schunk) {
-            const int sn = (nbf - s0 < schunk) ? nbf - s0 : schunk;
+        int c = 0;
+        for (int s0 = 0; s0 < nbf; s0 += schunk, c++) {
+            const int sn = std::min(schunk, nbf - s0);
             const double* src = AOERI + (size_t)s0 * n3;
-            if (!on_dev) {
-                CK(cudaMemcpyAsync(h->sChunk.p, src, (size_t)sn * n3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-                h2d += (double)sn * n3 * sizeof(double);
-                src = h->sChunk.d();
+            if (kind != PK_DEVICE) {
+                const int bsel = c & 1;
+                if (c >= 2) CK(cudaStreamWaitEvent(d.copy, d.ev_free[bsel], 0));
+                if (stage_to(h, d, d.sChunk[bsel].p, src, (size_t)sn * n3 * sizeof(double), kind)) return 1;
+                if (copy_then_stream(d)) return 1;
+                src = d.sChunk[bsel].d();
             }
             // rows (nu,rho,sigma) of this slab are rows [s0*nbf^2, (s0+sn)*nbf^2) of Q1, whose leading dimension is nbf^3
-            if (quarter(h, h->aoQ1.d() + (size_t)s0 * n2, src, dCo, (i64)sn * n2, o, nbf, n3)) return 1;
+            if (quarter(h, d, d.aoQ1.d() + (size_t)s0 * n2, src, dCo, (i64)sn * n2, o, nbf, n3)) return 1;
+            if (kind != PK_DEVICE) CK(cudaEventRecord(d.ev_free[c & 1], d.stream));
         }
     }
     // quarter 2: contract nu.  Q2v[(rho,sigma,i), a], Q2o[(rho,sigma,i), j]
-    if (h->aoQ2v.ensure((size_t)n2 * o * v * sizeof(double))) return 1;
-    if (h->aoQ2o.ensure((size_t)n2 * o * o * sizeof(double))) return 1;
-    if (quarter(h, h->aoQ2v.d(), h->aoQ1.d(), dCv, n2 * o, v, nbf)) return 1;
-    if (quarter(h, h->aoQ2o.d(), h->aoQ1.d(), dCo, n2 * o, o, nbf)) return 1;
+    if (d.aoQ2v.ensure((size_t)n2 * o * v * sizeof(double))) return 1;
+    if (d.aoQ2o.ensure((size_t)n2 * o * o * sizeof(double))) return 1;
+    if (quarter(h, d, d.aoQ2v.d(), d.aoQ1.d(), dCv, n2 * o, v, nbf)) return 1;
+    if (quarter(h, d, d.aoQ2o.d(), d.aoQ1.d(), dCo, n2 * o, o, nbf)) return 1;
     // quarter 3: contract rho.  Q3vv[(sigma,i,a), b], Q3vo[(sigma,i,a), j], Q3oo[(sigma,i,j), k]
-    if (h->aoQ3vv.ensure((size_t)n1 * o * v * v * sizeof(double))) return 1;
-    if (h->aoQ3vo.ensure((size_t)n1 * o * v * o * sizeof(double))) return 1;
-    if (h->aoQ3oo.ensure((size_t)n1 * o * o * o * sizeof(double))) return 1;
-    if (quarter(h, h->aoQ3vv.d(), h->aoQ2v.d(), dCv, n1 * o * v, v, nbf)) return 1;
-    if (quarter(h, h->aoQ3vo.d(), h->aoQ2v.d(), dCo, n1 * o * v, o, nbf)) return 1;
-    if (quarter(h, h->aoQ3oo.d(), h->aoQ2o.d(), dCo, n1 * o * o, o, nbf)) return 1;
+    if (d.aoQ3vv.ensure((size_t)n1 * o * v * v * sizeof(double))) return 1;
+    if (d.aoQ3vo.ensure((size_t)n1 * o * v * o * sizeof(double))) return 1;
+    if (d.aoQ3oo.ensure((size_t)n1 * o * o * o * sizeof(double))) return 1;
+    if (quarter(h, d, d.aoQ3vv.d(), d.aoQ2v.d(), dCv, n1 * o * v, v, nbf)) return 1;
+    if (quarter(h, d, d.aoQ3vo.d(), d.aoQ2v.d(), dCo, n1 * o * v, o, nbf)) return 1;
+    if (quarter(h, d, d.aoQ3oo.d(), d.aoQ2o.d(), dCo, n1 * o * o, o, nbf)) return 1;
     // quarter 4: contract sigma with Cv -> OVVV[i,a,b,c], OVOV[i,a,j,b], OOOV[i,j,k,a] in the reference's layouts
-    if (h->aoOVVV.ensure((size_t)o * v * v * v * sizeof(double))) return 1;
-    if (h->aoOVOV.ensure((size_t)o * v * o * v * sizeof(double))) return 1;
-    if (h->aoOOOV.ensure((size_t)o * o * o * v * sizeof(double))) return 1;
-    if (quarter(h, h->aoOVVV.d(), h->aoQ3vv.d(), dCv, (i64)o * v * v, v, nbf)) return 1;
-    if (quarter(h, h->aoOVOV.d(), h->aoQ3vo.d(), dCv, (i64)o * v * o, v, nbf)) return 1;
-    if (quarter(h, h->aoOOOV.d(), h->aoQ3oo.d(), dCv, (i64)o * o * o, v, nbf)) return 1;
+    if (d.aoOVVV.ensure((size_t)o * v * v * v * sizeof(double))) return 1;
+    if (d.aoOVOV.ensure((size_t)o * v * o * v * sizeof(double))) return 1;
+    if (d.aoOOOV.ensure((size_t)o * o * o * v * sizeof(double))) return 1;
+    if (quarter(h, d, d.aoOVVV.d(), d.aoQ3vv.d(), dCv, (i64)o * v * v, v, nbf)) return 1;
+    if (quarter(h, d, d.aoOVOV.d(), d.aoQ3vo.d(), dCv, (i64)o * v * o, v, nbf)) return 1;
+    if (quarter(h, d, d.aoOOOV.d(), d.aoQ3oo.d(), dCv, (i64)o * o * o, v, nbf)) return 1;
     const int ao_launches = h->launches;
-    if (fpt_upload_conv(h, o, v, T1, T2, h->aoOVVV.d(), h->aoOOOV.d(), h->aoOVOV.d(), fo, fv)) return 1;
+    if (upload_conv_impl(h, o, v, T1, T2, d.aoOVVV.d(), d.aoOOOV.d(), d.aoOVOV.d(), fo, fv, sync)) return 1;
     h->launches += ao_launches;
-    h->last.h2d_bytes += h2d;
-    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;
+}
+
+static int check_ao_args(fpt_handle* h, const char* who, int nbf, int o, int v)
+{
+    if (check_idle(h, who)) return 1;
+    if (nbf < 1 || o < 1 || v < 1 || o + v > nbf) return fail("%s: invalid dimensions nbf=%d o=%d v=%d", who, nbf, o, v);
+    return 0;
+}
+
+extern "C" int fpt_upload_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                             const double* Co, const double* Cv, const double* fo, const double* fv)
+{
+    if (check_ao_args(h, "fpt_upload_ao", nbf, o, v)) return 1;
+    if (!T1 || !T2 || !AOERI || !Co || !Cv || !fo || !fv) return fail("fpt_upload_ao: NULL array argument");
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_upload_ao", {T1, T2, AOERI, Co, Cv, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_ao_impl(h, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv, true)) return 1;
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h->h2d;
+    h->last.upload_ms = ms_since(t0);
+    return 0;
+}
+
+extern "C" int fpt_triples_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
+                              const double* Co, const double* Cv, const double* fo, const double* fv, double* Et, fpt_stats* st)
+{
+    if (check_ao_args(h, "fpt_triples_ao", nbf, o, v)) return 1;
+    if (!T1 || !T2 || !AOERI || !Co || !Cv || !fo || !fv || !Et) return fail("fpt_triples_ao: NULL argument");
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_triples_ao", {T1, T2, AOERI, Co, Cv, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_ao_impl(h, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv, false)) return 1;
+    return finish_call(h, false, t0, Et, st);
 }
 
 // Sparse AO list (the reference's default conventional container): `nint` symmetry-unique integrals, vals[z] = (mu nu|rho sigma)
 // with zero-based indices idx[4z..4z+3] stored as `index_bytes`-wide integers (2: Vector{NTuple{4,Int16}}, 4: Int32).
+static int upload_ao_sparse_impl(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
+                                 const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
+                                 const double* fo, const double* fv, bool sync)
+{
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
+    const size_t n4 = (size_t)nbf * nbf * nbf * nbf;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (n4 * sizeof(double) > free_b + d.aoDense.cap)
+        return fail("fpt_upload_ao_sparse: the dense AO tensor (%.1f GB for nbf=%d) does not fit the device", n4 * 8e-9, nbf);
+    if (d.aoDense.ensure(n4 * sizeof(double))) return 1;
+    if (d.aoFlag.ensure(sizeof(int))) return 1;
+    CK(cudaMemsetAsync(d.aoDense.p, 0, n4 * sizeof(double), d.stream));
+    CK(cudaMemsetAsync(d.aoFlag.p, 0, sizeof(int), d.stream));
+    double h2d_list = 0.0;
+    if (nint > 0) {
+        CK(cudaEventRecord(d.ev_start, d.stream));
+        CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));
+        const void* didx = idx;
+        const double* dvals = vals;
+        const double before = h->h2d;
+        if (classify(idx) != PK_DEVICE) {
+            if (d.sIdx.ensure((size_t)nint * 4 * index_bytes)) return 1;
+            if (stage_to(h, d, d.sIdx.p, idx, (size_t)nint * 4 * index_bytes, classify(idx))) return 1;
+            didx = d.sIdx.p;
+        }
+        if (classify(vals) != PK_DEVICE) {
+            if (d.sVals.ensure((size_t)nint * sizeof(double))) return 1;
+            if (stage_to(h, d, d.sVals.p, vals, (size_t)nint * sizeof(double), classify(vals))) return 1;
+            dvals = d.sVals.d();
+        }
+        h2d_list = h->h2d - before;
+        if (copy_then_stream(d)) return 1;
+        const int grid = (int)std::min<long long>((nint + 255) / 256, 148LL * 32);
+        if (index_bytes == 2)
+            expand_sparse_eri_kernel<short><<<grid, 256, 0, d.stream>>>(d.aoDense.d(), (const short*)didx, dvals, nint, nbf, (int*)d.aoFlag.p);
+        else
+            expand_sparse_eri_kernel<int><<<grid, 256, 0, d.stream>>>(d.aoDense.d(), (const int*)didx, dvals, nint, nbf, (int*)d.aoFlag.p);
+        CK(cudaGetLastError());
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, d.aoFlag.p, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        if (bad) return fail("fpt_upload_ao_sparse: the integral list holds an index outside [0, %d) (indices are zero-based)", nbf);
+    }
+    if (upload_ao_impl(h, nbf, o, v, T1, T2, d.aoDense.d(), Co, Cv, fo, fv, sync)) return 1;
+    h->launches += 1;
+    (void)h2d_list;
+    return 0;
+}
+
+static int check_sparse_args(fpt_handle* h, const char* who, int nbf, int o, int v, long long nint, const void* idx, int index_bytes,
+                             const double* vals)
+{
+    if (check_ao_args(h, who, nbf, o, v)) return 1;
+    if (nint < 0 || (nint > 0 && (!idx || !vals))) return fail("%s: invalid integral list (nint=%lld)", who, nint);
+    if (index_bytes != 2 && index_bytes != 4) return fail("%s: index_bytes must be 2 or 4, got %d", who, index_bytes);
+    if (index_bytes == 2 && nbf > 32767) return fail("%s: nbf=%d does not fit 16-bit indices", who, nbf);
+    return 0;
+}
+
 extern "C" int fpt_upload_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, long long nint,
                                     const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
                                     const double* fo, const double* fv)
 {
-    if (!h) return fail("fpt_upload_ao_sparse: NULL handle");
-    if (!T1 || !T2 || !Co || !Cv || !fo || !fv || (nint > 0 && (!idx || !vals))) return fail("fpt_upload_ao_sparse: NULL array argument");
-    if (nbf < 1 || o < 1 || v < 1 || o + v > nbf || nint < 0) return fail("fpt_upload_ao_sparse: invalid dimensions nbf=%d o=%d v=%d nint=%lld", nbf, o, v, nint);
-    if (index_bytes != 2 && index_bytes != 4) return fail("fpt_upload_ao_sparse: index_bytes must be 2 or 4, got %d", index_bytes);
-    if (index_bytes == 2 && nbf > 32767) return fail("fpt_upload_ao_sparse: nbf=%d does not fit 16-bit indices", nbf);
-    CK(cudaSetDevice(h->dev));
-    auto t0 = std::chrono::steady_clock::now();
-    const size_t n4 = (size_t)nbf * nbf * nbf * nbf;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    if (n4 * sizeof(double) > free_b + h->aoDense.cap)
-        return fail("fpt_upload_ao_sparse: the dense AO tensor (%.1f GB for nbf=%d) does not fit the device", n4 * 8e-9, nbf);
-    if (h->aoDense.ensure(n4 * sizeof(double))) return 1;
-    CK(cudaMemsetAsync(h->aoDense.p, 0, n4 * sizeof(double), h->stream));
-    double h2d = 0.0;
-    if (nint > 0) {
-        const bool idx_dev = is_device_ptr(idx);
-        const void* didx = idx;
-        if (!idx_dev) {
-            if (h->sIdx.ensure((size_t)nint * 4 * index_bytes)) return 1;
-            CK(cudaMemcpyAsync(h->sIdx.p, idx, (size_t)nint * 4 * index_bytes, cudaMemcpyHostToDevice, h->stream));
-            h2d += (double)nint * 4 * index_bytes;
-            didx = h->sIdx.p;
-        }
-        const double* dvals;
-        if (stage_in(h, h->sVals, vals, (size_t)nint, &dvals, &h2d)) return 1;
-        const int grid = (int)std::min<long long>((nint + 255) / 256, 148LL * 32);
-        if (index_bytes == 2)
-            expand_sparse_eri_kernel<short><<<grid, 256, 0, h->stream>>>(h->aoDense.d(), (const short*)didx, dvals, nint, nbf);
-        else
-            expand_sparse_eri_kernel<int><<<grid, 256, 0, h->stream>>>(h->aoDense.d(), (const int*)didx, dvals, nint, nbf);
-        CK(cudaGetLastError());
-    }
-    if (fpt_upload_ao(h, nbf, o, v, T1, T2, h->aoDense.d(), Co, Cv, fo, fv)) return 1;
-    h->launches += 1;
-    h->last.h2d_bytes += h2d;
-    h->last.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (check_sparse_args(h, "fpt_upload_ao_sparse", nbf, o, v, nint, idx, index_bytes, vals)) return 1;
+    if (!T1 || !T2 || !Co || !Cv || !fo || !fv) return fail("fpt_upload_ao_sparse: NULL array argument");
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_upload_ao_sparse", {T1, T2, idx, vals, Co, Cv, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_ao_sparse_impl(h, nbf, o, v, T1, T2, nint, idx, index_bytes, vals, Co, Cv, fo, fv, true)) return 1;
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h->h2d;
+    h->last.upload_ms = ms_since(t0);
     return 0;
 }
 
@@ -675,67 +1055,95 @@ extern "C" int fpt_triples_ao_sparse(fpt_handle* h, int nbf, int o, int v, const
                                      const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
                                      const double* fo, const double* fv, double* Et, fpt_stats* st)
 {
-    auto t0 = std::chrono::steady_clock::now();
-    if (fpt_upload_ao_sparse(h, nbf, o, v, T1, T2, nint, idx, index_bytes, vals, Co, Cv, fo, fv)) return 1;
-    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
-    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (st) *st = h->last;
-    return 0;
+    if (check_sparse_args(h, "fpt_triples_ao_sparse", nbf, o, v, nint, idx, index_bytes, vals)) return 1;
+    if (!T1 || !T2 || !Co || !Cv || !fo || !fv || !Et) return fail("fpt_triples_ao_sparse: NULL argument");
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    if (admit_device_inputs(h, "fpt_triples_ao_sparse", {T1, T2, idx, vals, Co, Cv, fo, fv})) return 1;
+    upload_begin(h);
+    if (upload_ao_sparse_impl(h, nbf, o, v, T1, T2, nint, idx, index_bytes, vals, Co, Cv, fo, fv, false)) return 1;
+    return finish_call(h, false, t0, Et, st);
 }
 
-extern "C" int fpt_triples_ao(fpt_handle* h, int nbf, int o, int v, const double* T1, const double* T2, const double* AOERI,
-                              const double* Co, const double* Cv, const double* fo, const double* fv, double* Et, fpt_stats* st)
-{
-    auto t0 = std::chrono::steady_clock::now();
-    if (fpt_upload_ao(h, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv)) return 1;
-    if (fpt_compute(h, 0, -1, Et, nullptr)) return 1;
-    h->last.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (st) *st = h->last;
-    return 0;
-}
-
+// ---- calibration and diagnostics ---------------------------------------------------------------------------------------------
 extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops)
 {
     if (!h || !tflops) return fail("fpt_fp64_peak: NULL argument");
-    CK(cudaSetDevice(h->dev));
-    if (h->out.ensure(sizeof(double))) return 1;
+    if (check_idle(h, "fpt_fp64_peak")) return 1;
+    DeviceGuard guard;
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
+    if (d.out.ensure(sizeof(double))) return 1;
     const int iters = 4096;
-    const int grid = h->n_sm * 8;   // 8 CTAs x 8 warps per SM -> 16 warps per SMSP
+    const int grid = d.n_sm * 8;   // 8 CTAs x 8 warps per SM -> 16 warps per SMSP
     // flops per launch
     const double fl = (variant == 0) ? (double)grid * 8 /*warps*/ * iters * 16.0 * 512.0
                                      : (double)grid * 256 /*threads*/ * iters * 16.0 * 2.0;
     auto launch = [&]() {
-        if (variant == 0) peak_dmma_kernel<<<grid, 256, 0, h->stream>>>(h->out.d(), iters, 1e-3);
-        else peak_dfma_kernel<<<grid, 256, 0, h->stream>>>(h->out.d(), iters, 1e-3);
+        if (variant == 0) peak_dmma_kernel<<<grid, 256, 0, d.stream>>>(d.out.d(), iters, 1e-3);
+        else peak_dfma_kernel<<<grid, 256, 0, d.stream>>>(d.out.d(), iters, 1e-3);
     };
     launch();
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(d.stream));
     CK(cudaGetLastError());
     // calibrate launch count
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaEventRecord(d.ev0, d.stream));
     launch();
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
     float ms1 = 0.f;
-    CK(cudaEventElapsedTime(&ms1, h->ev0, h->ev1));
+    CK(cudaEventElapsedTime(&ms1, d.ev0, d.ev1));
     int reps = (int)(ms_target / (ms1 > 1e-3f ? ms1 : 1e-3f));
     if (reps < 1) reps = 1;
     if (reps > 20000) reps = 20000;
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaEventRecord(d.ev0, d.stream));
     for (int t = 0; t < reps; t++) launch();
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
     *tflops = fl * reps / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+// Stand-alone timing of the K3 / K5 GEMM on synthetic operands (measurement aid): C(M x N) = A(M x K) . B(N x K)^T, column-major
+// output, `reps` launches; returns the sustained TFLOP/s (2 M N K per launch).
+extern "C" int fpt_gemm_bench(fpt_handle* h, long long M, int N, int K, int reps, double* tflops)
+{
+    if (!h || !tflops) return fail("fpt_gemm_bench: NULL argument");
+    if (check_idle(h, "fpt_gemm_bench")) return 1;
+    if (M < 1 || N < 1 || K < 1 || reps < 1) return fail("fpt_gemm_bench: invalid shape");
+    DeviceGuard guard;
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
+    DevBuf A, B, C;
+    if (A.ensure((size_t)M * K * sizeof(double)) || B.ensure((size_t)N * K * sizeof(double)) || C.ensure((size_t)M * N * sizeof(double))) {
+        A.release(); B.release(); C.release();
+        return 1;
+    }
+    cudaMemsetAsync(A.p, 0, (size_t)M * K * sizeof(double), d.stream);
+    cudaMemsetAsync(B.p, 0, (size_t)N * K * sizeof(double), d.stream);
+    GemmOut out{};
+    out.C = C.d();
+    out.ldc = M;
+    cudaError_t e = gemm_tn_launch<EPI_COLMAJOR>(d.stream, A.d(), rowmap_identity(), B.d(), rowmap_identity(), M, N, K, out);
+    cudaEventRecord(d.ev0, d.stream);
+    for (int r = 0; r < reps && e == cudaSuccess; r++)
+        e = gemm_tn_launch<EPI_COLMAJOR>(d.stream, A.d(), rowmap_identity(), B.d(), rowmap_identity(), M, N, K, out);
+    cudaEventRecord(d.ev1, d.stream);
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, d.ev0, d.ev1);
+    A.release(); B.release(); C.release();
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail("fpt_gemm_bench: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    *tflops = 2.0 * (double)M * N * K * reps / (ms * 1e-3) / 1e12;
     return 0;
 }
 
 extern "C" int fpt_set_debug_flags(fpt_handle* h, int flags)
 {
     if (!h) return fail("fpt_set_debug_flags: NULL handle");
-    h->prob.dbg_flags = flags;
-    h->dbg_flags = flags;
+    h->dbg_flags = flags;   // read by every GPU of the handle at the next compute
     return 0;
 }
 
@@ -745,15 +1153,14 @@ extern "C" int fpt_set_triplet_window(fpt_handle* h, long long t_begin, long lon
 {
     if (!h) return fail("fpt_set_triplet_window: NULL handle");
     if (!h->loaded) return fail("fpt_set_triplet_window: no problem uploaded");
-    Problem& P = h->prob;
-    const i64 nfull = (i64)P.o * (P.o + 1) * (P.o + 2) / 6;
+    const i64 nfull = (i64)h->o * (h->o + 1) * (h->o + 2) / 6;
     if (t_end < 0 || t_end > nfull) t_end = nfull;
     if (t_begin < 0) t_begin = 0;
     if (t_begin > t_end) t_begin = t_end;
-    const i64 u0 = triplets_before(P.o, t_begin), u1 = triplets_before(P.o, t_end);
-    P.tw_begin = u0;
-    P.tw_count = u1 - u0;
-    P.nitems = P.nb * P.tw_count;
+    const i64 u0 = triplets_before(h->o, t_begin), u1 = triplets_before(h->o, t_end);
+    h->tw_begin = u0;
+    h->tw_count = u1 - u0;
+    h->nitems = h->devs[0]->prob.nb * h->tw_count;
     return 0;
 }
 
@@ -763,7 +1170,6 @@ extern "C" int fpt_set_item_order(fpt_handle* h, int order)
     if (!h) return fail("fpt_set_item_order: NULL handle");
     if (order != 0 && order != 1) return fail("fpt_set_item_order: order must be 0 or 1, got %d", order);
     h->item_order = order;
-    h->prob.order = order;
     return 0;
 }
 
@@ -774,7 +1180,7 @@ extern "C" int fpt_shard_items(fpt_handle* h, int rank, int world, long long* it
     if (!h->loaded) return fail("fpt_shard_items: no problem uploaded");
     if (world < 1 || rank < 0 || rank >= world) return fail("fpt_shard_items: invalid rank %d of %d", rank, world);
     i64 sb, se;
-    shard_range(h, 0, h->prob.nitems, rank, world, &sb, &se);
+    shard_range(h, 0, h->nitems, rank, world, &sb, &se);
     *item_begin = sb;
     *item_end = se;
     return 0;
@@ -783,7 +1189,11 @@ extern "C" int fpt_shard_items(fpt_handle* h, int rank, int world, long long* it
 extern "C" int fpt_set_kernel_variant(fpt_handle* h, int variant)
 {
     if (!h) return fail("fpt_set_kernel_variant: NULL handle");
+#ifdef FPT_WITH_VARIANT2
     if (variant != 1 && variant != 2) return fail("fpt_set_kernel_variant: variant must be 1 or 2, got %d", variant);
+#else
+    if (variant != 1) return fail("fpt_set_kernel_variant: variant %d is not in this build (the experimental epilogue-warp kernel needs -DFPT_WITH_VARIANT2)", variant);
+#endif
     h->kernel_variant = variant;
     return 0;
 }
@@ -795,18 +1205,19 @@ extern "C" int fpt_set_profiling(fpt_handle* h, int on)
     return 0;
 }
 
-// Phase breakdown of the last fpt_compute (cycles summed over CTAs, warp 0's view):
-// out[0..5] = setup, zero+prologue, k-loops, RMW epilogues, energy stage, total
-extern "C" int fpt_last_profile(fpt_handle* h, double* out6)
+// Phase breakdown of the last fpt_compute on the handle's first GPU (cycles summed over CTAs; see the header for the 24 entries)
+extern "C" int fpt_last_profile(fpt_handle* h, double* out24)
 {
-    if (!h || !out6) return fail("fpt_last_profile: NULL argument");
-    if (h->last_grid <= 0 || !h->last_profiled) return fail("fpt_last_profile: the last compute was not profiled (fpt_set_profiling)");
-    CK(cudaSetDevice(h->dev));
-    std::vector<long long> buf((size_t)h->last_grid * NPROF);
-    CK(cudaMemcpy(buf.data(), h->prof.p, buf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int t = 0; t < NPROF; t++) out6[t] = 0.0;
-    for (int b = 0; b < h->last_grid; b++)
-        for (int t = 0; t < NPROF; t++) out6[t] += (double)buf[(size_t)b * NPROF + t];
+    if (!h || !out24) return fail("fpt_last_profile: NULL argument");
+    Dev& d = *h->devs[0];
+    if (d.last_grid <= 0 || !h->last_profiled) return fail("fpt_last_profile: the last compute was not profiled (fpt_set_profiling)");
+    DeviceGuard guard;
+    CK(cudaSetDevice(d.dev));
+    std::vector<long long> buf((size_t)d.last_grid * NPROF);
+    CK(cudaMemcpy(buf.data(), d.prof.p, buf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int t = 0; t < NPROF; t++) out24[t] = 0.0;
+    for (int b = 0; b < d.last_grid; b++)
+        for (int t = 0; t < NPROF; t++) out24[t] += (double)buf[(size_t)b * NPROF + t];
     return 0;
 }
 
@@ -815,8 +1226,11 @@ extern "C" int fpt_last_profile(fpt_handle* h, double* out6)
 extern "C" int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops)
 {
     if (!h || !tflops) return fail("fpt_dmma_sweep: NULL argument");
-    CK(cudaSetDevice(h->dev));
-    if (h->out.ensure(sizeof(double))) return 1;
+    if (check_idle(h, "fpt_dmma_sweep")) return 1;
+    DeviceGuard guard;
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
+    if (d.out.ensure(sizeof(double))) return 1;
     const int iters = 20000 / ilp;
     const int threads = warps_per_sm * 32;
     if (threads < 32 || threads > 1024) return fail("fpt_dmma_sweep: warps_per_sm out of range");
@@ -832,15 +1246,15 @@ extern "C" int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* 
     }
     const size_t smem = 120 * 1024;   // > half of the SM: forces 1 CTA/SM
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<h->n_sm, threads, smem, h->stream>>>(h->out.d(), iters, 1e-3);
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventRecord(h->ev0, h->stream));
-    for (int r = 0; r < 5; r++) k<<<h->n_sm, threads, smem, h->stream>>>(h->out.d(), iters, 1e-3);
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    k<<<d.n_sm, threads, smem, d.stream>>>(d.out.d(), iters, 1e-3);
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaEventRecord(d.ev0, d.stream));
+    for (int r = 0; r < 5; r++) k<<<d.n_sm, threads, smem, d.stream>>>(d.out.d(), iters, 1e-3);
+    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
     CK(cudaGetLastError());
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    *tflops = 5.0 * h->n_sm * warps_per_sm * (double)iters * ilp * 512.0 / (ms * 1e-3) / 1e12;
+    CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    *tflops = 5.0 * d.n_sm * warps_per_sm * (double)iters * ilp * 512.0 / (ms * 1e-3) / 1e12;
     return 0;
 }

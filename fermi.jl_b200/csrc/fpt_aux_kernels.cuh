@@ -1,6 +1,7 @@
 // Auxiliary sm_100a kernels of the B200 RCCSD(T) path:
 //   K4  prep_*            layout prep (ijk.jl:24-32 replaced by one pass into the Pt/Qt/OV2/T1d layouts)
-//   K3  df_gemm_kernel    density-fitted assembly of the same layouts from BOO/BOV/BVV (DFERI.jl:88-180)
+//   K6  expand_sparse_eri_kernel   sparse AO list -> dense AO tensor
+//   (K3 / K5, the DF assembly and the AO -> MO quarter transforms, are the GEMM of fpt_gemm.cuh)
 //   reduce_partials       fixed-order final sum (ijk.jl:145)
 //   peak_* / dmma_ilp_*   FP64 pipe calibration (roofline denominator)
 #pragma once
@@ -63,7 +64,8 @@ __global__ void prep_pt_hole(Problem P, double* Pt, const double* __restrict__ T
     }
 }
 
-// Qt[(q,r)][g][z][kk8]: kappa<v: T2[r,q,z,kappa]; v<=kappa<v+o: OOOV[kappa-v,q,r,z]; else 0
+// Qt[(q,r)][g][z][kk8]: kappa<v: T2[r,q,z,kappa]; v<=kappa<v+o: OOOV[kappa-v,q,r,z]; else 0.
+// OOOV == nullptr (density-fitted route): the hole part is left zero here and written by the DF assembly GEMM.
 __global__ void prep_qt(Problem P, double* Qt, const double* __restrict__ T2, const double* __restrict__ OOOV)
 {
     const int o = P.o, v = P.v;
@@ -79,7 +81,7 @@ __global__ void prep_qt(Problem P, double* Qt, const double* __restrict__ T2, co
         double val = 0.0;
         if (z < v) {
             if (kappa < v) val = T2[r + (i64)o * (q + (i64)o * (z + (i64)v * kappa))];
-            else if (kappa < v + o) val = OOOV[(kappa - v) + (i64)o * (q + (i64)o * (r + (i64)o * z))];
+            else if (kappa < v + o && OOOV) val = OOOV[(kappa - v) + (i64)o * (q + (i64)o * (r + (i64)o * z))];
         }
         Qt[idx] = val;
     }
@@ -177,128 +179,7 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters, 
 
 }  // namespace fpt
 
-// ---------------------------------------------------------------------------------------------------
-// K3: density-fitted assembly.  C(m,n) = sum_Q A[Q + naux*rowA(m)] * B[Q + naux*rowB(n)] on DMMA.8x8x4, written
-// straight into the device layouts (the o*v^3 tensor never exists on the host -- the reference materialises it in
-// DFERI.jl:156-180).  MODE 0: Pt particle part from BOV,BVV.  MODE 1: Qt hole part (OOOV) from BOO,BOV.
-// MODE 2: OV2 (OVOV) from BOV,BOV.  CTA = 4 warps, 64x64 tile, fragments loaded straight from global (L1-shared).
-// ---------------------------------------------------------------------------------------------------
 namespace fpt {
-
-template <int MODE>
-__device__ __forceinline__ void df_store(const Problem& P, double* out, int m, int n, double val)
-{
-    const int o = P.o, v = P.v;
-    if (MODE == 0) {
-        const int p = m % o, y = m / o, d = n % v, x = n / v;
-        out[pt_row(P, p, y, x) + d] = val;
-    } else if (MODE == 1) {
-        const int l = m % o, q = m / o, r = n % o, z = n / o;
-        const int kappa = v + l;
-        out[qt_row(P, q, r, kappa / KGROUP, z) + (kappa % KGROUP)] = val;
-    } else {
-        const int q = m % o, y = m / o, r = n % o, z = n / o;
-        out[ov2_idx(P, q, r, y, z)] = val;
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(128) df_gemm_kernel(Problem P, double* out, const double* __restrict__ A,
-                                                      const double* __restrict__ B, int M, int N, int naux)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = lane >> 2, kk = lane & 3;
-    const int m0 = blockIdx.x * 64 + (warp >> 1) * 32;
-    const int n0 = blockIdx.y * 64 + (warp & 1) * 32;
-    const double* ap[4];
-    const double* bp[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        int m = m0 + 8 * t + r; if (m >= M) m = M - 1;
-        ap[t] = A + (i64)naux * m;
-        int n = n0 + 8 * t + r; if (n >= N) n = N - 1;
-        int rowb = n;
-        if (MODE == 0) { const int d = n % P.v, x = n / P.v; rowb = x + P.v * d; }
-        bp[t] = B + (i64)naux * rowb;
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int k0 = 0; k0 < naux; k0 += 4) {
-        const int k = k0 + kk;
-        const bool ok = k < naux;
-        double a[4], b[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) { a[t] = ok ? __ldg(ap[t] + k) : 0.0; b[t] = ok ? __ldg(bp[t] + k) : 0.0; }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int m = m0 + 8 * i + r, n = n0 + 8 * j + 2 * kk + e;
-                if (m < M && n < N) df_store<MODE>(P, out, m, n, acc[i][j][e]);
-            }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K5: one quarter of the AO -> MO integral transformation (Chonky.jl:28-114 computes OOOV/OVOV/OVVV with four-index
-// @tensoropt contractions on the CPU).  C[m + ldc*n] = sum_q A[q + Q*m] * B[q + Q*n]: both operands have the contracted AO index
-// fastest and the result has the surviving indices of A fastest, so chaining four calls rotates
-// (mu nu rho sigma) -> (nu rho sigma | i) -> (rho sigma i | x) -> (sigma i x | y) -> (i x y | z): every quarter contracts a
-// contiguous index and the last one lands in the reference's own column-major [i,x,y,z] layout.  Same DMMA.8x8x4 tiling
-// as K3 (64x64 CTA tile, fragments from global).
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) quarter_gemm_kernel(double* __restrict__ C, const double* __restrict__ A,
-                                                           const double* __restrict__ B, i64 M, int N, int Q, i64 ldc)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = lane >> 2, kk = lane & 3;
-    const i64 m0 = (i64)blockIdx.x * 64 + (warp >> 1) * 32;
-    const int n0 = blockIdx.y * 64 + (warp & 1) * 32;
-    const double* ap[4];
-    const double* bp[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        i64 m = m0 + 8 * t + r; if (m >= M) m = M - 1;
-        ap[t] = A + (i64)Q * m;
-        int n = n0 + 8 * t + r; if (n >= N) n = N - 1;
-        bp[t] = B + (i64)Q * n;
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int k0 = 0; k0 < Q; k0 += 4) {
-        const int k = k0 + kk;
-        const bool ok = k < Q;
-        double a[4], b[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) { a[t] = ok ? __ldg(ap[t] + k) : 0.0; b[t] = ok ? __ldg(bp[t] + k) : 0.0; }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const i64 m = m0 + 8 * i + r;
-                const int n = n0 + 8 * j + 2 * kk + e;
-                if (m < M && n < N) C[m + ldc * n] = acc[i][j][e];
-            }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // K6: sparse AO integral list -> dense AO tensor.  The reference's default AO container is a list of the symmetry-unique
@@ -307,13 +188,16 @@ __global__ void __launch_bounds__(128) quarter_gemm_kernel(double* __restrict__ 
 // the first index (Sparse.jl:78-151, 236-313, 316-393).  Here the images are written into a zero-initialised dense tensor
 // (plain stores: images of one entry that coincide carry the same value), which then feeds the K5 chain.
 // ---------------------------------------------------------------------------------------------------
+// An index outside [0, nbf) (e.g. a one-based list) is not stored: the entry is skipped and *bad is raised, which the host turns
+// into an error return.
 template <typename Ti>
 __global__ void expand_sparse_eri_kernel(double* __restrict__ AO, const Ti* __restrict__ idx, const double* __restrict__ vals,
-                                         i64 nint, int nbf)
+                                         i64 nint, int nbf, int* bad)
 {
     const i64 n1 = nbf, n2 = n1 * nbf, n3 = n2 * nbf;
     for (i64 z = (i64)blockIdx.x * blockDim.x + threadIdx.x; z < nint; z += (i64)gridDim.x * blockDim.x) {
         const i64 m = idx[4 * z], n = idx[4 * z + 1], r = idx[4 * z + 2], s = idx[4 * z + 3];
+        if (m < 0 || n < 0 || r < 0 || s < 0 || m >= nbf || n >= nbf || r >= nbf || s >= nbf) { *bad = 1; continue; }
         const double V = vals[z];
         AO[m + n1 * n + n2 * r + n3 * s] = V;
         AO[n + n1 * m + n2 * r + n3 * s] = V;

@@ -1,0 +1,174 @@
+// Host-side state of libfermi_pt_b200.so: error reporting, device buffers, the per-GPU state (`Dev`), the handle, and the NCCL
+// entry points (resolved at run time, only handles that span more than one GPU need them).
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fermi_pt_b200.h"
+#include "fpt_layout.h"
+#include "fpt_stage.h"
+
+namespace fpt {
+
+inline std::string& err_text()
+{
+    static thread_local std::string s;
+    return s;
+}
+inline int fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err_text() = buf;
+    return 1;
+}
+#define CK(call)                                                                                                             \
+    do {                                                                                                                     \
+        cudaError_t e_ = (call);                                                                                             \
+        if (e_ != cudaSuccess) return fpt::fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+// every entry point leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)   // the owning device must be current
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    double* d() const { return (double*)p; }
+};
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    bool ok = false;
+    std::string why;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+inline NcclApi& nccl_api()
+{
+    static NcclApi api;
+    return api;
+}
+inline int nccl_load()
+{
+    static std::once_flag once;
+    NcclApi& g = nccl_api();
+    std::call_once(once, [&g] {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { g.why = std::string("cannot load libnccl.so.2 (") + dlerror() + ")"; return; }
+#define FPT_SYM(field, name)                                                        \
+    g.field = reinterpret_cast<decltype(g.field)>(dlsym(lib, name));                \
+    if (!g.field) { g.why = std::string("libnccl lacks ") + name; return; }
+        FPT_SYM(CommInitAll, "ncclCommInitAll");
+        FPT_SYM(CommInitRank, "ncclCommInitRank");
+        FPT_SYM(GetUniqueId, "ncclGetUniqueId");
+        FPT_SYM(CommDestroy, "ncclCommDestroy");
+        FPT_SYM(GroupStart, "ncclGroupStart");
+        FPT_SYM(GroupEnd, "ncclGroupEnd");
+        FPT_SYM(Broadcast, "ncclBroadcast");
+        FPT_SYM(AllGather, "ncclAllGather");
+        FPT_SYM(AllReduce, "ncclAllReduce");
+        FPT_SYM(GetErrorString, "ncclGetErrorString");
+#undef FPT_SYM
+        g.lib = lib;
+        g.ok = true;
+    });
+    if (!g.ok) return fail("multi-GPU handle: %s", g.why.c_str());
+    return 0;
+}
+#define NCK(call)                                                                                                                        \
+    do {                                                                                                                                 \
+        ncclResult_t r_ = (call);                                                                                                        \
+        if (r_ != ncclSuccess) return fpt::fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, fpt::nccl_api().GetErrorString(r_)); \
+    } while (0)
+
+// ---- one GPU of a handle -----------------------------------------------------------------------------------------------
+constexpr int NTL = 6;   // timeline events: upload begin, last H2D done, operands ready, kernel begin, kernel end, result ready
+struct Dev {
+    int dev = 0;
+    int idx = 0;          // position in fpt_handle::devs
+    int grank = 0;        // rank in the NCCL communicator (= global shard number)
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;   // kernels + collectives
+    cudaStream_t copy = nullptr;     // host -> device DMAs
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;            // around the fused kernel
+    cudaEvent_t ev_copy = nullptr, ev_start = nullptr;   // copy -> stream / stream -> copy hand-offs
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};         // OVVV chunk buffer c&1 has been consumed by its prep kernel
+    cudaEvent_t tl[NTL] = {};
+    ncclComm_t comm = nullptr;
+    // resident operands
+    DevBuf Pt, Qt, OV2, T1d, fo, fv, partials, counter, out, prof, blocktab;
+    // raw inputs (staging)
+    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sBOO, sBOV, sBVV;
+    // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
+    DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
+    Problem prob{};
+    int tab_vp = -1;          // the block table on this device was built for this padded virtual dimension
+    // Pt holds zeros in its padding (x,y >= v, kappa >= v+o) for this shape: a new upload of the same shape may skip the memset
+    int clean_o = -1, clean_v = -1;
+    void* clean_ptr = nullptr;
+    int last_grid = 0;
+    i64 shard_b = 0, shard_e = 0;
+};
+
+}  // namespace fpt
+
+struct fpt_handle {
+    std::vector<fpt::Dev*> devs;   // the GPUs this process drives
+    int world = 1;                 // GPUs in the communicator (== devs.size() unless created with fpt_create_rank)
+    bool rank_mode = false;        // one process per GPU: uploads and computes are collective calls over `world` processes
+    fpt::CopyPool pool;
+    fpt::PinnedRing ring;
+    double* res_pinned = nullptr;  // the 8-byte result lands here
+    // problem (identical on every GPU)
+    int o = 0, v = 0;
+    std::vector<fpt::BlockTabEntry> tab;
+    int tab_vp = -1;
+    std::vector<double> block_cost;
+    fpt::i64 tw_begin = 0, tw_count = 0, nitems = 0;
+    int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
+    int dbg_flags = 0;
+    bool profiling = false, last_profiled = false;
+    int kernel_variant = 1;
+    bool loaded = false;
+    bool pending = false;     // an asynchronous call is in flight (fpt_wait has to collect it)
+    fpt::i64 pend_items = 0;
+    fpt_stats last{};
+    int launches = 0;
+    double h2d = 0.0, stage_host_ms = 0.0;
+    double timeline[8] = {};
+};

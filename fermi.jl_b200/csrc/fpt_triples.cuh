@@ -6,7 +6,7 @@
 //                                                  W and V never go to HBM
 //   accumulation                                   ijk.jl:133,145: per-thread FP64 partial, warp-shuffle, per-CTA partial
 //
-// CTA = 4 consumer warpgroups (16 warps, 120 registers/thread after setmaxnreg) + 1 producer warpgroup (24 registers),
+// CTA = 4 consumer warpgroups (16 warps, 112 registers/thread after setmaxnreg) + 1 producer warpgroup (24 registers),
 // 640 threads, 1 CTA / SM, grid = #SMs.
 //   producer (warp 16, lane 0): pulls items off the global counter, decodes them into a double-buffered control
 //       block (item / block / GEMM descriptors) and streams the Q operand chunks of all GEMMs of the item through a
@@ -29,7 +29,8 @@ constexpr int NCWARPS = 16;                        // consumer warps = 4 warpgro
 constexpr int NCTHREADS = NCWARPS * 32;            // 512
 constexpr int NTHREADS = NCTHREADS + 128;          // + producer warpgroup (only its first lane works)
 // setmaxnreg only redistributes the CTA's launch-time allocation: 640 threads x 96 registers (launch bound) = 61440,
-// so 512*R_consumer + 128*R_producer must not exceed that (otherwise the TRY_ALLOC spins forever).
+// so 512*R_consumer + 128*R_producer must not exceed that (otherwise the TRY_ALLOC spins forever).  LAUNCH_REGS is what ptxas
+// assigns under the launch bound below; build.py checks the built library (cuobjdump -res-usage) and refuses anything else.
 constexpr int LAUNCH_REGS = 96, CONSUMER_REGS = 112, PRODUCER_REGS = 24;
 static_assert(NCTHREADS * CONSUMER_REGS + 128 * PRODUCER_REGS <= NTHREADS * LAUNCH_REGS, "setmaxnreg budget exceeds the CTA pool");
 constexpr int QSTAGES = 3;

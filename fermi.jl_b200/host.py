@@ -145,7 +145,9 @@ class RCCSDpT:
     reference's varargs entry `RCCSDpT(x...)` (:51-63): with no algorithm among the arguments the one selected by
     Options["pt_alg"] is appended; `RCCSDpT(ccsd, moints, B200())` is the boundary method (ijk.jl:20)."""
 
-    def __init__(self, *x, device=None):
+    def __init__(self, *x, device=None, engine=None):
+        """device: GPU ordinal or list of ordinals (one handle per distinct value is kept and reused); engine: an existing
+        `Engine` (e.g. a rank handle of a one-process-per-GPU run, for which this constructor is a collective call)."""
         algs = [a for a in x if isinstance(a, RpTAlgorithm)]
         if not algs:
             x = x + (get_rpt_alg(),)
@@ -160,7 +162,7 @@ class RCCSDpT:
         if tuple(T2.shape) != (o, o, v, v):
             raise FermiException(f"invalid T2 shape {tuple(T2.shape)} for T1 shape {(o, v)}")
         fo, fv = moints["Fii"], moints["Faa"]
-        eng = _engine(device)
+        eng = engine if engine is not None else _engine(device)
         output("Computing energy contribution from occupied orbitals:")
         t0 = time.perf_counter()
         if moints.is_df and "OVVV" not in moints:

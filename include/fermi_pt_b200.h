@@ -19,8 +19,15 @@
  *     BOO [Q,i,j]    (naux,o,o)   moints["BOO"]      DFERI.jl:15-29
  *     BOV [Q,i,a]    (naux,o,v)   moints["BOV"]      DFERI.jl:31-51
  *     BVV [Q,a,b]    (naux,v,v)   moints["BVV"]      DFERI.jl:53-69
- * Pointers may be host memory (pageable or pinned) or device memory of the handle's GPU; they are read-only,
- * caller-owned, and only need to stay valid for the duration of the call.
+ * Pointers may be host memory (pageable or pinned) or device memory; they are read-only, caller-owned, and only need to stay
+ * valid for the duration of the call.
+ *   - pageable host memory (what a Julia ccall or numpy hands over) is copied by a pool of host threads into a ring of pinned
+ *     bounce buffers and sent from there, so it moves at the PCIe rate; with several GPUs every GPU pulls only its own 1/N of
+ *     each array over its own PCIe link and the parts are exchanged with one ncclAllGather over NVLink;
+ *   - device memory must live on the handle's (first) GPU and is consumed in place on the library's own streams: the library
+ *     issues one cudaDeviceSynchronize() on that GPU before the first read, so work queued on ANY stream of the caller
+ *     (PyTorch's or CUDA.jl's current stream) that produced the arrays is complete -- no caller-side synchronisation needed.
+ * Every entry point restores the caller's current CUDA device before it returns.
  *
  * Every function returns 0 on success and a nonzero status on failure; fpt_last_error() then describes it
  * (the Julia glue rethrows it as FermiException, Options.jl:196-199).  There is no CPU fallback: if no
@@ -49,11 +56,23 @@ typedef struct fpt_stats {
 
 /* ngpu = 1: devices[0] = CUDA device ordinal (devices == NULL -> current device).
  * ngpu > 1 (single-process multi-GPU, what a Julia caller uses): devices[0..ngpu) form one NCCL clique (libnccl.so.2 is
- * loaded at run time); every upload prepares the operands on devices[0] and broadcasts them once over NVLink, every
- * compute splits its item range into ngpu contiguous shards and ends with one scalar all-reduce of E(T).
- * Multi-process runs (one process per GPU, torchrun) use ngpu = 1 handles and fpt_compute's item ranges instead. */
+ * loaded at run time).  Every upload is sharded: GPU g copies part g of every large array from the caller's memory over its
+ * own PCIe link, one in-place ncclAllGather per array (per 64 MB chunk of OVVV) completes it on every GPU over NVLink, and
+ * every GPU runs the layout prep itself; every compute splits its item range into ngpu contiguous cost-weighted shards and
+ * ends with one scalar ncclAllReduce of E(T). */
 int fpt_create(int ngpu, const int* devices, fpt_handle** out);
 int fpt_destroy(fpt_handle* h);
+
+/* One process per GPU (torchrun / MPI style launchers): rank 0 calls fpt_nccl_unique_id, the launcher's control plane hands
+ * the 128 bytes to the other ranks, and every rank calls fpt_create_rank(device, rank, world, id, &h)  (ncclCommInitRank).
+ * On such a handle fpt_upload_*, fpt_triples_* and fpt_compute are COLLECTIVE calls: every rank makes the same call with
+ * the same arrays (host arrays: every rank reads only its own 1/world share of them) and item range; the data plane
+ * -- sharded H2D, all-gather, all-reduce -- is the library's own, and every rank receives the full E(T). */
+int fpt_nccl_unique_id(void* id128);
+int fpt_create_rank(int device, int rank, int world, const void* id128, fpt_handle** out);
+/* host threads that copy pageable memory into the pinned ring (default: the process's CPU affinity count, divided by `world`
+ * on rank handles, at most 16; environment override FERMI_PT_B200_THREADS) */
+int fpt_set_host_threads(fpt_handle* h, int n);
 
 /* replaces RCCSDpT(ccsd, moints, ::ijk) for conventional integrals (ijk.jl:20-150): Et = E(T) */
 int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
@@ -65,6 +84,15 @@ int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double
 int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
                    const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
                    fpt_stats* stats);
+
+/* Asynchronous forms (gradient_findif makes 6 N_atoms (T) calls, FiniteDifferences.jl:48-74): the call returns
+ * as soon as the caller's arrays have been consumed -- they may be freed or overwritten, the next CCSD can start on the CPU --
+ * while the GPU is still computing; fpt_wait blocks for E(T).  One call may be in flight per handle. */
+int fpt_triples_conv_async(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                           const double* OOOV, const double* OVOV, const double* fo, const double* fv);
+int fpt_triples_df_async(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
+                         const double* BOV, const double* BVV, const double* fo, const double* fv);
+int fpt_wait(fpt_handle* h, double* Et, fpt_stats* stats);
 
 /* Same, from the AO-basis integrals: replaces the reference's dense AO -> MO contractions for the three blocks the (T)
  * path reads (Chonky.jl:28-48 OOOV, :72-92 OVOV, :94-114 OVVV) with four quarter transformations on the GPU, so the o*v^3
@@ -89,9 +117,11 @@ int fpt_upload_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1,
                          const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
                          const double* fo, const double* fv);
 
-/* Staged form of the calls above (used for sharded multi-GPU runs and kernel-only timing):
- * upload = copy + layout prep, operands stay resident on the GPU; compute = fused kernel over the item range
- * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T). */
+/* Staged form of the calls above (kernel-only timing, partial evaluations):
+ * upload = copy + layout prep, operands stay resident on the GPU(s); compute = fused kernel over the item range
+ * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T).  A handle
+ * over several GPUs (fpt_create with ngpu > 1, or fpt_create_rank) splits the range into one cost-weighted shard per GPU and
+ * all-reduces the scalar. */
 int fpt_upload_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
                     const double* OOOV, const double* OVOV, const double* fo, const double* fv);
 int fpt_upload_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO,
@@ -115,6 +145,12 @@ int fpt_shard_items(fpt_handle* h, int rank, int world, long long* item_begin, l
 /* FP64 pipe calibration for the roofline denominator: variant 0 = DMMA.8x8x4 stream, 1 = DFMA stream.
  * Returns sustained TFLOP/s over `ms_target` milliseconds of back-to-back launches. */
 int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
+/* Stand-alone timing of the DF-assembly / quarter-transform GEMM (fpt_gemm.cuh) on zero operands: C(M x N) = A(M x K).B(N x K)^T,
+ * `reps` launches, sustained TFLOP/s. */
+int fpt_gemm_bench(fpt_handle* h, long long M, int N, int K, int reps, double* tflops);
+/* Milliseconds since the start of the last upload on the first GPU's clock: out8 = {host time spent copying pageable memory
+ * into the pinned ring, last H2D done, operands ready (gathers + prep done), kernel begin, kernel end, result sent, 0, 0}. */
+int fpt_last_timeline(fpt_handle* h, double* out8);
 
 /* Diagnostics (not part of the drop-in path): with profiling on, fpt_compute runs the instrumented kernel variant and
  * fpt_last_profile returns its phase breakdown in SM cycles summed over CTAs (warp 0's view) --
@@ -122,7 +158,7 @@ int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, double* tflops);
  *          pure RMW, wait on the Q ring inside the k-loops, wait for the staged OV2 tiles, barrier before / after the energy stage}
  * for the first warp of consumer group 0 (entries 0-11) and of group 3 (entries 12-23); and a DMMA issue study. */
 int fpt_set_profiling(fpt_handle* h, int on);
-int fpt_set_kernel_variant(fpt_handle* h, int variant);   /* 1 (default): the DMMA warps add their accumulators into the W slots; 2: experimental epilogue-warp kernel (TMEM parking) */
+int fpt_set_kernel_variant(fpt_handle* h, int variant);   /* 1 (default): the DMMA warps update the W slots themselves; 2: experimental epilogue-warp kernel (TMEM parking), only in builds with -DFPT_WITH_VARIANT2 */
 int fpt_set_debug_flags(fpt_handle* h, int flags);   /* 1: skip RMW, 2: skip energy stage -- timing studies only, E(T) is wrong */
 int fpt_last_profile(fpt_handle* h, double* out24);
 int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* tflops);

@@ -14,7 +14,10 @@
  *   pt_oracle_gemm   the ijk2.jl organisation: per triplet six [v^2 x v].[v x v] + six
  *                    [v^2 x o].[o x v] GEMMs, permute-adds, V build, the identical a>=b>=c energy
  *                    loop; OpenMP over triplets (the reference threads over i, ijk.jl:49).  This is
- *                    the timed CPU baseline ("port") and the checker at larger shapes.
+ *                    the timed CPU baseline ("port") and the checker at larger shapes.  The GEMMs run
+ *                    either on the register-blocked kernel below ("own") or, after pt_oracle_use_blas, on a
+ *                    single-threaded cblas_dgemm of an OpenBLAS loaded at run time -- the reference's own
+ *                    set-up (BLAS.set_num_threads(1) inside the threaded triplet loop, ijk.jl:45-46).
  *
  * PARITY PIN: Julia is not available in the build container, so the reference itself cannot be run.
  * The pin is: naive == gemm == numpy transcriptions (oracle/pt_numpy.py) == independent spin-orbital
@@ -25,6 +28,7 @@
  *   T1[i,a] (o,v)  T2[i,j,a,b] (o,o,v,v)  OVVV[i,a,b,c]=(ia|bc) (o,v,v,v)
  *   OOOV[i,j,k,a]=(ij|ka) (o,o,o,v)  OVOV[i,a,j,b]=(ia|jb) (o,v,o,v)  fo (o)  fv (v)
  */
+#include <dlfcn.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -145,8 +149,34 @@ static inline void micro_8x6(i64 M, int K, const double *A, const double *B, int
     }
 }
 
+/* optional external BLAS (column-major cblas_dgemm, 32-bit integers), see pt_oracle_use_blas */
+typedef void (*cblas_dgemm_fn)(int, int, int, int, int, int, double, const double *, int, const double *, int, double, double *, int);
+static cblas_dgemm_fn ext_dgemm = NULL;
+
+/* path == NULL or "": back to the built-in kernel.  Otherwise dlopen `path`, pin it to one thread per caller and route every
+ * GEMM of pt_oracle_gemm through its cblas_dgemm.  Returns 0 on success. */
+int pt_oracle_use_blas(const char *path)
+{
+    ext_dgemm = NULL;
+    if (!path || !path[0]) return 0;
+    void *lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return 1;
+    void (*set_threads)(int) = (void (*)(int))dlsym(lib, "scipy_openblas_set_num_threads");
+    if (!set_threads) set_threads = (void (*)(int))dlsym(lib, "openblas_set_num_threads");
+    cblas_dgemm_fn f = (cblas_dgemm_fn)dlsym(lib, "scipy_cblas_dgemm");
+    if (!f) f = (cblas_dgemm_fn)dlsym(lib, "cblas_dgemm");
+    if (!f) return 2;
+    if (set_threads) set_threads(1);
+    ext_dgemm = f;
+    return 0;
+}
+
 static void dgemm_nn(i64 M, int N, int K, double alpha, const double *A, const double *B, double beta, double *C)
 {
+    if (ext_dgemm) { /* CblasColMajor = 102, CblasNoTrans = 111 */
+        ext_dgemm(102, 111, 111, (int)M, N, K, alpha, A, (int)M, B, K, beta, C, (int)M);
+        return;
+    }
     const i64 MB = 96; /* rows per panel: 96*K*8 B stays in L2 */
     for (i64 m0 = 0; m0 < M; m0 += MB) {
         i64 m1 = m0 + MB < M ? m0 + MB : M;

@@ -100,20 +100,153 @@ def test_interface_mirror(engine):
 
 
 def test_single_process_multi_gpu_handle(built):
-    """ngpu > 1 handle (what the Julia glue uses): NCCL broadcast of the prepared operands + sharded compute + one scalar
-    all-reduce must give the single-GPU answer."""
+    """ngpu > 1 handle (what the Julia glue uses): sharded H2D + ncclAllGather of the raw arrays, prep on every GPU, sharded
+    compute + one scalar all-reduce must give the single-GPU answer -- conventional (arrays above and below the 1 MB sharding
+    threshold, several OVVV chunks), DF (p-sliced assembly + broadcasts), device-resident inputs, and the AO route."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    x = fb.synth.make_inputs(6, 37, naux=10, seed=11)
-    ref = oracle.pt_gemm(*_args(x))
     eng = fb.Engine(list(range(min(n, 8))))
-    e, st = eng.triples_conv(6, 37, *_args(x))
-    assert abs(e - ref) < TOL, (e, ref)
-    e2, _ = eng.triples_df(6, 37, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
-    assert abs(e2 - ref) < TOL, (e2, ref)
+    for o, v, naux, seed in [(6, 37, 10, 11), (9, 70, 40, 12), (3, 130, 24, 13)]:
+        x = fb.synth.make_inputs(o, v, naux=naux, seed=seed)
+        ref = oracle.pt_gemm(*_args(x))
+        e, st = eng.triples_conv(o, v, *_args(x))
+        assert abs(e - ref) < TOL, (o, v, e, ref)
+        e2, _ = eng.triples_df(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+        assert abs(e2 - ref) < TOL, (o, v, e2, ref)
+        dev = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda(0) for a in _args(x)]
+        e3, _ = eng.triples_conv(o, v, *dev)
+        assert abs(e3 - ref) < TOL, (o, v, e3, ref)
     eng.close()
+
+
+def _rank_worker(rank, world, idfile, out):
+    import os, sys, time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    import fermi_jl_b200 as fb
+    if rank == 0:
+        with open(idfile + ".tmp", "wb") as fh:
+            fh.write(fb.nccl_unique_id())
+        os.replace(idfile + ".tmp", idfile)
+    while not os.path.exists(idfile):
+        time.sleep(0.01)
+    eng = fb.Engine(rank, rank=rank, world=world, nccl_id=open(idfile, "rb").read())
+    res = []
+    for o, v, naux, seed in [(6, 37, 10, 11), (9, 70, 40, 12)]:
+        x = fb.synth.make_inputs(o, v, naux=naux, seed=seed)
+        a = (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+        e, _ = eng.triples_conv(o, v, *a)                      # collective: sharded H2D, all-gather, shard, all-reduce
+        e2, _ = eng.triples_df(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+        eng.upload_conv(o, v, *a)
+        e3, _ = eng.compute(0, -1)
+        res.append((e, e2, e3))
+    eng.close()
+    out.put((rank, res))
+
+
+def test_one_process_per_gpu_rank_handles(built):
+    """fpt_create_rank (ncclCommInitRank): two processes, one GPU each; every rank must obtain the full E(T) of the oracle."""
+    import os, tempfile
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    idfile = os.path.join(tempfile.mkdtemp(), "nccl_id")
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, idfile, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for n, (o, v, naux, seed) in enumerate([(6, 37, 10, 11), (9, 70, 40, 12)]):
+        x = fb.synth.make_inputs(o, v, naux=naux, seed=seed)
+        ref = oracle.pt_gemm(*_args(x))
+        for r in range(2):
+            for e in got[r][n]:
+                assert abs(e - ref) < TOL, (r, o, v, e, ref)
+
+
+def test_pageable_pinned_and_async_calls(engine):
+    """Inputs large enough to go through the pinned bounce ring (OVVV 23 MB > the 4 MB slots): pageable numpy arrays, pinned
+    torch tensors and the asynchronous form must agree to the last bit of the item-order noise; the asynchronous call has
+    consumed its inputs when it returns (they are overwritten before fpt_wait)."""
+    import torch
+    o, v = 7, 74
+    x = fb.synth.make_inputs(o, v, naux=20, seed=31)
+    ref = oracle.pt_gemm(*_args(x))
+    e_pg, st = engine.triples_conv(o, v, *_args(x))
+    assert abs(e_pg - ref) < TOL, (e_pg, ref)
+    assert st["h2d_bytes"] == sum(a.size * 8 for a in _args(x))
+    pinned = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in _args(x)]
+    e_pin, _ = engine.triples_conv(o, v, *pinned)
+    assert abs(e_pin - e_pg) < 1e-13
+    for threads in (1, 3):
+        engine.set_host_threads(threads)
+        e_t, _ = engine.triples_conv(o, v, *_args(x))
+        assert abs(e_t - e_pg) < 1e-13
+    scratch = [np.array(a, order="F", copy=True) for a in _args(x)]
+    engine.triples_conv_async(o, v, *scratch)
+    for a in scratch:
+        a[...] = np.nan                       # inputs were consumed
+    with pytest.raises(fb.FermiException):
+        engine.compute(0, -1)                 # one call in flight: collect it first
+    e_as, st = engine.wait()
+    assert abs(e_as - e_pg) < 1e-13 and st["kernel_ms"] > 0
+    engine.triples_df_async(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+    e_df, _ = engine.wait()
+    assert abs(e_df - ref) < TOL
+    with pytest.raises(fb.FermiException):
+        engine.wait()                         # nothing in flight
+    tl = engine.last_timeline()
+    assert 0 < tl["operands_ready_ms"] <= tl["kernel_begin_ms"] <= tl["kernel_end_ms"]
+
+
+def test_current_device_is_restored_and_foreign_device_pointers_are_rejected(engine):
+    import torch
+    x = fb.synth.make_inputs(3, 21, naux=8, seed=5)
+    if torch.cuda.device_count() >= 2:
+        torch.cuda.set_device(1)
+        e, _ = engine.triples_conv(3, 21, *_args(x))          # engine lives on GPU 0
+        assert torch.cuda.current_device() == 1
+        assert abs(e - oracle.pt_gemm(*_args(x))) < TOL
+        other = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda(1) for a in _args(x)]
+        with pytest.raises(fb.FermiException, match="lives on GPU 1"):
+            engine.triples_conv(3, 21, *other)
+        torch.cuda.set_device(0)
+    # inputs produced on a side stream without any caller-side synchronisation: the library orders itself behind them
+    side = torch.cuda.Stream()
+    host = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in _args(x)]
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(20_000_000)
+        dev = [t.to("cuda:0", non_blocking=True) for t in host]
+    e, _ = engine.triples_conv(3, 21, *dev)
+    assert abs(e - oracle.pt_gemm(*_args(x))) < TOL
+
+
+def test_sparse_list_with_out_of_range_index_is_an_error(engine):
+    from oracle import pt_numpy as PN
+    AO, C, T1, T2, fo, fv = fb.synth.make_ao_inputs(9, 3, 0, 0, seed=6)
+    idx, vals = PN.sparse_from_dense(AO, threshold=0.0)
+    Co, Cv = np.asfortranarray(C[:, :3]), np.asfortranarray(C[:, 3:])
+    with pytest.raises(fb.FermiException, match="zero-based"):
+        engine.triples_ao_sparse(9, 3, 6, T1, T2, (idx + 1).astype(np.int16), vals, Co, Cv, fo, fv)   # a one-based list
+    e, _ = engine.triples_ao_sparse(9, 3, 6, T1, T2, idx.astype(np.int16), vals, Co, Cv, fo, fv)
+    assert np.isfinite(e)
+
+
+def test_gemm_kernel_shapes(engine):
+    """K3/K5 GEMM on awkward shapes through the DF route: naux odd (8-byte copies) and even (16-byte copies), M, N not multiples of
+    the 128 x 128 tile, o*v below one tile."""
+    for o, v, naux in [(2, 5, 3), (4, 37, 64), (5, 50, 131), (3, 66, 258)]:
+        x = fb.synth.make_inputs(o, v, naux=naux, seed=naux)
+        ref = oracle.pt_gemm(*_args(x))
+        e, _ = engine.triples_df(o, v, naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+        assert abs(e - ref) < TOL, (o, v, naux, e, ref)
 
 
 @pytest.mark.parametrize("o,v", [(7, 5), (6, 6), (12, 20), (9, 31), (4, 44), (3, 68)])
@@ -187,6 +320,11 @@ def test_kernel_variants_agree(engine, o, v, variant):
     ref = oracle.pt_gemm(*_args(x))
     engine.upload_conv(o, v, *_args(x))
     default = engine.kernel_variant
+    if variant == 2:
+        try:
+            engine.set_kernel_variant(2)
+        except fb.FermiException:
+            pytest.skip("the experimental epilogue-warp kernel is only in builds with -DFPT_WITH_VARIANT2")
     try:
         engine.set_kernel_variant(variant)
         e, _ = engine.compute(0, -1)

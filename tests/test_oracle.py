@@ -137,3 +137,21 @@ def test_sparse_ao_list_transcription():
     OVVV_sparse = PN.ovvv_from_sparse(idx, vals, C, ndocc, dc, dv)
     OVVV, _, _ = PN.mo_blocks_from_ao(AO, C, ndocc, dc, dv)
     assert np.abs(OVVV_sparse - OVVV).max() < 1e-13
+
+
+def test_oracle_blas_backends_agree():
+    """pt_gemm on its own register-blocked kernel and on the single-threaded OpenBLAS bundled with scipy (the arrangement of
+    ijk.jl:45-46) give the same E(T); the timed CPU baseline uses whichever is faster."""
+    import fermi_jl_b200 as fb
+    x = fb.synth.make_inputs(4, 19, naux=8, seed=3)
+    a = (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
+    assert oracle.use_blas("own") == "own"
+    e_own = oracle.pt_gemm(*a)
+    if oracle.use_blas("openblas") != "openblas":
+        pytest.skip("no OpenBLAS in this environment")
+    try:
+        e_ob = oracle.pt_gemm(*a)
+    finally:
+        oracle.use_blas("own")
+    assert abs(e_own - e_ob) < 1e-13
+    assert abs(e_own - oracle.pt_naive(*a)) < 1e-13
