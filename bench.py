@@ -239,6 +239,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"    # NCCL's default prints a version banner on stdout; stdout carries one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier: an NCCL barrier parks a spinning kernel on every waiting GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # The engine.  N = 1: a plain handle.  N > 1: one process per GPU, every process holds a *rank handle* (fpt_create_rank ->
@@ -327,6 +328,7 @@ def main():
     e2e_handle = None
     if world > 1:
         barrier()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 engh = fb.Engine(list(range(world)))
@@ -336,6 +338,7 @@ def main():
                               "what": f"fpt_triples_conv on a single-process handle over {world} GPUs (fpt_create(ngpu={world})), pageable host inputs"}
             except fb.FermiException as ex:
                 e2e_handle = {"error": str(ex)}
+        dist.barrier(group=cpu_group)    # the other ranks wait here on the CPU, their GPUs idle
         barrier()
 
     if rank == 0:

@@ -112,9 +112,8 @@ static int default_host_threads(int share)
 static int handle_finish(fpt_handle* h)
 {
     CK(cudaSetDevice(h->devs[0]->dev));
-    h->pool.start(default_host_threads(h->rank_mode ? h->world : 1));
-    const int nslots = std::max(8, 2 * (int)h->devs.size());
-    CK(h->ring.init(nslots, (int)h->devs.size()));
+    if (const char* nt = getenv("FERMI_PT_B200_NT")) h->pool.nt_stores = atoi(nt) != 0;
+    CK(h->pool.start(default_host_threads(h->rank_mode ? h->world : 1), (int)h->devs.size()));
     CK(cudaHostAlloc((void**)&h->res_pinned, 64, cudaHostAllocPortable));
     return 0;
 }
@@ -128,7 +127,6 @@ extern "C" int fpt_destroy(fpt_handle* h)
         cudaDeviceSynchronize();
     }
     h->pool.stop();
-    h->ring.release();
     if (h->res_pinned) cudaFreeHost(h->res_pinned);
     for (Dev* d : h->devs) dev_destroy(d);
     delete h;
@@ -216,7 +214,12 @@ extern "C" int fpt_set_host_threads(fpt_handle* h, int n)
 {
     if (!h) return fail("fpt_set_host_threads: NULL handle");
     if (n < 1 || n > 64) return fail("fpt_set_host_threads: n=%d out of range (1..64)", n);
-    h->pool.start(n);
+    DeviceGuard guard;
+    for (Dev* d : h->devs) {   // no DMA may still be reading the slots that are about to be freed
+        CK(cudaSetDevice(d->dev));
+        CK(cudaStreamSynchronize(d->copy));
+    }
+    CK(h->pool.start(n, (int)h->devs.size()));
     return 0;
 }
 
@@ -265,14 +268,10 @@ static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, size_t by
         return 0;
     }
     const auto t0 = wall::now();
-    for (size_t off = 0; off < bytes; off += PinnedRing::SLOT_BYTES) {
-        const size_t nb = std::min(PinnedRing::SLOT_BYTES, bytes - off);
-        PinnedRing::Slot* s = nullptr;
-        CK(h->ring.acquire(&s));
-        h->pool.copy(s->p, (const char*)src + off, nb);
-        CK(cudaMemcpyAsync((char*)dst + off, s->p, nb, cudaMemcpyHostToDevice, d.copy));
-        CK(h->ring.sent(s, d.idx, d.copy));
-    }
+    StagePool::Job job;
+    job.dst = (char*)dst; job.src = (const char*)src; job.bytes = bytes;
+    job.dev = d.dev; job.idev = d.idx; job.stream = d.copy;
+    CK(h->pool.transfer(job));
     h->stage_host_ms += ms_since(t0);
     return 0;
 }
@@ -988,13 +987,11 @@ static int upload_ao_sparse_impl(fpt_handle* h, int nbf, int o, int v, const dou
     if (d.aoFlag.ensure(sizeof(int))) return 1;
     CK(cudaMemsetAsync(d.aoDense.p, 0, n4 * sizeof(double), d.stream));
     CK(cudaMemsetAsync(d.aoFlag.p, 0, sizeof(int), d.stream));
-    double h2d_list = 0.0;
     if (nint > 0) {
         CK(cudaEventRecord(d.ev_start, d.stream));
         CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));
         const void* didx = idx;
         const double* dvals = vals;
-        const double before = h->h2d;
         if (classify(idx) != PK_DEVICE) {
             if (d.sIdx.ensure((size_t)nint * 4 * index_bytes)) return 1;
             if (stage_to(h, d, d.sIdx.p, idx, (size_t)nint * 4 * index_bytes, classify(idx))) return 1;
@@ -1005,7 +1002,6 @@ static int upload_ao_sparse_impl(fpt_handle* h, int nbf, int o, int v, const dou
             if (stage_to(h, d, d.sVals.p, vals, (size_t)nint * sizeof(double), classify(vals))) return 1;
             dvals = d.sVals.d();
         }
-        h2d_list = h->h2d - before;
         if (copy_then_stream(d)) return 1;
         const int grid = (int)std::min<long long>((nint + 255) / 256, 148LL * 32);
         if (index_bytes == 2)
@@ -1020,7 +1016,6 @@ static int upload_ao_sparse_impl(fpt_handle* h, int nbf, int o, int v, const dou
     }
     if (upload_ao_impl(h, nbf, o, v, T1, T2, d.aoDense.d(), Co, Cv, fo, fv, sync)) return 1;
     h->launches += 1;
-    (void)h2d_list;
     return 0;
 }
 

@@ -6,7 +6,7 @@
 // on the CPU with @tensoropt) and (K5) the four quarter transformations AO -> MO (Chonky.jl:28-114).  The epilogue writes the
 // result straight into the layout its consumer wants (Pt / Qt / OV2 of the fused kernel, or a column-major matrix).
 //
-// CTA = 16 warps, tile 128 x BN (BN = 128, or 32 for the transforms onto the occupied space), K in chunks of 32.  Operand
+// Persistent CTAs (one per SM) of 16 warps, tile 128 x BN (BN = 128, or 32 for the transforms onto the occupied space), K in chunks of 32.  Operand
 // tiles are staged in shared memory by cp.async (SASS LDGSTS) through a 3-stage ring shared by all warps -- every operand
 // element is fetched from L2 once per CTA -- in rows of 34 doubles (16 bytes of skew per row: the 32-byte fragment loads of
 // a quarter-warp then cover all 32 banks).  A lane's fragment for one 16-wide kappa group is 4 consecutive kappa (one
@@ -38,8 +38,9 @@ constexpr int GEMM_KC = 32;                 // kappa per stage
 constexpr int GEMM_LDS = GEMM_KC + 2;       // doubles per staged row (272 B: 16 B skew mod 128 B)
 constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_THREADS = 512;
+constexpr int GEMM_ROWOFF_RING = 4;         // row-offset tables kept: tiles j-1 .. j+2 of a CTA's tile sequence
 template <int BN>
-constexpr size_t gemm_smem_bytes() { return (size_t)GEMM_STAGES * (GEMM_BM + BN) * GEMM_LDS * sizeof(double) + (GEMM_BM + BN) * sizeof(i64); }
+constexpr size_t gemm_smem_bytes() { return (size_t)GEMM_STAGES * (GEMM_BM + BN) * GEMM_LDS * sizeof(double) + (size_t)GEMM_ROWOFF_RING * (GEMM_BM + BN) * sizeof(i64); }
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* g, int src_bytes)
 {
@@ -84,7 +85,11 @@ __device__ __forceinline__ void gemm_store(const GemmOut& out, i64 m, int n, dou
     }
 }
 
-// MT x NT DMMA tiles per warp; warps laid out WM x WN with WM*MT*8 = 128, WN*NT*8 = BN
+// MT x NT DMMA tiles per warp; warps laid out WM x WN with WM*MT*8 = 128, WN*NT*8 = BN.
+// Persistent: CTA b works on output tiles b, b + grid, ... (m fastest, so concurrently running CTAs share their B rows in L2),
+// and the (tile, kappa-chunk) steps of all its tiles form ONE software pipeline: while a tile's last chunks are multiplied and
+// its result is stored, the first chunks of the next tile are already in flight.  With K = naux or nbf a tile has only 5-16
+// chunks, so a per-tile prologue would idle the tensor pipe for a fifth of the time.
 template <int BN, int EPI, bool ALIGN16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const double* __restrict__ A, RowMap mapA, const double* __restrict__ B, RowMap mapB, i64 M, int N, int K, GemmOut out)
@@ -95,118 +100,142 @@ gemm_tn_kernel(const double* __restrict__ A, RowMap mapA, const double* __restri
     constexpr int ROWS = GEMM_BM + BN;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tiles = reinterpret_cast<double*>(smem_raw);
-    i64* rowoff = reinterpret_cast<i64*>(tiles + (size_t)GEMM_STAGES * ROWS * GEMM_LDS);
+    i64* rowoff = reinterpret_cast<i64*>(tiles + (size_t)GEMM_STAGES * ROWS * GEMM_LDS);   // [GEMM_ROWOFF_RING][ROWS]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const i64 m0 = (i64)blockIdx.x * GEMM_BM;
-    const int n0 = blockIdx.y * BN;
-    // element offsets of the staged rows (A rows first, then B rows); rows past the edge are clamped (results are not stored)
-    for (int r = tid; r < ROWS; r += GEMM_THREADS) {
-        if (r < GEMM_BM) {
-            i64 m = m0 + r; if (m >= M) m = M - 1;
-            rowoff[r] = rowmap_apply(mapA, m) * (i64)K;
-        } else {
-            i64 n = n0 + (r - GEMM_BM); if (n >= N) n = N - 1;
-            rowoff[r] = rowmap_apply(mapB, n) * (i64)K;
-        }
-    }
-    __syncthreads();
-
+    const i64 tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const i64 ntiles = tiles_m * ((N + BN - 1) / BN);
+    const i64 nmine = ntiles > blockIdx.x ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     const int nk = (K + GEMM_KC - 1) / GEMM_KC;
-    auto load_stage = [&](int kt) {
-        double* st = tiles + (size_t)(kt % GEMM_STAGES) * ROWS * GEMM_LDS;
-        const int k0 = kt * GEMM_KC;
-        if (ALIGN16) {
-            constexpr int CPR = GEMM_KC / 2;   // 16-byte chunks per row
-            for (int c = tid; c < ROWS * CPR; c += GEMM_THREADS) {
-                const int r = c / CPR, kc = (c % CPR) * 2;
-                const double* base = (r < GEMM_BM) ? A : B;
-                int nb = (K - (k0 + kc)) * 8;
-                nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                const i64 koff = nb > 0 ? (k0 + kc) : 0;
-                cp_async16(st + r * GEMM_LDS + kc, base + rowoff[r] + koff, nb);
-            }
-        } else {
-            for (int c = tid; c < ROWS * GEMM_KC; c += GEMM_THREADS) {
-                const int r = c / GEMM_KC, kc = c % GEMM_KC;
-                const double* base = (r < GEMM_BM) ? A : B;
-                const bool ok = k0 + kc < K;
-                cp_async8(st + r * GEMM_LDS + kc, base + rowoff[r] + (ok ? k0 + kc : 0), ok ? 8 : 0);
+
+    // element offsets of the staged rows of my j-th tile (A rows first, then B rows); rows past the edge are clamped (their
+    // results are not stored).  Ring of 4: tile j+3's offsets are written when tile j is finished.
+    auto fill_rowoff = [&](i64 j) {
+        const i64 t = blockIdx.x + j * gridDim.x;
+        const i64 m0 = (t % tiles_m) * GEMM_BM;
+        const i64 n0 = (t / tiles_m) * BN;
+        i64* ro = rowoff + (j & (GEMM_ROWOFF_RING - 1)) * ROWS;
+        for (int r = tid; r < ROWS; r += GEMM_THREADS) {
+            if (r < GEMM_BM) {
+                i64 m = m0 + r; if (m >= M) m = M - 1;
+                ro[r] = rowmap_apply(mapA, m) * (i64)K;
+            } else {
+                i64 n = n0 + (r - GEMM_BM); if (n >= N) n = N - 1;
+                ro[r] = rowmap_apply(mapB, n) * (i64)K;
             }
         }
     };
-
-    double acc[MT][NT][2];
+    // the load pipeline runs GEMM_STAGES-1 steps ahead of the multiply pipeline and has its own (tile, chunk, stage) counters
+    i64 lj = 0;
+    int lkt = 0, lstage = 0;
+    auto load_next = [&]() {
+        if (lj < nmine) {
+            const i64* ro = rowoff + (lj & (GEMM_ROWOFF_RING - 1)) * ROWS;
+            double* st = tiles + (size_t)lstage * ROWS * GEMM_LDS;
+            const int k0 = lkt * GEMM_KC;
+            if (ALIGN16) {
+                constexpr int CPR = GEMM_KC / 2;   // 16-byte chunks per row
 #pragma unroll
-    for (int i = 0; i < MT; i++)
-#pragma unroll
-        for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; s++) {
-        if (s < nk) load_stage(s);
+                for (int c = tid; c < ROWS * CPR; c += GEMM_THREADS) {
+                    const int r = c / CPR, kc = (c % CPR) * 2;
+                    const double* base = (r < GEMM_BM) ? A : B;
+                    int nb = (K - (k0 + kc)) * 8;
+                    nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+                    const i64 koff = nb > 0 ? (k0 + kc) : 0;
+                    cp_async16(st + r * GEMM_LDS + kc, base + ro[r] + koff, nb);
+                }
+            } else {
+#pragma unroll 4
+                for (int c = tid; c < ROWS * GEMM_KC; c += GEMM_THREADS) {
+                    const int r = c / GEMM_KC, kc = c % GEMM_KC;
+                    const double* base = (r < GEMM_BM) ? A : B;
+                    const bool ok = k0 + kc < K;
+                    cp_async8(st + r * GEMM_LDS + kc, base + ro[r] + (ok ? k0 + kc : 0), ok ? 8 : 0);
+                }
+            }
+            if (++lkt == nk) { lkt = 0; lj++; }
+            if (++lstage == GEMM_STAGES) lstage = 0;
+        }
         cp_async_commit();
-    }
+    };
+
+    for (i64 j = 0; j < GEMM_ROWOFF_RING - 1 && j < nmine; j++) fill_rowoff(j);
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) load_next();
     const int wm = warp / WN, wn = warp % WN;
     const int r8 = lane >> 2, kk = lane & 3;
-    const int arow = wm * MT * 8 + r8;                  // + 8*i
-    const int brow = GEMM_BM + wn * NT * 8 + r8;        // + 8*j
-    for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<GEMM_STAGES - 2>();
-        __syncthreads();   // stage kt has landed for every thread; stage (kt-1) is no longer read by anyone
-        if (kt + GEMM_STAGES - 1 < nk) load_stage(kt + GEMM_STAGES - 1);
-        cp_async_commit();
-        const double* st = tiles + (size_t)(kt % GEMM_STAGES) * ROWS * GEMM_LDS;
+    const double* afrag = tiles + (wm * MT * 8 + r8) * GEMM_LDS + 4 * kk;                 // + stage, + 8*i rows, + 16*g + 2*hh
+    const double* bfrag = tiles + (GEMM_BM + wn * NT * 8 + r8) * GEMM_LDS + 4 * kk;
+    int cstage = 0;
+    for (i64 j = 0; j < nmine; j++) {
+        double acc[MT][NT][2];
 #pragma unroll
-        for (int g = 0; g < GEMM_KC / 16; g++) {
+        for (int i = 0; i < MT; i++)
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                double2 a[MT], b[NT];
+            for (int jj = 0; jj < NT; jj++) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+        for (int kt = 0; kt < nk; kt++) {
+            cp_async_wait<GEMM_STAGES - 2>();
+            __syncthreads();   // this step has landed for every thread; the stage of the previous step is no longer read by anyone
+            load_next();
+            const int so = cstage * ROWS * GEMM_LDS;
 #pragma unroll
-                for (int i = 0; i < MT; i++)
-                    a[i] = *reinterpret_cast<const double2*>(st + (arow + 8 * i) * GEMM_LDS + 16 * g + 4 * kk + 2 * hh);
+            for (int g = 0; g < GEMM_KC / 16; g++) {
 #pragma unroll
-                for (int j = 0; j < NT; j++)
-                    b[j] = *reinterpret_cast<const double2*>(st + (brow + 8 * j) * GEMM_LDS + 16 * g + 4 * kk + 2 * hh);
+                for (int hh = 0; hh < 2; hh++) {
+                    double2 a[MT], b[NT];
 #pragma unroll
-                for (int i = 0; i < MT; i++)
+                    for (int i = 0; i < MT; i++)
+                        a[i] = *reinterpret_cast<const double2*>(afrag + so + 8 * i * GEMM_LDS + 16 * g + 2 * hh);
 #pragma unroll
-                    for (int j = 0; j < NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+                    for (int jj = 0; jj < NT; jj++)
+                        b[jj] = *reinterpret_cast<const double2*>(bfrag + so + 8 * jj * GEMM_LDS + 16 * g + 2 * hh);
 #pragma unroll
-                for (int i = 0; i < MT; i++)
+                    for (int i = 0; i < MT; i++)
 #pragma unroll
-                    for (int j = 0; j < NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+                        for (int jj = 0; jj < NT; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i].x, b[jj].x);
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+#pragma unroll
+                        for (int jj = 0; jj < NT; jj++) dmma884(acc[i][jj][0], acc[i][jj][1], a[i].y, b[jj].y);
+                }
             }
+            if (++cstage == GEMM_STAGES) cstage = 0;
         }
+        // tile finished: store it (the next tile's first chunks are already in flight)
+        const i64 t = blockIdx.x + j * gridDim.x;
+        const i64 m0 = (t % tiles_m) * GEMM_BM;
+        const int n0 = (int)((t / tiles_m) * BN);
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int jj = 0; jj < NT; jj++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const i64 m = m0 + wm * MT * 8 + 8 * i + r8;
+                    const int n = n0 + wn * NT * 8 + 8 * jj + 2 * kk + e;
+                    if (m < M && n < N) gemm_store<EPI>(out, m, n, acc[i][jj][e]);
+                }
+        // the offsets of tile j+3 replace those of tile j-1; they are first read two barriers from now at the earliest
+        if (j + GEMM_ROWOFF_RING - 1 < nmine) fill_rowoff(j + GEMM_ROWOFF_RING - 1);
     }
     cp_async_wait<0>();
-#pragma unroll
-    for (int i = 0; i < MT; i++)
-#pragma unroll
-        for (int j = 0; j < NT; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const i64 m = m0 + wm * MT * 8 + 8 * i + r8;
-                const int n = n0 + wn * NT * 8 + 8 * j + 2 * kk + e;
-                if (m < M && n < N) gemm_store<EPI>(out, m, n, acc[i][j][e]);
-            }
 }
 
 // host-side launch (stream-ordered); returns the CUDA error of the launch
 template <int EPI>
 inline cudaError_t gemm_tn_launch(cudaStream_t stream, const double* A, RowMap mapA, const double* B, RowMap mapB, i64 M, int N, int K,
-                                  const GemmOut& out)
+                                  const GemmOut& out, int n_sm = 148)
 {
     if (M <= 0 || N <= 0) return cudaSuccess;
     const bool al = (K % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
     const bool narrow = N <= 48;
-    const unsigned gx = (unsigned)((M + GEMM_BM - 1) / GEMM_BM);
+    const i64 tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (narrow ? (N + 31) / 32 : (N + 127) / 128);
+    const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);
     if (narrow) {
-        dim3 grid(gx, (unsigned)((N + 31) / 32));
         if (al) gemm_tn_kernel<32, EPI, true><<<grid, GEMM_THREADS, gemm_smem_bytes<32>(), stream>>>(A, mapA, B, mapB, M, N, K, out);
         else gemm_tn_kernel<32, EPI, false><<<grid, GEMM_THREADS, gemm_smem_bytes<32>(), stream>>>(A, mapA, B, mapB, M, N, K, out);
     } else {
-        dim3 grid(gx, (unsigned)((N + 127) / 128));
         if (al) gemm_tn_kernel<128, EPI, true><<<grid, GEMM_THREADS, gemm_smem_bytes<128>(), stream>>>(A, mapA, B, mapB, M, N, K, out);
         else gemm_tn_kernel<128, EPI, false><<<grid, GEMM_THREADS, gemm_smem_bytes<128>(), stream>>>(A, mapA, B, mapB, M, N, K, out);
     }

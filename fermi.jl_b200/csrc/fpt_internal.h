@@ -151,8 +151,7 @@ struct fpt_handle {
     std::vector<fpt::Dev*> devs;   // the GPUs this process drives
     int world = 1;                 // GPUs in the communicator (== devs.size() unless created with fpt_create_rank)
     bool rank_mode = false;        // one process per GPU: uploads and computes are collective calls over `world` processes
-    fpt::CopyPool pool;
-    fpt::PinnedRing ring;
+    fpt::StagePool pool;           // host threads + pinned bounce slots for pageable inputs
     double* res_pinned = nullptr;  // the 8-byte result lands here
     // problem (identical on every GPU)
     int o = 0, v = 0;

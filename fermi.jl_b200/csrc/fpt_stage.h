@@ -2,31 +2,83 @@
 //
 // A Julia `ccall` (or numpy through ctypes) hands over ordinary pageable arrays.  cudaMemcpyAsync from pageable memory is
 // staged by the driver on one thread (~11 GB/s measured on the B200 boxes, profiles/r01_ao_route_nbf144.json), five times below
-// the PCIe rate.  Here the copy into pinned memory is done by a small pool of host threads, piece by piece, into a ring of
-// pinned slots; every filled slot is sent with its own cudaMemcpyAsync, so the host copy of piece n+1 overlaps the DMA of
-// piece n and -- with several GPUs in one process -- the DMAs of different GPUs run concurrently on their own PCIe links.
+// the PCIe rate.  Here a pool of host threads does it: a transfer is cut into pieces of 2 MB, thread t takes pieces
+// t, t + T, ...; for each it copies the piece into one of its own two pinned slots (non-temporal stores: the data is read next by
+// the DMA engine, not by the CPU) and enqueues the slot's cudaMemcpyAsync itself.  No barrier per piece -- the threads only meet
+// once per transfer -- and the copy of piece n+1 overlaps the DMA of piece n.  With several GPUs in one process the transfers to
+// different GPUs are issued back to back, so their DMAs run concurrently on their own PCIe links.
 #pragma once
 #include <cuda_runtime.h>
+#include <immintrin.h>
+#include <atomic>
 #include <condition_variable>
+#include <cstdint>
 #include <cstring>
-#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 namespace fpt {
 
-class CopyPool {
+// memcpy with non-temporal stores (dst 32-byte aligned); falls back to memcpy on CPUs without AVX2
+__attribute__((target("avx2"))) inline void copy_stream_avx2(void* dst, const void* src, size_t bytes)
+{
+    char* d = (char*)dst;
+    const char* s = (const char*)src;
+    size_t n = bytes / 128;
+    for (size_t i = 0; i < n; i++) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(s)), b = _mm256_loadu_si256((const __m256i*)(s + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i*)(s + 64)), e = _mm256_loadu_si256((const __m256i*)(s + 96));
+        _mm256_stream_si256((__m256i*)(d), a);
+        _mm256_stream_si256((__m256i*)(d + 32), b);
+        _mm256_stream_si256((__m256i*)(d + 64), c);
+        _mm256_stream_si256((__m256i*)(d + 96), e);
+        s += 128;
+        d += 128;
+    }
+    if (bytes % 128) memcpy(d, s, bytes % 128);
+    _mm_sfence();
+}
+inline void copy_to_pinned(void* dst, const void* src, size_t bytes, bool nt)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (nt && avx2 && ((uintptr_t)dst % 32) == 0) copy_stream_avx2(dst, src, bytes);
+    else memcpy(dst, src, bytes);
+}
+
+class StagePool {
 public:
-    ~CopyPool() { stop(); }
+    static constexpr size_t PIECE = (size_t)2 << 20;
+    static constexpr int SLOTS_PER_THREAD = 2;
+    struct Job {
+        char* dst = nullptr;          // device
+        const char* src = nullptr;    // pageable host
+        size_t bytes = 0;
+        int dev = 0;                  // CUDA ordinal
+        int idev = 0;                 // index of the GPU inside the handle (event bank)
+        cudaStream_t stream = nullptr;
+    };
+    ~StagePool() { stop(); }
     int size() const { return nthreads_; }
-    // n = total number of threads taking part in a copy, the caller included (n - 1 workers are spawned)
-    void start(int n)
+    bool nt_stores = true;
+
+    // n = total number of threads taking part in a transfer, the caller included; ndev = GPUs of the handle
+    cudaError_t start(int n, int ndev)
     {
         stop();
         nthreads_ = n < 1 ? 1 : n;
+        ndev_ = ndev;
+        slots_.assign((size_t)nthreads_ * SLOTS_PER_THREAD, Slot{});
+        for (auto& s : slots_) {
+            s.ev.assign(ndev, nullptr);
+            cudaError_t e = cudaHostAlloc((void**)&s.p, PIECE, cudaHostAllocPortable);
+            if (e != cudaSuccess) return e;
+        }
+        next_.assign(nthreads_, 0);
         quit_ = false;
-        for (int t = 1; t < nthreads_; t++) workers_.emplace_back([this] { run(); });
+        gen_ = 0;
+        for (int t = 1; t < nthreads_; t++) workers_.emplace_back([this, t] { worker(t); });
+        return cudaSuccess;
     }
     void stop()
     {
@@ -37,116 +89,92 @@ public:
         cv_.notify_all();
         for (auto& t : workers_) t.join();
         workers_.clear();
+        for (auto& s : slots_) {
+            for (cudaEvent_t e : s.ev)
+                if (e) cudaEventDestroy(e);
+            if (s.p) cudaFreeHost(s.p);
+        }
+        slots_.clear();
         nthreads_ = 1;
     }
-    // memcpy split over the pool; returns when every byte is in place
-    void copy(void* dst, const void* src, size_t bytes)
+    // enqueue the whole transfer (returns when every piece has been copied out of `src` and its DMA is enqueued)
+    cudaError_t transfer(const Job& job)
     {
-        const size_t min_slice = (size_t)256 << 10;
-        int parts = (int)((bytes + min_slice - 1) / min_slice);
-        if (parts > nthreads_) parts = nthreads_;
-        if (parts <= 1) { memcpy(dst, src, bytes); return; }
-        size_t slice = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
-        {
+        const size_t np = (job.bytes + PIECE - 1) / PIECE;
+        const int active = (int)(np < (size_t)nthreads_ ? np : (size_t)nthreads_);
+        err_.store((int)cudaSuccess);
+        if (active > 1) {
             std::lock_guard<std::mutex> lk(m_);
-            for (int p = 1; p < parts; p++) {
-                const size_t b = (size_t)p * slice;
-                if (b >= bytes) break;
-                const size_t n = bytes - b < slice ? bytes - b : slice;
-                q_.push_back(Task{(char*)dst + b, (const char*)src + b, n});
-                pending_++;
-            }
+            job_ = job;
+            active_ = active;
+            pending_ = active - 1;
+            gen_++;
+        } else {
+            job_ = job;
+            active_ = 1;
         }
-        cv_.notify_all();
-        memcpy(dst, src, slice < bytes ? slice : bytes);
-        std::unique_lock<std::mutex> lk(m_);
-        // help with whatever is still queued, then wait for the stragglers
-        while (!q_.empty()) {
-            Task t = q_.front();
-            q_.pop_front();
-            lk.unlock();
-            memcpy(t.dst, t.src, t.n);
-            lk.lock();
-            pending_--;
+        if (active > 1) cv_.notify_all();
+        work(0);
+        if (active > 1) {
+            std::unique_lock<std::mutex> lk(m_);
+            done_.wait(lk, [this] { return pending_ == 0; });
         }
-        done_.wait(lk, [this] { return pending_ == 0; });
+        return (cudaError_t)err_.load();
     }
 
 private:
-    struct Task { char* dst; const char* src; size_t n; };
-    void run()
+    struct Slot { char* p = nullptr; std::vector<cudaEvent_t> ev; int busy = -1; };
+    void note(cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; err_.compare_exchange_strong(ok, (int)e); } }
+    void work(int t)
     {
+        const Job job = job_;
+        const int T = active_;
+        if (t >= T) return;
+        if (cudaSetDevice(job.dev) != cudaSuccess) { note(cudaGetLastError()); return; }
+        const size_t np = (job.bytes + PIECE - 1) / PIECE;
+        for (size_t p = t; p < np; p += T) {
+            Slot& s = slots_[(size_t)t * SLOTS_PER_THREAD + next_[t]];
+            next_[t] = (next_[t] + 1) % SLOTS_PER_THREAD;
+            if (s.busy >= 0) {   // the DMA that last read this slot must have finished
+                note(cudaEventSynchronize(s.ev[s.busy]));
+                s.busy = -1;
+            }
+            const size_t off = p * PIECE, nb = job.bytes - off < PIECE ? job.bytes - off : PIECE;
+            copy_to_pinned(s.p, job.src + off, nb, nt_stores);
+            note(cudaMemcpyAsync(job.dst + off, s.p, nb, cudaMemcpyHostToDevice, job.stream));
+            if (!s.ev[job.idev]) note(cudaEventCreateWithFlags(&s.ev[job.idev], cudaEventDisableTiming));
+            if (s.ev[job.idev]) {
+                note(cudaEventRecord(s.ev[job.idev], job.stream));
+                s.busy = job.idev;
+            }
+        }
+    }
+    void worker(int t)
+    {
+        unsigned long long seen = 0;
         std::unique_lock<std::mutex> lk(m_);
         for (;;) {
-            cv_.wait(lk, [this] { return quit_ || !q_.empty(); });
+            cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
             if (quit_) return;
-            Task t = q_.front();
-            q_.pop_front();
+            seen = gen_;
+            if (t >= active_) continue;
             lk.unlock();
-            memcpy(t.dst, t.src, t.n);
+            work(t);
             lk.lock();
             if (--pending_ == 0) done_.notify_all();
         }
     }
     std::vector<std::thread> workers_;
-    std::deque<Task> q_;
+    std::vector<Slot> slots_;
+    std::vector<int> next_;
     std::mutex m_;
     std::condition_variable cv_, done_;
-    int pending_ = 0;
-    int nthreads_ = 1;
+    std::atomic<int> err_{0};
+    Job job_;
+    unsigned long long gen_ = 0;
+    int active_ = 1, pending_ = 0;
+    int nthreads_ = 1, ndev_ = 1;
     bool quit_ = false;
-};
-
-// Ring of pinned bounce slots shared by the GPUs of one handle.  A slot is reusable once the DMA that read it has finished
-// (an event recorded on the copy stream of the GPU it went to; events are tied to a device, so a slot keeps one per GPU).
-struct PinnedRing {
-    static constexpr size_t SLOT_BYTES = (size_t)4 << 20;
-    struct Slot { char* p = nullptr; std::vector<cudaEvent_t> ev; int busy = -1; };
-    std::vector<Slot> slots;
-    size_t next = 0;
-    cudaError_t init(int nslots, int ndev)
-    {
-        slots.resize(nslots);
-        for (auto& s : slots) {
-            s.ev.assign(ndev, nullptr);
-            cudaError_t e = cudaHostAlloc((void**)&s.p, SLOT_BYTES, cudaHostAllocPortable);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    }
-    void release()
-    {
-        for (auto& s : slots) {
-            for (cudaEvent_t e : s.ev)
-                if (e) cudaEventDestroy(e);
-            if (s.p) cudaFreeHost(s.p);
-        }
-        slots.clear();
-    }
-    // next slot, free to be overwritten by the host
-    cudaError_t acquire(Slot** out)
-    {
-        Slot& s = slots[next];
-        next = (next + 1) % slots.size();
-        if (s.busy >= 0) {
-            cudaError_t e = cudaEventSynchronize(s.ev[s.busy]);
-            if (e != cudaSuccess) return e;
-            s.busy = -1;
-        }
-        *out = &s;
-        return cudaSuccess;
-    }
-    // the slot's content is being read by a DMA enqueued on `stream` of local GPU `idev` (the current device)
-    cudaError_t sent(Slot* s, int idev, cudaStream_t stream)
-    {
-        if (!s->ev[idev]) {
-            cudaError_t e = cudaEventCreateWithFlags(&s->ev[idev], cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
-        }
-        cudaError_t e = cudaEventRecord(s->ev[idev], stream);
-        if (e == cudaSuccess) s->busy = idev;
-        return e;
-    }
 };
 
 }  // namespace fpt

@@ -12,8 +12,8 @@ x = fb.synth.make_inputs(o, v, naux=64)
 names = ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv")
 page = [np.asfortranarray(getattr(x, k)) for k in names]
 pinned = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in page]
-eng = fb.Engine(0)
 res = {"o": o, "v": v, "h2d_MB": sum(a.size * 8 for a in page) / 1e6, "cpus": len(os.sched_getaffinity(0)), "runs": []}
+eng = None
 
 
 def run(label, arrs, threads):
@@ -29,9 +29,14 @@ def run(label, arrs, threads):
     print(json.dumps(best), flush=True)
 
 
-for th in (1, 2, 4, 8, 16):
-    run("pageable", page, th)
-run("pinned", pinned, 1)
+for nt in ("0", "1"):       # bounce copies with ordinary / non-temporal stores (FERMI_PT_B200_NT, read when the handle is created)
+    os.environ["FERMI_PT_B200_NT"] = nt
+    if eng is not None:
+        eng.close()
+    eng = fb.Engine(0)
+    for th in (1, 2, 4, 8, 16):
+        run("pageable nt=" + nt, page, th)
+run("pinned", pinned, 16)
 # DF route at the benzene shape
 xo = fb.synth.make_inputs(15, 93, naux=420)
 for rep in range(3):
