@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "c1": ("c1_h2o_dz", 5, 19, 32),
     "c2": ("c2_h2o_tz", 5, 53, 48),
-    "c3": ("c3_benzene_dz", 15, 93, 64),
+    "c3": ("c3_benzene_dz_df", 15, 93, 420),
     "c4": ("c4_h2o6_dz", 24, 114, 64),
     "c5": ("c5_synth_o40_v400", 40, 400, 64),
 }
@@ -160,7 +160,12 @@ def cpu_reference_sample(x, o, v, budget_s=15.0):
             "triplet_range": (tb, te), "blas": best, "other": other}
 
 
-def run_reference(args, name, o, v, naux):
+def workload_text(name, o, v, naux, route):
+    integrals = "conventional integrals" if route == "conv" else f"density-fitted integrals, naux={naux}, B factors handed over, (ia|bd) etc. assembled on the GPU"
+    return f"{name} (o={o}, v={v}, {integrals}, synthetic symmetric inputs, seed 20240517)"
+
+
+def run_reference(args, name, o, v, naux, route):
     import fermi_jl_b200 as fb
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,8 +183,7 @@ def run_reference(args, name, o, v, naux):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
-                       "o": o, "v": v},
+            "config": {"workload": workload_text(name, o, v, naux, route), "o": o, "v": v, "route": route},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "blas": s["blas"], "other_blas": s["other"], "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU restatement of Fermi.jl ijk2.jl (oracle/pt_oracle.c: OpenMP over triplets, single-threaded dgemm per contraction "
@@ -218,12 +222,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--route", default=None, choices=["conv", "df"], help="conventional MO integrals or density-fitted B factors (default: df for c3, conv otherwise)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     name, o, v, naux = parse_workload(args.workload)
+    route = args.route or ("df" if args.workload == "c3" else "conv")
     if args.impl == "reference":
-        return run_reference(args, name, o, v, naux)
+        return run_reference(args, name, o, v, naux, route)
 
     import torch
     import fermi_jl_b200 as fb
@@ -254,7 +260,7 @@ def main():
 
     # ---- synthetic inputs (same seed on every rank): ordinary pageable numpy arrays, column-major like the reference's ----
     x = fb.synth.make_inputs(o, v, naux=naux)
-    names = ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv")
+    names = ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv") if route == "conv" else ("T1", "T2", "BOO", "BOV", "BVV", "fo", "fv")
     harr = {k: np.asfortranarray(getattr(x, k), dtype=np.float64) for k in names}
     h2d_bytes = sum(a.size * 8 for a in harr.values())
 
@@ -272,7 +278,10 @@ def main():
         return float(t.item())
 
     # ---- leg 1: operands resident in HBM (collective at N > 1: every rank computes its shard, one scalar all-reduce) ----
-    eng.upload_conv(o, v, *[harr[k] for k in names])
+    if route == "conv":
+        eng.upload_conv(o, v, *[harr[k] for k in names])
+    else:
+        eng.upload_df(o, v, naux, *[harr[k] for k in names])
     n_items = eng.num_items()
     ntrip = n_triplets(o)
     flops = algorithmic_flops(o, v, ntrip)
@@ -297,7 +306,10 @@ def main():
 
     # ---- leg 2: end to end through the public API, from pageable host arrays (what a Julia ccall passes) ----
     ccsd = fb.RCCSD(0.0, 0.0, 0.0, harr["T1"], harr["T2"])
-    moints = fb.IntegralHelper({"OVVV": harr["OVVV"], "OOOV": harr["OOOV"], "OVOV": harr["OVOV"], "Fii": harr["fo"], "Faa": harr["fv"]})
+    if route == "conv":
+        moints = fb.IntegralHelper({"OVVV": harr["OVVV"], "OOOV": harr["OOOV"], "OVOV": harr["OVOV"], "Fii": harr["fo"], "Faa": harr["fv"]})
+    else:   # a DF helper holds only the B factors (DFERI.jl:15-69); the 4-index blocks are assembled on the GPU
+        moints = fb.IntegralHelper({"BOO": harr["BOO"], "BOV": harr["BOV"], "BVV": harr["BVV"], "Fii": harr["fo"], "Faa": harr["fv"]}, eri_type="RIFIT")
 
     def e2e_step(engine):
         return fb.RCCSDpT(ccsd, moints, fb.B200(), engine=engine).correction
@@ -367,8 +379,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"{name} (o={o}, v={v}, conventional integrals, synthetic symmetric inputs, seed 20240517)",
-                           "o": o, "v": v, "triplets": ntrip, "work_items": n_items,
+                "config": {"workload": workload_text(name, o, v, naux, route),
+                           "o": o, "v": v, "triplets": ntrip, "work_items": n_items, "route": route,
                            "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} GPU(s)",
                            "e2e_inputs": "pageable host arrays; sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)",
                            "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 15) // 16 * 16) * 8 / 1e6)},
