@@ -1,6 +1,6 @@
 """Synthetic o=40 / v=400 (T) (BASELINE config 5) on 1..8 GPUs.
 
-    python tools/run_c5.py [--o 40 --v 400] [--steps 1] [--host] [--check 402] [--tag name]
+    python tools/run_c5.py [--shape 40x400] [--steps 1] [--host] [--check 402] [--tag name]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/run_c5.py ...        (N > 1)
 
 One process per GPU with rank handles (fpt_create_rank): torch.distributed only carries the NCCL id and the barriers.
@@ -20,14 +20,14 @@ import torch
 import fermi_jl_b200 as fb
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--o", type=int, default=40)
-ap.add_argument("--v", type=int, default=400)
+ap.add_argument("--shape", default="40x400", help="occupied x virtual (one option: torchrun's own parser claims short prefixes such as --v)")
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--host", action="store_true")
 ap.add_argument("--check", type=int, default=0)
 ap.add_argument("--tag", default=None)
 args = ap.parse_args()
-o, v, naux = args.o, args.v, 64
+o, v = (int(t) for t in args.shape.split("x"))
+naux = 64
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
