@@ -113,6 +113,10 @@ static int handle_finish(fpt_handle* h)
 {
     CK(cudaSetDevice(h->devs[0]->dev));
     if (const char* nt = getenv("FERMI_PT_B200_NT")) h->pool.nt_stores = atoi(nt) != 0;
+    if (const char* kb = getenv("FERMI_PT_B200_PIECE_KB")) {
+        const long n = atol(kb);
+        if (n >= 64 && n <= 65536) h->pool.PIECE = (size_t)n << 10;
+    }
     CK(h->pool.start(default_host_threads(h->rank_mode ? h->world : 1), (int)h->devs.size()));
     CK(cudaHostAlloc((void**)&h->res_pinned, 64, cudaHostAllocPortable));
     return 0;

@@ -48,7 +48,7 @@ inline void copy_to_pinned(void* dst, const void* src, size_t bytes, bool nt)
 
 class StagePool {
 public:
-    static constexpr size_t PIECE = (size_t)2 << 20;
+    size_t PIECE = (size_t)2 << 20;   // bytes per piece = per pinned slot (set before start())
     static constexpr int SLOTS_PER_THREAD = 2;
     struct Job {
         char* dst = nullptr;          // device
