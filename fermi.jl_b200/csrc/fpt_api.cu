@@ -35,11 +35,11 @@ static void dev_destroy(Dev* d)
     cudaSetDevice(d->dev);
     if (d->comm) nccl_api().CommDestroy(d->comm);
     DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhaseB, &d->sBOO, &d->sBOV, &d->sBVV,
                       &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
                       &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
     for (DevBuf* b : bufs) b->release();
-    cudaEvent_t evs[] = {d->ev0, d->ev1, d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
+    cudaEvent_t evs[] = {d->ev0, d->ev1, d->ev0b, d->ev1b, d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d->tl)
@@ -61,6 +61,8 @@ static int dev_init(Dev* d)
     CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
     CK(cudaEventCreate(&d->ev0));
     CK(cudaEventCreate(&d->ev1));
+    CK(cudaEventCreate(&d->ev0b));
+    CK(cudaEventCreate(&d->ev1b));
     CK(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->ev_free[0], cudaEventDisableTiming));
@@ -262,18 +264,24 @@ static int admit_device_inputs(fpt_handle* h, const char* who, std::initializer_
 
 // ---- staging ---------------------------------------------------------------------------------------------------------------
 // enqueue the copy of `bytes` from host `src` to `dst` on GPU d (its copy stream)
-static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, size_t bytes, PtrKind kind)
+// (row_bytes != 0: the source is bytes / row_bytes rows of row_bytes, src_pitch bytes apart; they arrive contiguously)
+static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, size_t bytes, PtrKind kind, size_t row_bytes = 0, size_t src_pitch = 0)
 {
     if (bytes == 0) return 0;
     CK(cudaSetDevice(d.dev));
     h->h2d += (double)bytes;
-    if (kind == PK_PINNED || bytes <= ((size_t)64 << 10)) {
+    if (row_bytes && kind == PK_PINNED) {   // the DMA engine gathers the rows itself
+        CK(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, bytes / row_bytes, cudaMemcpyHostToDevice, d.copy));
+        return 0;
+    }
+    if (!row_bytes && (kind == PK_PINNED || bytes <= ((size_t)64 << 10))) {
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.copy));
         return 0;
     }
     const auto t0 = wall::now();
     StagePool::Job job;
     job.dst = (char*)dst; job.src = (const char*)src; job.bytes = bytes;
+    job.row_bytes = row_bytes; job.src_pitch = src_pitch;
     job.dev = d.dev; job.idev = d.idx; job.stream = d.copy;
     CK(h->pool.transfer(job));
     h->stage_host_ms += ms_since(t0);
@@ -297,13 +305,16 @@ constexpr size_t SHARD_MIN_BYTES = (size_t)1 << 20;
 //    over NVLink completes the array everywhere (in rank mode every process passes the same array and pulls its own part);
 //  * host memory otherwise: every GPU of this process pulls the whole array;
 //  * device memory (on devs[0]): used in place; the other GPUs of a single-process handle receive it by ncclBroadcast.
+//  * row_len != 0 (host memory only): the source is n / row_len rows of row_len doubles, `pitch` doubles apart -- a sub-range of the
+//    fastest index of a column-major array; the rows arrive packed, and the parts of a sharded transfer are whole rows.
 template <class BufOf>
-static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, std::vector<const double*>& out)
+static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, std::vector<const double*>& out, size_t row_len = 0, size_t pitch = 0)
 {
     const int L = (int)h->devs.size(), W = h->world;
     out.assign(L, nullptr);
     const PtrKind kind = classify(src);
     if (kind == PK_DEVICE) {
+        if (row_len) return fail("internal: row views of device-resident arrays are not supported");
         out[0] = src;
         if (L > 1) {
             for (int i = 1; i < L; i++) {
@@ -328,19 +339,24 @@ static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, s
             CK(cudaSetDevice(d.dev));
             if (bufof(d).ensure(n * sizeof(double))) return 1;
             out[i] = bufof(d).d();
-            if (stage_to(h, d, bufof(d).p, src, n * sizeof(double), kind)) return 1;
+            if (stage_to(h, d, bufof(d).p, src, n * sizeof(double), kind, row_len * sizeof(double), pitch * sizeof(double))) return 1;
             if (copy_then_stream(d)) return 1;
         }
         return 0;
     }
-    const size_t part = ((n + W - 1) / W + 511) & ~(size_t)511;
+    size_t part = ((n + W - 1) / W + 511) & ~(size_t)511;
+    if (row_len) {   // whole rows per part
+        const size_t rows = n / row_len;
+        part = (((rows + W - 1) / W + 63) & ~(size_t)63) * row_len;
+    }
     for (int i = 0; i < L; i++) {
         Dev& d = *h->devs[i];
         CK(cudaSetDevice(d.dev));
         if (bufof(d).ensure((size_t)W * part * sizeof(double))) return 1;
         out[i] = bufof(d).d();
         const size_t b = std::min(n, (size_t)d.grank * part), e = std::min(n, (size_t)(d.grank + 1) * part);
-        if (stage_to(h, d, bufof(d).d() + b, src + b, (e - b) * sizeof(double), kind)) return 1;
+        const double* from = row_len ? src + (b / row_len) * pitch : src + b;
+        if (stage_to(h, d, bufof(d).d() + b, from, (e - b) * sizeof(double), kind, row_len * sizeof(double), pitch * sizeof(double))) return 1;
         if (copy_then_stream(d)) return 1;
     }
     NCK(nccl_api().GroupStart());
@@ -485,12 +501,61 @@ static int upload_common(fpt_handle* h, const double* T1, const double* T2, cons
     return 0;
 }
 
-static int upload_conv_impl(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
-                            const double* OOOV, const double* OVOV, const double* fo, const double* fv, bool sync)
+// OVVV[p0 : p0+np, :, :, :] -> Pt particle part on every GPU.
+//  * chunked: in chunks over the slowest index d; chunk c is staged (and gathered) into buffer c & 1 while the prep kernel of chunk
+//    c-1 runs out of the other one;
+//  * !chunked: one transfer of the whole sub-block into its own buffer (second phase of a split call, see triples_conv: nothing on
+//    the compute stream can run before the first phase's kernel has finished, so the buffer cannot be recycled anyway).
+// A proper sub-range of p is a row view of the host array (rows of np doubles, o apart) and arrives packed.
+static int upload_ovvv(fpt_handle* h, const double* OVVV, int p0, int np, bool chunked)
+{
+    const int o = h->o, v = h->v, L = (int)h->devs.size();
+    const size_t slab = (size_t)o * v * v;            // doubles per d in the caller's array
+    const size_t cslab = (size_t)np * v * v;          // doubles per d as they arrive
+    const bool whole = (p0 == 0 && np == o);
+    const bool on_dev = classify(OVVV) == PK_DEVICE;
+    std::vector<const double*> dChunk;
+    int dchunk = v;
+    if (chunked && (!on_dev || L > 1)) {
+        const size_t budget = (size_t)64 << 20;
+        dchunk = (int)std::max<size_t>(1, budget / (cslab * sizeof(double)));
+        if (dchunk > v) dchunk = v;
+    }
+    int c = 0;
+    for (int d0 = 0; d0 < v; d0 += dchunk, c++) {
+        const int dn = std::min(dchunk, v - d0);
+        const int bsel = c & 1;
+        if (chunked && c >= 2)
+            for (Dev* dp : h->devs) {   // the buffer's previous content has been consumed
+                CK(cudaSetDevice(dp->dev));
+                CK(cudaStreamWaitEvent(dp->copy, dp->ev_free[bsel], 0));
+            }
+        auto buf = [bsel, chunked](Dev& d) -> DevBuf& { return chunked ? d.sChunk[bsel] : d.sPhaseB; };
+        if (whole) {
+            if (distribute(h, buf, OVVV + (size_t)d0 * slab, (size_t)dn * slab, dChunk)) return 1;
+        } else {
+            if (distribute(h, buf, OVVV + (size_t)d0 * slab + p0, (size_t)dn * cslab, dChunk, (size_t)np, (size_t)o)) return 1;
+        }
+        for (int i = 0; i < L; i++) {
+            Dev& d = *h->devs[i];
+            CK(cudaSetDevice(d.dev));
+            dim3 grid((unsigned)(((size_t)np * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
+            prep_pt_particle<<<grid, dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], d0, dn, p0, np);
+            CK(cudaGetLastError());
+            if (chunked) CK(cudaEventRecord(d.ev_free[bsel], d.stream));
+        }
+        h->launches += 1;
+    }
+    return 0;
+}
+
+// everything of a conventional upload except OVVV
+static int upload_conv_small(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OOOV, const double* OVOV,
+                             const double* fo, const double* fv)
 {
     if (setup_problem(h, o, v)) return 1;
-    const int L = (int)h->devs.size(), W = h->world;
-    std::vector<const double*> dT2, dOOOV, dOVOV, dChunk;
+    const int L = (int)h->devs.size();
+    std::vector<const double*> dT2, dOOOV, dOVOV;
     if (upload_common(h, T1, T2, fo, fv, dT2)) return 1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOOOV; }, OOOV, (size_t)o * o * o * v, dOOOV)) return 1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOVOV; }, OVOV, (size_t)o * v * o * v, dOVOV)) return 1;
@@ -503,37 +568,14 @@ static int upload_conv_impl(fpt_handle* h, int o, int v, const double* T1, const
         CK(cudaGetLastError());
     }
     h->launches += 2;
-    // OVVV -> Pt particle part, in chunks over the slowest index d: chunk c is staged (and gathered) into buffer c & 1 while the
-    // prep kernel of chunk c-1 runs out of the other one
-    const size_t slab = (size_t)o * v * v;   // doubles per d
-    const bool on_dev = classify(OVVV) == PK_DEVICE;
-    int dchunk = v;
-    if (!on_dev || L > 1) {
-        const size_t budget = (size_t)64 << 20;
-        dchunk = (int)std::max<size_t>(1, budget / (slab * sizeof(double)));
-        if (dchunk > v) dchunk = v;
-    }
-    int c = 0;
-    for (int d0 = 0; d0 < v; d0 += dchunk, c++) {
-        const int dn = std::min(dchunk, v - d0);
-        const int bsel = c & 1;
-        if (c >= 2)
-            for (Dev* dp : h->devs) {   // the buffer's previous content has been consumed
-                CK(cudaSetDevice(dp->dev));
-                CK(cudaStreamWaitEvent(dp->copy, dp->ev_free[bsel], 0));
-            }
-        if (distribute(h, [bsel](Dev& d) -> DevBuf& { return d.sChunk[bsel]; }, OVVV + (size_t)d0 * slab, (size_t)dn * slab, dChunk)) return 1;
-        for (int i = 0; i < L; i++) {
-            Dev& d = *h->devs[i];
-            CK(cudaSetDevice(d.dev));
-            dim3 grid((unsigned)(((size_t)o * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
-            prep_pt_particle<<<grid, dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], d0, dn);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(d.ev_free[bsel], d.stream));
-        }
-        h->launches += 1;
-    }
-    (void)W;
+    return 0;
+}
+
+static int upload_conv_impl(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
+                            const double* OOOV, const double* OVOV, const double* fo, const double* fv, bool sync)
+{
+    if (upload_conv_small(h, o, v, T1, T2, OOOV, OVOV, fo, fv)) return 1;
+    if (upload_ovvv(h, OVVV, 0, o, true)) return 1;
     return upload_end(h, sync);
 }
 
@@ -645,21 +687,21 @@ static Problem current_problem(const fpt_handle* h, const Dev& d)
 
 // Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost (shard_items in fpt_layout.h,
 // shared with the CPU emulator so that the gloo tests exercise the very same split)
-static void shard_range(const fpt_handle* h, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
+static void shard_range(const fpt_handle* h, const Problem& P, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
 {
-    shard_items(current_problem(h, *h->devs[0]), h->block_cost.data(), b, e, rank, world, sb, se);
+    shard_items(P, h->block_cost.data(), b, e, rank, world, sb, se);
 }
 
-// launch the fused kernel + reduction for [item_begin, item_end) on one GPU (asynchronous; result in d.out)
-static int compute_launch(fpt_handle* h, Dev& d, i64 item_begin, i64 item_end)
+// launch the fused kernel + reduction for [item_begin, item_end) of the work list described by P on one GPU (asynchronous; the result
+// is stored in d.out, or added to it for the second phase of a split call, which also has its own pair of timing events)
+static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begin, i64 item_end, int phase)
 {
     CK(cudaSetDevice(d.dev));
-    const Problem P = current_problem(h, d);
     const i64 n = item_end - item_begin;
     int grid = d.n_sm;
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
     CK(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
-    CK(cudaEventRecord(d.ev0, d.stream));
+    CK(cudaEventRecord(phase ? d.ev0b : d.ev0, d.stream));
     unsigned long long* ctr = (unsigned long long*)d.counter.p;
 #ifdef FPT_WITH_VARIANT2
     if (h->kernel_variant == 2) {
@@ -673,29 +715,35 @@ static int compute_launch(fpt_handle* h, Dev& d, i64 item_begin, i64 item_end)
         triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
     d.last_grid = grid;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(d.ev1, d.stream));
-    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d());
+    CK(cudaEventRecord(phase ? d.ev1b : d.ev1, d.stream));
+    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), phase);
     CK(cudaGetLastError());
     d.shard_b = item_begin;
     d.shard_e = item_end;
     return 0;
 }
 
-// Enqueue the evaluation of [item_begin, item_end): every GPU of the communicator takes its static, cost-weighted shard, E(T) is
-// one scalar all-reduce, and the 8-byte result is sent to the host.  Nothing here waits for the GPU.
-static int compute_enqueue(fpt_handle* h, i64 item_begin, i64 item_end)
+// Enqueue the kernels for items [item_begin, item_end) of the work list over the triplet window [tw_begin, tw_begin + tw_count):
+// every GPU of the communicator takes its static, cost-weighted shard.
+static int compute_launch_all(fpt_handle* h, i64 tw_begin, i64 tw_count, i64 item_begin, i64 item_end, int phase)
 {
-    if (item_end < 0 || item_end > h->nitems) item_end = h->nitems;
-    if (item_begin < 0) item_begin = 0;
-    if (item_begin > item_end) item_begin = item_end;
-    const int W = h->world;
     for (Dev* dp : h->devs) {
+        Problem P = current_problem(h, *dp);
+        P.tw_begin = tw_begin;
+        P.tw_count = tw_count;
+        P.nitems = P.nb * tw_count;
         i64 sb, se;
-        shard_range(h, item_begin, item_end, dp->grank, W, &sb, &se);
-        if (compute_launch(h, *dp, sb, se)) return 1;
+        shard_range(h, P, item_begin, item_end, dp->grank, h->world, &sb, &se);
+        if (compute_launch(h, *dp, P, sb, se, phase)) return 1;
     }
     h->last_profiled = h->profiling;
-    if (W > 1) {   // the single scalar all-reduce of E(T)
+    return 0;
+}
+
+// E(T) is one scalar all-reduce; the 8-byte result is sent to the host.  Nothing here waits for the GPU.
+static int compute_collect(fpt_handle* h, i64 n_items)
+{
+    if (h->world > 1) {
         NCK(nccl_api().GroupStart());
         for (Dev* dp : h->devs) NCK(nccl_api().AllReduce(dp->out.p, dp->out.p, 1, ncclDouble, ncclSum, dp->comm, dp->stream));
         NCK(nccl_api().GroupEnd());
@@ -704,8 +752,18 @@ static int compute_enqueue(fpt_handle* h, i64 item_begin, i64 item_end)
     CK(cudaSetDevice(d0.dev));
     CK(cudaMemcpyAsync(h->res_pinned, d0.out.p, sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
     CK(cudaEventRecord(d0.tl[5], d0.stream));
-    h->pend_items = item_end - item_begin;
+    h->pend_items = n_items;
     return 0;
+}
+
+static int compute_enqueue(fpt_handle* h, i64 item_begin, i64 item_end)
+{
+    if (item_end < 0 || item_end > h->nitems) item_end = h->nitems;
+    if (item_begin < 0) item_begin = 0;
+    if (item_begin > item_end) item_begin = item_end;
+    h->split = false;
+    if (compute_launch_all(h, h->tw_begin, h->tw_count, item_begin, item_end, 0)) return 1;
+    return compute_collect(h, item_end - item_begin);
 }
 
 static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
@@ -714,9 +772,10 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
     for (Dev* dp : h->devs) {
         CK(cudaSetDevice(dp->dev));
         CK(cudaStreamSynchronize(dp->stream));
-        float ms = 0.f;
+        float ms = 0.f, msb = 0.f;
         CK(cudaEventElapsedTime(&ms, dp->ev0, dp->ev1));
-        if (ms > ms_max) ms_max = ms;
+        if (h->split) CK(cudaEventElapsedTime(&msb, dp->ev0b, dp->ev1b));
+        if (ms + msb > ms_max) ms_max = ms + msb;
     }
     if (Et) *Et = *h->res_pinned;
     // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
@@ -733,7 +792,7 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
     CK(cudaSetDevice(d0.dev));
     for (double& t : h->timeline) t = 0.0;
     h->timeline[0] = h->stage_host_ms;
-    cudaEvent_t marks[5] = {d0.tl[1], d0.tl[2], d0.ev0, d0.ev1, d0.tl[5]};
+    cudaEvent_t marks[5] = {d0.tl[1], d0.tl[2], d0.ev0, h->split ? d0.ev1b : d0.ev1, d0.tl[5]};
     for (int t = 0; t < 5; t++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, d0.tl[0], marks[t]) == cudaSuccess) h->timeline[1 + t] = ms;
@@ -766,11 +825,8 @@ extern "C" int fpt_last_timeline(fpt_handle* h, double* out8)
 // ---- one-call forms ----------------------------------------------------------------------------------------------------------
 // upload and compute are enqueued back to back (no host synchronisation in between); `async` returns as soon as the caller's
 // arrays have been consumed, fpt_wait collects the result.
-static int finish_call(fpt_handle* h, bool async, wall::time_point t0, double* Et, fpt_stats* st)
+static int finish_tail(fpt_handle* h, bool async, wall::time_point t0, double* Et, fpt_stats* st)
 {
-    h->last = fpt_stats{};
-    h->last.h2d_bytes = h->h2d;
-    if (compute_enqueue(h, 0, -1)) return 1;
     if (async) {
         for (Dev* dp : h->devs) {   // inputs in pinned memory are read by the DMA engines directly: wait for those reads
             CK(cudaSetDevice(dp->dev));
@@ -786,6 +842,29 @@ static int finish_call(fpt_handle* h, bool async, wall::time_point t0, double* E
     if (st) *st = h->last;
     return 0;
 }
+static int finish_call(fpt_handle* h, bool async, wall::time_point t0, double* Et, fpt_stats* st)
+{
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h->h2d;
+    if (compute_enqueue(h, 0, -1)) return 1;
+    return finish_tail(h, async, t0, Et, st);
+}
+
+// Where to split a one-call conventional evaluation (0: do not): host-resident OVVV small enough that the second phase's packed copy
+// (half of it, on every GPU) is cheap to hold, enough occupied orbitals for two phases, and a full default work list.  pA is a multiple
+// of 4 (32-byte rows for the streaming copies) near o/2: the first phase is then (pA/o)^3 = 1/8 of the triplets -- long enough to
+// cover the staging of the other half of OVVV.  FERMI_PT_B200_SPLIT=0 switches it off.
+static int split_point(fpt_handle* h, int o, int v, const double* OVVV)
+{
+    if (const char* e = getenv("FERMI_PT_B200_SPLIT"))
+        if (atoi(e) == 0) return 0;
+    if (o < 8 || classify(OVVV) == PK_DEVICE) return 0;
+    if ((double)o * v * v * v * sizeof(double) > 4e9) return 0;
+    if (h->dbg_flags || h->profiling || h->item_order != 1) return 0;
+    int pA = ((o / 2) + 3) & ~3;
+    if (pA >= o) pA = o / 2;
+    return pA;
+}
 
 static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
                         const double* OVOV, const double* fo, const double* fv, double* Et, fpt_stats* st, bool async, const char* who)
@@ -796,8 +875,28 @@ static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const dou
     const auto t0 = wall::now();
     if (admit_device_inputs(h, who, {T1, T2, OVVV, OOOV, OVOV, fo, fv})) return 1;
     upload_begin(h);
-    if (upload_conv_impl(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, false)) return 1;
-    return finish_call(h, async, t0, Et, st);
+    const int pA = split_point(h, o, v, OVVV);
+    if (pA <= 0) {
+        if (upload_conv_impl(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, false)) return 1;
+        return finish_call(h, async, t0, Et, st);
+    }
+    // Split call.  The triplets with i < pA only read the operands of the occupied indices p < pA, and they are the first uA entries of
+    // the reference's triplet list (ijk.jl:49,63,83 loops i slowest).  So: upload everything but OVVV, then OVVV[p < pA]; launch the
+    // kernel over that window; while it runs, the host threads and the DMA engines bring OVVV[p >= pA]; then the rest of the list.
+    // The second half of the host-bound staging time -- the part of an 8-GPU call that does not shrink with the number of GPUs --
+    // disappears behind the first kernel.
+    if (upload_conv_small(h, o, v, T1, T2, OOOV, OVOV, fo, fv)) return 1;
+    if (upload_ovvv(h, OVVV, 0, pA, true)) return 1;
+    const i64 uA = num_triplets(pA), uAll = num_triplets(o), nb = h->devs[0]->prob.nb;
+    h->split = true;
+    if (compute_launch_all(h, 0, uA, 0, nb * uA, 0)) return 1;
+    if (upload_ovvv(h, OVVV, pA, o - pA, false)) return 1;
+    if (upload_end(h, false)) return 1;
+    if (compute_launch_all(h, uA, uAll - uA, 0, nb * (uAll - uA), 1)) return 1;
+    h->last = fpt_stats{};
+    h->last.h2d_bytes = h->h2d;
+    if (compute_collect(h, nb * uAll)) return 1;
+    return finish_tail(h, async, t0, Et, st);
 }
 
 static int triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO, const double* BOV,
@@ -1179,7 +1278,7 @@ extern "C" int fpt_shard_items(fpt_handle* h, int rank, int world, long long* it
     if (!h->loaded) return fail("fpt_shard_items: no problem uploaded");
     if (world < 1 || rank < 0 || rank >= world) return fail("fpt_shard_items: invalid rank %d of %d", rank, world);
     i64 sb, se;
-    shard_range(h, 0, h->nitems, rank, world, &sb, &se);
+    shard_range(h, current_problem(h, *h->devs[0]), 0, h->nitems, rank, world, &sb, &se);
     *item_begin = sb;
     *item_end = se;
     return 0;

@@ -11,10 +11,10 @@
 
 namespace fpt {
 
-__global__ void reduce_partials(const double* partials, int n, double* out)
+__global__ void reduce_partials(const double* partials, int n, double* out, int accumulate)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
+        double s = accumulate ? out[0] : 0.0;
         for (int t = 0; t < n; t++) s += partials[t];
         out[0] = s;
     }
@@ -23,11 +23,12 @@ __global__ void reduce_partials(const double* partials, int n, double* out)
 // ---------------------------------------------------------------------------------------------------
 // K4: layout prep.  Sources are the reference's column-major arrays (first index fastest).
 // ---------------------------------------------------------------------------------------------------
-// Pt[p][y][x][d] = OVVV[p,y,x,d] for d in [d0, d0+dn); `src` points at OVVV[:,:,:,d0].
-__global__ void prep_pt_particle(Problem P, double* Pt, const double* __restrict__ src, int d0, int dn)
+// Pt[p][y][x][d] = OVVV[p,y,x,d] for d in [d0, d0+dn) and p in [p0, p0+np); `src` holds that sub-block compactly,
+// src[pl + np*(y + v*(x + v*dd))] (np = o, p0 = 0: it points at OVVV[:,:,:,d0] itself).
+__global__ void prep_pt_particle(Problem P, double* Pt, const double* __restrict__ src, int d0, int dn, int p0, int np)
 {
     __shared__ double tile[32][33];
-    const int o = P.o, v = P.v;
+    const int o = np, v = P.v;
     const i64 ov = (i64)o * v;
     const int x = blockIdx.z;
     const i64 py0 = (i64)blockIdx.x * 32;
@@ -43,7 +44,7 @@ __global__ void prep_pt_particle(Problem P, double* Pt, const double* __restrict
         const i64 py = py0 + ty + kk;
         const int dd = dd0 + tx;
         if (dd < dn && py < ov) {
-            const int p = (int)(py % o), y = (int)(py / o);
+            const int p = p0 + (int)(py % o), y = (int)(py / o);
             Pt[pt_row(P, p, y, x) + d0 + dd] = tile[tx][ty + kk];
         }
     }

@@ -126,6 +126,7 @@ struct Dev {
     cudaStream_t stream = nullptr;   // kernels + collectives
     cudaStream_t copy = nullptr;     // host -> device DMAs
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;            // around the fused kernel
+    cudaEvent_t ev0b = nullptr, ev1b = nullptr;          // around the second kernel of a split call
     cudaEvent_t ev_copy = nullptr, ev_start = nullptr;   // copy -> stream / stream -> copy hand-offs
     cudaEvent_t ev_free[2] = {nullptr, nullptr};         // OVVV chunk buffer c&1 has been consumed by its prep kernel
     cudaEvent_t tl[NTL] = {};
@@ -133,7 +134,7 @@ struct Dev {
     // resident operands
     DevBuf Pt, Qt, OV2, T1d, fo, fv, partials, counter, out, prof, blocktab;
     // raw inputs (staging)
-    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sBOO, sBOV, sBVV;
+    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sPhaseB, sBOO, sBOV, sBVV;
     // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
     DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
     Problem prob{};
@@ -165,6 +166,7 @@ struct fpt_handle {
     int kernel_variant = 1;
     bool loaded = false;
     bool pending = false;     // an asynchronous call is in flight (fpt_wait has to collect it)
+    bool split = false;       // the evaluation in flight / last finished ran as two kernels (triples_conv, split call)
     fpt::i64 pend_items = 0;
     fpt_stats last{};
     int launches = 0;

@@ -45,6 +45,23 @@ inline void copy_to_pinned(void* dst, const void* src, size_t bytes, bool nt)
     if (nt && avx2 && ((uintptr_t)dst % 32) == 0) copy_stream_avx2(dst, src, bytes);
     else memcpy(dst, src, bytes);
 }
+// gather `nrows` rows of `row_bytes` (source pitch `pitch`) into a contiguous pinned buffer
+__attribute__((target("avx2"))) inline void copy_rows_stream_avx2(char* d, const char* s, size_t nrows, size_t row_bytes, size_t pitch)
+{
+    for (size_t r = 0; r < nrows; r++, s += pitch) {
+        for (size_t b = 0; b < row_bytes; b += 32, d += 32)
+            _mm256_stream_si256((__m256i*)d, _mm256_loadu_si256((const __m256i*)(s + b)));
+    }
+    _mm_sfence();
+}
+inline void copy_rows_to_pinned(void* dst, const void* src, size_t nrows, size_t row_bytes, size_t pitch, bool nt)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (nt && avx2 && ((uintptr_t)dst % 32) == 0 && row_bytes % 32 == 0) { copy_rows_stream_avx2((char*)dst, (const char*)src, nrows, row_bytes, pitch); return; }
+    char* d = (char*)dst;
+    const char* s = (const char*)src;
+    for (size_t r = 0; r < nrows; r++, s += pitch, d += row_bytes) memcpy(d, s, row_bytes);
+}
 
 class StagePool {
 public:
@@ -53,7 +70,9 @@ public:
     struct Job {
         char* dst = nullptr;          // device
         const char* src = nullptr;    // pageable host
-        size_t bytes = 0;
+        size_t bytes = 0;             // total bytes that arrive at dst (contiguous there)
+        size_t row_bytes = 0;         // 0: `src` is contiguous too; else the source is a set of rows of row_bytes ...
+        size_t src_pitch = 0;         // ... src_pitch bytes apart (a sub-range of the fastest index of a column-major array)
         int dev = 0;                  // CUDA ordinal
         int idev = 0;                 // index of the GPU inside the handle (event bank)
         cudaStream_t stream = nullptr;
@@ -71,7 +90,7 @@ public:
         slots_.assign((size_t)nthreads_ * SLOTS_PER_THREAD, Slot{});
         for (auto& s : slots_) {
             s.ev.assign(ndev, nullptr);
-            cudaError_t e = cudaHostAlloc((void**)&s.p, PIECE, cudaHostAllocPortable);
+            cudaError_t e = cudaHostAlloc((void**)&s.p, PIECE, cudaHostAllocPortable);   // rows never exceed PIECE (o * 8 bytes)
             if (e != cudaSuccess) return e;
         }
         next_.assign(nthreads_, 0);
@@ -100,7 +119,7 @@ public:
     // enqueue the whole transfer (returns when every piece has been copied out of `src` and its DMA is enqueued)
     cudaError_t transfer(const Job& job)
     {
-        const size_t np = (job.bytes + PIECE - 1) / PIECE;
+        const size_t np = (job.bytes + piece_bytes(job) - 1) / piece_bytes(job);
         const int active = (int)(np < (size_t)nthreads_ ? np : (size_t)nthreads_);
         err_.store((int)cudaSuccess);
         if (active > 1) {
@@ -123,6 +142,8 @@ public:
     }
 
 private:
+    // bytes per piece: PIECE, or the whole number of rows that fits into it
+    size_t piece_bytes(const Job& j) const { return j.row_bytes ? (PIECE / j.row_bytes ? PIECE / j.row_bytes : 1) * j.row_bytes : PIECE; }
     struct Slot { char* p = nullptr; std::vector<cudaEvent_t> ev; int busy = -1; };
     void note(cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; err_.compare_exchange_strong(ok, (int)e); } }
     void work(int t)
@@ -131,7 +152,8 @@ private:
         const int T = active_;
         if (t >= T) return;
         if (cudaSetDevice(job.dev) != cudaSuccess) { note(cudaGetLastError()); return; }
-        const size_t np = (job.bytes + PIECE - 1) / PIECE;
+        const size_t pb = piece_bytes(job);
+        const size_t np = (job.bytes + pb - 1) / pb;
         for (size_t p = t; p < np; p += T) {
             Slot& s = slots_[(size_t)t * SLOTS_PER_THREAD + next_[t]];
             next_[t] = (next_[t] + 1) % SLOTS_PER_THREAD;
@@ -139,8 +161,9 @@ private:
                 note(cudaEventSynchronize(s.ev[s.busy]));
                 s.busy = -1;
             }
-            const size_t off = p * PIECE, nb = job.bytes - off < PIECE ? job.bytes - off : PIECE;
-            copy_to_pinned(s.p, job.src + off, nb, nt_stores);
+            const size_t off = p * pb, nb = job.bytes - off < pb ? job.bytes - off : pb;
+            if (job.row_bytes) copy_rows_to_pinned(s.p, job.src + (off / job.row_bytes) * job.src_pitch, nb / job.row_bytes, job.row_bytes, job.src_pitch, nt_stores);
+            else copy_to_pinned(s.p, job.src + off, nb, nt_stores);
             note(cudaMemcpyAsync(job.dst + off, s.p, nb, cudaMemcpyHostToDevice, job.stream));
             if (!s.ev[job.idev]) note(cudaEventCreateWithFlags(&s.ev[job.idev], cudaEventDisableTiming));
             if (s.ev[job.idev]) {

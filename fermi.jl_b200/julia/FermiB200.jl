@@ -4,10 +4,11 @@
 # (include/fermi_pt_b200.h) is exercised from Python/ctypes by tests/ and bench.py.
 #
 # Usage (inside a Fermi.jl session):
-#     include("FermiB200.jl")                      # defines Fermi.CoupledCluster.B200 <: RpTAlgorithm, pt_alg = 4
+#     include("FermiB200.jl")                      # defines FermiB200.B200 <: Fermi.CoupledCluster.RpTAlgorithm, registers pt_alg = 4
 #     @set pt_alg 4
-#     @energy ccsd(t)                              # -> RCCSDpT() -> RCCSDpT(B200()) -> RCCSDpT(ccsd, moints, B200())
-#  or, warm:  @energy cc, moints => ccsd(t)   /   Fermi.CoupledCluster.RCCSDpT(cc, moints, Fermi.CoupledCluster.B200())
+#     @energy ccsd(t)                              # -> RCCSDpT() -> RCCSDpT(FermiB200.B200()) -> RCCSDpT(ccsd, moints, FermiB200.B200())
+#  or, warm:  @energy cc, moints => ccsd(t)   /   Fermi.CoupledCluster.RCCSDpT(cc, moints, FermiB200.B200())
+#  FERMI_PT_B200_NGPU=8 makes the one handle drive GPUs 0..7 (sharded upload, NCCL all-gather, one scalar all-reduce).
 #
 # Mirrors src/Methods/CoupledCluster/PerturbativeTriples/ijk.jl:4-20 (the three overloads) and replaces
 # ijk.jl:20-150 by one ccall.
@@ -101,12 +102,14 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
                         (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                          Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
                         handle(), o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, Et, st))
-        elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV") && get(ENV, "FERMI_PT_B200_AO", "sparse") == "sparse"
-            # default conventional route of the reference: the MO helper is Chonky, its AO helper holds the *sparse* list
-            # (IntegralHelper.jl:88-90); instead of Sparse.jl:78-151,236-393 on the CPU the list itself goes to the GPU
+        elseif moints.eri_type isa Chonky && !haskey(moints.cache, "OVVV") && T === Float64 && get(ENV, "FERMI_PT_B200_AO", "dense") == "sparse"
+            # opt-in (FERMI_PT_B200_AO=sparse; Float64 only -- the reference's sparse builder does not support single precision):
+            # hand the GPU the *sparse* AO list (what IntegralHelper.jl:88-90 gives an AO helper by default) instead of letting
+            # Sparse.jl:78-151,236-393 scatter and contract it on the CPU.  Not the default because compute!(::IntegralHelper{T,Chonky})
+            # itself builds its AO helper with eri_type = I.eri_type, i.e. dense (ROIntegrals.jl:1-7): the branch below mirrors that.
             basis = moints.orbitals.basis                          # ROIntegrals.jl:3
             aoorbs = AtomicOrbitals(moints.molecule, basis)
-            aoints = IntegralHelper{T}(molecule=moints.molecule, orbitals=aoorbs, basis=basis, eri_type=Fermi.Integrals.SparseERI())
+            aoints = IntegralHelper{Float64}(molecule=moints.molecule, orbitals=aoorbs, basis=basis, eri_type=Fermi.Integrals.SparseERI())
             eri = aoints["ERI"]                                   # FermiSparse{Float64,Int16,4}: .indexes (zero-based), .data
             C = moints.orbitals.C
             core = Options.get("drop_occ"); inac = Options.get("drop_vir")

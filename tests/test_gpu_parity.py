@@ -431,3 +431,27 @@ def test_randomised_sweep(engine):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "40", "11"], capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("o,v", [(8, 30), (9, 70), (13, 41), (24, 57)])
+def test_split_call_matches_single_launch(engine, o, v):
+    """fpt_triples_conv with o >= 8 runs as a split call (operands of the occupied indices p < pA first, kernel over the triplets with
+    i < pA, the rest of OVVV staged behind it, second kernel): same E(T) as the oracle and as the unsplit call, from pageable and from
+    pinned host arrays (the latter take the cudaMemcpy2DAsync row gather)."""
+    import os
+    import torch
+    x = fb.synth.make_inputs(o, v, naux=12, seed=40 + o)
+    ref = oracle.pt_gemm(*_args(x))
+    e_split, st = engine.triples_conv(o, v, *_args(x))
+    assert st["n_launches"] >= 9          # two fused kernels + two reductions among them
+    os.environ["FERMI_PT_B200_SPLIT"] = "0"
+    try:
+        e_whole, st0 = engine.triples_conv(o, v, *_args(x))
+    finally:
+        del os.environ["FERMI_PT_B200_SPLIT"]
+    assert abs(e_split - ref) < TOL and abs(e_whole - ref) < TOL, (e_split, e_whole, ref)
+    assert abs(e_split - e_whole) < 1e-13
+    assert st["h2d_bytes"] == st0["h2d_bytes"] == sum(a.size * 8 for a in _args(x))
+    pinned = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in _args(x)]
+    e_pin, _ = engine.triples_conv(o, v, *pinned)
+    assert abs(e_pin - e_split) < 1e-13
