@@ -785,7 +785,7 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
     h->last.n_items = h->pend_items;
     h->last.n_triplets = (long long)ntrip;
     h->last.flops = 12.0 * v * (double)v * v * (v + o) * ntrip * (h->nitems ? (double)h->pend_items / (double)h->nitems : 0.0);
-    h->last.n_launches = h->launches + 2 * (int)h->devs.size();
+    h->last.n_launches = h->launches + (h->split ? 4 : 2) * (int)h->devs.size();
     h->last.n_sm = h->devs[0]->n_sm;
     // timeline of the first GPU, milliseconds since the upload began (entries stay 0 when the compute followed an older upload)
     Dev& d0 = *h->devs[0];
