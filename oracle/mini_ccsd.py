@@ -12,8 +12,11 @@ tests/test_oracle_kat.py then feeds the stored T1/T2/integrals to the oracle and
 A second case pins it on a value the reference's own test suite asserts: water / 6-31G / df false, `@energy ccsd(t)` total
 -76.121147867765558 (test/test_pT.jl:69-72, rtol 2e-8) -> tests/golden/water_631g.npz.
 
-Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g):
-    python oracle/mini_ccsd.py [sto-3g|6-31g]
+A third case is BASELINE config C2 itself: water / cc-pVTZ (o = 5, v = 53; d and f shells), for which test/test_pT.jl:5,31 holds
+Psi4's CCSD(T) and CCSD totals, i.e. E(T) = -0.008051775570 -> tests/golden/water_ccpvtz.npz (integrals: oracle/mini_ints.py, numba).
+
+Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
+    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz] [numba]
 """
 from __future__ import annotations
 
@@ -53,12 +56,31 @@ B631G = {
           (0, [0.2700058], [1.0]),
           (1, [0.2700058], [1.0])],
 }
-BASES = {"sto-3g": STO3G, "6-31g": B631G}
+# cc-pVTZ (Dunning, JCP 90, 1007 (1989); Basis Set Exchange, optimised general contractions): O (10s5p2d1f) -> [4s3p2d1f],
+# H (5s2p1d) -> [3s2p1d]; real solid harmonics (58 functions for water).  Integrals: oracle/mini_ints.py.
+CCPVTZ = {
+    "H": [(0, [33.87, 5.095, 1.159], [0.006068, 0.045308, 0.202822]),
+          (0, [0.3258], [1.0]), (0, [0.1027], [1.0]),
+          (1, [1.407], [1.0]), (1, [0.388], [1.0]),
+          (2, [1.057], [1.0])],
+    "O": [(0, [15330.0, 2299.0, 522.4, 147.3, 47.55, 16.76, 6.207, 0.6882],
+              [0.000508, 0.003929, 0.020243, 0.079181, 0.230687, 0.433118, 0.350260, -0.008154]),
+          (0, [15330.0, 2299.0, 522.4, 147.3, 47.55, 16.76, 6.207, 0.6882],
+              [-0.000115, -0.000895, -0.004636, -0.018724, -0.058463, -0.136463, -0.175740, 0.603418]),
+          (0, [1.752], [1.0]), (0, [0.2384], [1.0]),
+          (1, [34.46, 7.749, 2.280], [0.015928, 0.099740, 0.310492]),
+          (1, [0.7156], [1.0]), (1, [0.2140], [1.0]),
+          (2, [2.314], [1.0]), (2, [0.645], [1.0]),
+          (3, [1.428], [1.0])],
+}
+BASES = {"sto-3g": STO3G, "6-31g": B631G, "cc-pvtz": CCPVTZ}
 # What the reference holds for each case: the printed run of examples/Juliacon2022.ipynb:497-615 (STO-3G) and the Psi4 total
 # energy its own test asserts for `@energy ccsd(t)`, water / 6-31G / df false (test/test_pT.jl:69-72, rtol 2e-8).
 REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd": -75.0187095932, "e_t": -0.0000738086,
                         "e_ccsd_t": -75.0187834019},
-             "6-31g": {"e_ccsd_t": -76.121147867765558}}
+             "6-31g": {"e_ccsd_t": -76.121147867765558},
+             # Psi4 totals the reference's test suite holds for water / cc-pVTZ / df false (test/test_pT.jl:5 Econv[1], :31 CCSDconv[1])
+             "cc-pvtz": {"e_ccsd": -76.335767822597347, "e_ccsd_t": -76.343819598166903, "e_t": -76.343819598166903 + 76.335767822597347}}
 
 
 def dfact(n):
@@ -282,7 +304,7 @@ def ccsd_spinorbital(eps, MO, ndocc, tol=1e-13, maxit=200):
     Dijab = fo[:, None, None, None] + fo[None, :, None, None] - fv[None, None, :, None] - fv[None, None, None, :]
     t1 = np.zeros((no, ns - no))
     t2 = A[o, o, v, v] / Dijab
-    es = np.einsum
+    es = lambda *a: np.einsum(*a, optimize=True)
     e_old = 0.0
     hist_t, hist_e = [], []
     for it in range(maxit):
@@ -354,17 +376,33 @@ def pt_spinorbital(t1, t2, A, fs, no):
     return float(np.sum(conn * (conn + disc) / D) / 36.0)
 
 
-def main(basis="sto-3g"):
+def integrals_numba(basis):
+    """The same integrals from oracle/mini_ints.py (numba, any angular momentum, real solid harmonics)."""
+    from oracle import mini_ints
+    shells, atoms = [], []
+    for sym, xyz in GEOM:
+        pos = np.array(xyz) / BOHR_TO_ANGSTROM
+        atoms.append((Z[sym], pos))
+        for l, exps, coefs in BASES[basis][sym]:
+            shells.append((pos, l, exps, coefs))
+    return mini_ints.integrals(shells, atoms)
+
+
+def main(basis="sto-3g", engine="auto"):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
-    bfs, atoms = build_basis(basis)
-    S, T, V, ERI, enuc = integrals(bfs, atoms)
+    if engine == "numba" or (engine == "auto" and basis == "cc-pvtz"):
+        S, T, V, ERI, enuc = integrals_numba(basis)
+    else:
+        bfs, atoms = build_basis(basis)
+        S, T, V, ERI, enuc = integrals(bfs, atoms)
     ndocc = 5
     e_el, eps, C = rhf(S, T + V, ERI, ndocc)
     e_rhf = e_el + enuc
     MO = np.einsum("pqrs,pi,qj,rk,sl->ijkl", ERI, C, C, C, C, optimize=True)
     e_cc, t1, t2, A, fs, no = ccsd_spinorbital(eps, MO, ndocc)
-    e_t_so = pt_spinorbital(t1, t2, A, fs, no)
+    # the 6-index spin-orbital (T) is an independent check for the small cases only ((2o)^3 (2v)^3 doubles)
+    e_t_so = pt_spinorbital(t1, t2, A, fs, no) if len(eps) <= 16 else float("nan")
     o, n = ndocc, len(eps)
     v = n - o
     T1 = np.asfortranarray(t1[0::2, 0::2])
@@ -387,6 +425,13 @@ def main(basis="sto-3g"):
     print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}" + note("e_ccsd_t"))
     out = os.path.join(root, "tests", "golden", "water_" + basis.replace("-", "") + ".npz")
     extra = {}
+    if basis == "cc-pvtz":   # 5 x 53^3 doubles: keep only b >= c of (ia|bc) = (ia|cb) (tests/test_oracle_kat.py unpacks it)
+        iu = np.triu_indices(v)
+        packed = np.ascontiguousarray(OVVV[:, :, iu[1], iu[0]])      # [i, a, (b >= c)]
+        assert np.max(np.abs(OVVV - OVVV.transpose(0, 1, 3, 2))) < 1e-12
+        np.savez_compressed(out, T1=T1, T2=T2, OVVV_packed=packed, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t)
+        print("wrote", out)
+        return
     if basis == "sto-3g":   # small enough to keep: lets the AO -> MO route (fpt_triples_ao) be checked on a real molecule
         extra = {"AOERI": np.asfortranarray(ERI), "C": np.asfortranarray(C)}
     np.savez(out, T1=T1, T2=T2, OVVV=OVVV, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t,
@@ -395,4 +440,4 @@ def main(basis="sto-3g"):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "sto-3g")
+    main(sys.argv[1] if len(sys.argv) > 1 else "sto-3g", sys.argv[2] if len(sys.argv) > 2 else "auto")

@@ -101,3 +101,48 @@ def test_gpu_ao_route_matches_reference_known_answer(engine):
     res = fb.RCCSDpT(ccsd, moints, fb.B200())
     assert abs(res.correction - REF_ET) < 5e-11
     assert abs(res.energy - REF_ECCSDT) < 5e-11
+
+
+# ---- water / cc-pVTZ = BASELINE config C2 on the real molecule (test/test_pT.jl:5,31) ----------------------------------
+# The reference's test holds Psi4's CCSD(T) and CCSD totals for water / cc-pVTZ / `df false`; their difference is E(T).
+# `python oracle/mini_ccsd.py cc-pvtz` (d and f shells: oracle/mini_ints.py) rebuilt RHF + CCSD for it (o = 5, v = 53) and stored
+# the amplitudes and MO blocks in tests/golden/water_ccpvtz.npz ((ia|bc) packed over b >= c).
+G3 = np.load(os.path.join(os.path.dirname(__file__), "golden", "water_ccpvtz.npz"))
+REF3_ECCSDT = -76.343819598166903   # test/test_pT.jl:5  Econv[1]
+REF3_ECCSD = -76.335767822597347    # test/test_pT.jl:31 CCSDconv[1]
+REF3_ET = REF3_ECCSDT - REF3_ECCSD  # -0.008051775570
+
+
+def _args3():
+    v = G3["T1"].shape[1]
+    iu = np.triu_indices(v)
+    ovvv = np.empty((5, v, v, v))
+    ovvv[:, :, iu[1], iu[0]] = G3["OVVV_packed"]
+    ovvv[:, :, iu[0], iu[1]] = G3["OVVV_packed"]
+    return tuple(np.asfortranarray(a) for a in (G3["T1"], G3["T2"], ovvv, G3["OOOV"], G3["OVOV"], G3["fo"], G3["fv"]))
+
+
+def test_stored_ccpvtz_inputs_reproduce_reference_ccsd_total():
+    assert G3["T1"].shape == (5, 53) and G3["T2"].shape == (5, 5, 53, 53)
+    assert abs(float(G3["e_rhf"]) + float(G3["e_corr"]) - REF3_ECCSD) < 1e-9     # measured: 7e-11
+
+
+@pytest.mark.parametrize("impl", ["gemm", "numpy_ijk2"])
+def test_oracle_matches_reference_test_value_ccpvtz(impl):
+    f = {"gemm": oracle.pt_gemm, "numpy_ijk2": P.pt_ijk2}[impl]
+    e = f(*_args3())
+    assert abs(e - REF3_ET) < 1e-9, (e, REF3_ET)                                   # measured: 3e-12
+    assert abs(float(G3["e_rhf"]) + float(G3["e_corr"]) + e - REF3_ECCSDT) < 1e-9
+    assert abs(e - float(G3["e_t"])) < 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_test_value_ccpvtz(engine):
+    import fermi_jl_b200 as fb
+    a = _args3()
+    ccsd = fb.RCCSD(0.0, float(G3["e_corr"]), float(G3["e_rhf"]) + float(G3["e_corr"]), a[0], a[1])
+    moints = fb.IntegralHelper({"OVVV": a[2], "OOOV": a[3], "OVOV": a[4], "Fii": a[5], "Faa": a[6]})
+    res = fb.RCCSDpT(ccsd, moints, fb.B200())
+    assert abs(res.correction - REF3_ET) < 1e-9
+    assert abs(res.energy - REF3_ECCSDT) < 1e-9
+    assert abs(res.correction - float(G3["e_t"])) < 1e-12
