@@ -311,8 +311,12 @@ def main():
     else:   # a DF helper holds only the B factors (DFERI.jl:15-69); the 4-index blocks are assembled on the GPU
         moints = fb.IntegralHelper({"BOO": harr["BOO"], "BOV": harr["BOV"], "BVV": harr["BVV"], "Fii": harr["fo"], "Faa": harr["fv"]}, eri_type="RIFIT")
 
+    last_stats = {}
+
     def e2e_step(engine):
-        return fb.RCCSDpT(ccsd, moints, fb.B200(), engine=engine).correction
+        res = fb.RCCSDpT(ccsd, moints, fb.B200(), engine=engine)
+        last_stats.update(res.stats)
+        return res.correction
 
     def time_e2e(engine, collective):
         for _ in range(3):
@@ -333,6 +337,13 @@ def main():
 
     e_e2e, e2e_ms, breakdown = time_e2e(eng, True)
     e2e_ms = max_over_ranks(e2e_ms)
+    # bytes that crossed PCIe in one end-to-end step, as counted by the library (every rank pulls its own share: sum over ranks);
+    # host arrays of 4 MB and more cross as their symmetry-unique halves, so this is below the size of the arrays (h2d_bytes)
+    moved = float(last_stats.get("h2d_bytes", 0.0))
+    if dist is not None:
+        t = torch.tensor([moved], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        moved = float(t.item())
     e2e_value = flops / (e2e_ms * 1e-3) / 1e12
 
     # ---- leg 3 (N > 1): the same call on ONE process driving all N GPUs (fpt_create(ngpu = N), what the Julia glue uses);
@@ -382,10 +393,10 @@ def main():
                 "config": {"workload": workload_text(name, o, v, naux, route),
                            "o": o, "v": v, "triplets": ntrip, "work_items": n_items, "route": route,
                            "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} GPU(s)",
-                           "e2e_inputs": "pageable host arrays; sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)",
+                           "e2e_inputs": "pageable host arrays (%.0f MB); the symmetry-unique halves of OVVV, T2, OVOV cross PCIe (%.0f MB); sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)" % (h2d_bytes / 1e6, moved / 1e6),
                            "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 15) // 16 * 16) * 8 / 1e6)},
                 "triplets_per_s": ntrip / (step_ms * 1e-3), "E_T": e_gpu, "E_T_e2e": e_e2e,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(moved), "host_array_bytes": h2d_bytes, "d2h_bytes_per_step": 8,
                         "breakdown_ms": breakdown},
                 "e2e_handle": e2e_handle,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}

@@ -8,6 +8,7 @@
 #include <sched.h>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -35,11 +36,11 @@ static void dev_destroy(Dev* d)
     cudaSetDevice(d->dev);
     if (d->comm) nccl_api().CommDestroy(d->comm);
     DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhaseB, &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->sBOO, &d->sBOV, &d->sBVV,
                       &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
                       &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
     for (DevBuf* b : bufs) b->release();
-    cudaEvent_t evs[] = {d->ev0, d->ev1, d->ev0b, d->ev1b, d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
+    cudaEvent_t evs[] = {d->ev0[0], d->ev1[0], d->ev0[1], d->ev1[1], d->ev0[2], d->ev1[2], d->ev0[3], d->ev1[3], d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d->tl)
@@ -59,10 +60,11 @@ static int dev_init(Dev* d)
     d->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&d->ev0));
-    CK(cudaEventCreate(&d->ev1));
-    CK(cudaEventCreate(&d->ev0b));
-    CK(cudaEventCreate(&d->ev1b));
+    static_assert(MAX_PHASES == 4, "dev_destroy lists the phase events and buffers one by one");
+    for (int t = 0; t < MAX_PHASES; t++) {
+        CK(cudaEventCreate(&d->ev0[t]));
+        CK(cudaEventCreate(&d->ev1[t]));
+    }
     CK(cudaEventCreateWithFlags(&d->ev_copy, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->ev_free[0], cudaEventDisableTiming));
@@ -216,6 +218,13 @@ extern "C" int fpt_create_rank(int device, int rank, int world, const void* id12
     return 0;
 }
 
+extern "C" int fpt_set_symmetric_inputs(fpt_handle* h, int on)
+{
+    if (!h) return fail("fpt_set_symmetric_inputs: NULL handle");
+    h->sym_inputs = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int fpt_set_host_threads(fpt_handle* h, int n)
 {
     if (!h) return fail("fpt_set_host_threads: NULL handle");
@@ -263,29 +272,49 @@ static int admit_device_inputs(fpt_handle* h, const char* who, std::initializer_
 }
 
 // ---- staging ---------------------------------------------------------------------------------------------------------------
-// enqueue the copy of `bytes` from host `src` to `dst` on GPU d (its copy stream)
-// (row_bytes != 0: the source is bytes / row_bytes rows of row_bytes, src_pitch bytes apart; they arrive contiguously)
-static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, size_t bytes, PtrKind kind, size_t row_bytes = 0, size_t src_pitch = 0)
+// enqueue the copy of bytes [begin, begin + bytes) of the packed stream of `view` (a view of the host array `src`, see fpt_stage.h)
+// to `dst` on GPU d (its copy stream).  Pinned or tiny contiguous sources are handed to the DMA engine directly, a pinned single
+// slab of rows as a 2-D copy; everything else becomes a job for the staging threads, collected in `jobs` so that the parts of one
+// array that go to different GPUs are staged as ONE transfer (stage_flush).  `view` must stay alive until the flush.
+static int stage_to(fpt_handle* h, Dev& d, void* dst, const void* src, const View& view, size_t begin, size_t bytes, PtrKind kind,
+                    std::vector<StagePool::Job>& jobs)
 {
     if (bytes == 0) return 0;
     CK(cudaSetDevice(d.dev));
     h->h2d += (double)bytes;
-    if (row_bytes && kind == PK_PINNED) {   // the DMA engine gathers the rows itself
-        CK(cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, bytes / row_bytes, cudaMemcpyHostToDevice, d.copy));
+    const bool one = view.slabs.size() == 1;
+    const Slab& s0 = view.slabs[0];
+    if (one && s0.nrows == 1 && (kind == PK_PINNED || bytes <= ((size_t)64 << 10))) {
+        CK(cudaMemcpyAsync(dst, (const char*)src + s0.src_off + begin, bytes, cudaMemcpyHostToDevice, d.copy));
         return 0;
     }
-    if (!row_bytes && (kind == PK_PINNED || bytes <= ((size_t)64 << 10))) {
-        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.copy));
+    if (one && kind == PK_PINNED && begin % s0.row_bytes == 0 && bytes % s0.row_bytes == 0) {   // the DMA engine gathers the rows itself
+        CK(cudaMemcpy2DAsync(dst, s0.row_bytes, (const char*)src + s0.src_off + (begin / s0.row_bytes) * s0.pitch, s0.pitch, s0.row_bytes,
+                             bytes / s0.row_bytes, cudaMemcpyHostToDevice, d.copy));
         return 0;
     }
-    const auto t0 = wall::now();
     StagePool::Job job;
-    job.dst = (char*)dst; job.src = (const char*)src; job.bytes = bytes;
-    job.row_bytes = row_bytes; job.src_pitch = src_pitch;
+    job.dst = (char*)dst; job.src = (const char*)src; job.view = &view; job.begin = begin; job.bytes = bytes;
     job.dev = d.dev; job.idev = d.idx; job.stream = d.copy;
-    CK(h->pool.transfer(job));
-    h->stage_host_ms += ms_since(t0);
+    jobs.push_back(job);
     return 0;
+}
+static int stage_flush(fpt_handle* h, std::vector<StagePool::Job>& jobs)
+{
+    if (jobs.empty()) return 0;
+    const auto t0 = wall::now();
+    CK(h->pool.transfer(jobs));
+    h->stage_host_ms += ms_since(t0);
+    jobs.clear();
+    return 0;
+}
+// one contiguous array to one GPU, staged right away
+static int stage_now(fpt_handle* h, Dev& d, void* dst, const void* src, size_t bytes, PtrKind kind)
+{
+    std::vector<StagePool::Job> jobs;
+    const View view = View::contiguous(bytes);
+    if (stage_to(h, d, dst, src, view, 0, bytes, kind, jobs)) return 1;
+    return stage_flush(h, jobs);
 }
 
 // the copy stream's work so far is what the compute stream continues from
@@ -299,22 +328,21 @@ static int copy_then_stream(Dev& d)
 
 constexpr size_t SHARD_MIN_BYTES = (size_t)1 << 20;
 
-// Makes the array `src` (n doubles; host or device memory) resident on every GPU of the handle, ordered on each GPU's compute
-// stream; out[i] = its address on devs[i].  `bufof(d)` names the staging buffer to use on GPU d.
-//  * host memory, world > 1, >= 1 MB: GPU g pulls only part g of `world` over its own PCIe link, then one in-place ncclAllGather
-//    over NVLink completes the array everywhere (in rank mode every process passes the same array and pulls its own part);
-//  * host memory otherwise: every GPU of this process pulls the whole array;
+// Makes the array `src` (host or device memory) resident on every GPU of the handle, ordered on each GPU's compute stream;
+// out[i] = its address on devs[i].  `bufof(d)` names the staging buffer to use on GPU d.  `view` (host memory only): what of the array
+// is wanted, in bytes (fpt_stage.h) -- its packed stream of n doubles is what arrives; nullptr = the n doubles at `src` themselves.
+//  * host memory, world > 1, >= 1 MB: GPU g pulls only part g of `world` of the packed stream over its own PCIe link, then one
+//    in-place ncclAllGather over NVLink completes it everywhere (in rank mode every process passes the same array and pulls its part);
+//  * host memory otherwise: every GPU of this process pulls the whole stream;
 //  * device memory (on devs[0]): used in place; the other GPUs of a single-process handle receive it by ncclBroadcast.
-//  * row_len != 0 (host memory only): the source is n / row_len rows of row_len doubles, `pitch` doubles apart -- a sub-range of the
-//    fastest index of a column-major array; the rows arrive packed, and the parts of a sharded transfer are whole rows.
 template <class BufOf>
-static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, std::vector<const double*>& out, size_t row_len = 0, size_t pitch = 0)
+static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, std::vector<const double*>& out, const View* view = nullptr)
 {
     const int L = (int)h->devs.size(), W = h->world;
     out.assign(L, nullptr);
     const PtrKind kind = classify(src);
     if (kind == PK_DEVICE) {
-        if (row_len) return fail("internal: row views of device-resident arrays are not supported");
+        if (view) return fail("internal: views of device-resident arrays are not supported");
         out[0] = src;
         if (L > 1) {
             for (int i = 1; i < L; i++) {
@@ -332,33 +360,36 @@ static int distribute(fpt_handle* h, BufOf bufof, const double* src, size_t n, s
         }
         return 0;
     }
+    const View whole = View::contiguous(n * sizeof(double));
+    const View& vw = view ? *view : whole;
+    if (vw.total != n * sizeof(double)) return fail("internal: view of %zu bytes for %zu doubles", vw.total, n);
     const bool shard = W > 1 && n * sizeof(double) >= SHARD_MIN_BYTES;
+    std::vector<StagePool::Job> jobs;
     if (!shard) {
         for (int i = 0; i < L; i++) {
             Dev& d = *h->devs[i];
             CK(cudaSetDevice(d.dev));
             if (bufof(d).ensure(n * sizeof(double))) return 1;
             out[i] = bufof(d).d();
-            if (stage_to(h, d, bufof(d).p, src, n * sizeof(double), kind, row_len * sizeof(double), pitch * sizeof(double))) return 1;
-            if (copy_then_stream(d)) return 1;
+            if (stage_to(h, d, bufof(d).p, src, vw, 0, n * sizeof(double), kind, jobs)) return 1;
         }
+        if (stage_flush(h, jobs)) return 1;
+        for (int i = 0; i < L; i++)
+            if (copy_then_stream(*h->devs[i])) return 1;
         return 0;
     }
-    size_t part = ((n + W - 1) / W + 511) & ~(size_t)511;
-    if (row_len) {   // whole rows per part
-        const size_t rows = n / row_len;
-        part = (((rows + W - 1) / W + 63) & ~(size_t)63) * row_len;
-    }
+    const size_t part = ((n + W - 1) / W + 511) & ~(size_t)511;
     for (int i = 0; i < L; i++) {
         Dev& d = *h->devs[i];
         CK(cudaSetDevice(d.dev));
         if (bufof(d).ensure((size_t)W * part * sizeof(double))) return 1;
         out[i] = bufof(d).d();
         const size_t b = std::min(n, (size_t)d.grank * part), e = std::min(n, (size_t)(d.grank + 1) * part);
-        const double* from = row_len ? src + (b / row_len) * pitch : src + b;
-        if (stage_to(h, d, bufof(d).d() + b, from, (e - b) * sizeof(double), kind, row_len * sizeof(double), pitch * sizeof(double))) return 1;
-        if (copy_then_stream(d)) return 1;
+        if (stage_to(h, d, bufof(d).d() + b, src, vw, b * sizeof(double), (e - b) * sizeof(double), kind, jobs)) return 1;
     }
+    if (stage_flush(h, jobs)) return 1;
+    for (int i = 0; i < L; i++)
+        if (copy_then_stream(*h->devs[i])) return 1;
     NCK(nccl_api().GroupStart());
     for (int i = 0; i < L; i++) {
         Dev& d = *h->devs[i];
@@ -477,14 +508,12 @@ static int upload_end(fpt_handle* h, bool sync)
     return 0;
 }
 
-// the parts common to all routes: T1, T2 -> T1d, Pt hole part; fo, fv.  dT2[i] = T2 on GPU i for the route's own Qt build.
-static int upload_common(fpt_handle* h, const double* T1, const double* T2, const double* fo, const double* fv,
-                         std::vector<const double*>& dT2)
+// the parts common to all routes that do not depend on a slice of the occupied range: T1 -> T1d; fo, fv; Pt's zero padding
+static int upload_t1_f(fpt_handle* h, const double* T1, const double* fo, const double* fv)
 {
     const int o = h->o, v = h->v;
-    std::vector<const double*> dT1, dfo, dfv;
+    std::vector<const double*> dT1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sT1; }, T1, (size_t)o * v, dT1)) return 1;
-    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sT2; }, T2, (size_t)o * o * v * v, dT2)) return 1;
     for (size_t i = 0; i < h->devs.size(); i++) {
         Dev& d = *h->devs[i];
         CK(cudaSetDevice(d.dev));
@@ -494,88 +523,200 @@ static int upload_common(fpt_handle* h, const double* T1, const double* T2, cons
         if (!dev_in) h->h2d += (o + v) * sizeof(double);
         if (pt_zero_padding(d)) return 1;
         prep_t1<<<grid1d(o * v), 256, 0, d.stream>>>(d.prob, d.T1d.d(), dT1[i]);
-        prep_pt_hole<<<grid1d((i64)o * o * v * v), 256, 0, d.stream>>>(d.prob, d.Pt.d(), dT2[i]);
+        CK(cudaGetLastError());
+    }
+    h->launches += 1;
+    return 0;
+}
+
+// ---- symmetry-unique halves ---------------------------------------------------------------------------------------------------
+// The reference's algorithms are only consistent for inputs that carry the physical index symmetries:
+//     OVVV[i,a,b,c] = OVVV[i,a,c,b],   T2[i,j,a,b] = T2[j,i,b,a],   OVOV[i,a,j,b] = OVOV[j,b,i,a].
+// For pageable host inputs only the half the symmetry leaves free crosses PCIe -- b <= c of OVVV, a <= b of T2 and OVOV: contiguous
+// prefixes of the slowest index's slabs, so the host threads still stream through memory -- and the device kernels write the mirror
+// images (prep_pt_particle_tri, expand_*_tri).  The bytes the host has to touch, which bound the end-to-end time of a multi-GPU
+// call, drop from 417 to 215 MB at C4.  Arrays are sampled first; any that does not look symmetric is uploaded in full, as is
+// everything after fpt_set_symmetric_inputs(h, 0).
+static bool sample_symmetric(const double* A, size_t n0, size_t n1, size_t n2, size_t n3, int kind)
+{
+    // kind 0: A[i,a,b,c] vs A[i,a,c,b];  1: A[i,j,a,b] vs A[j,i,b,a];  2: A[i,a,j,b] vs A[j,b,i,a]   (first index fastest)
+    unsigned long long s = 0x9E3779B97F4A7C15ull;
+    auto next = [&s](size_t m) { s = s * 6364136223846793005ull + 1442695040888963407ull; return (size_t)((s >> 33) % m); };
+    for (int t = 0; t < 512; t++) {
+        const size_t i0 = next(n0), i1 = next(n1), i2 = next(n2), i3 = next(n3);
+        const double x = A[i0 + n0 * (i1 + n1 * (i2 + n2 * i3))];
+        double y;
+        if (kind == 0) y = A[i0 + n0 * (i1 + n1 * (i3 + n2 * i2))];
+        else if (kind == 1) y = A[i1 + n0 * (i0 + n1 * (i3 + n2 * i2))];
+        else y = A[i2 + n0 * (i3 + n1 * (i0 + n2 * i1))];
+        if (fabs(x - y) > 1e-12 * (fabs(x) + fabs(y)) + 1e-300) return false;
+    }
+    return true;
+}
+static bool use_half(const fpt_handle* h, const double* A, size_t n0, size_t n1, size_t n2, size_t n3, int kind)
+{
+    if (!h->sym_inputs || classify(A) != PK_PAGEABLE) return false;
+    if (n0 * n1 * n2 * n3 * sizeof(double) < ((size_t)4 << 20)) return false;   // not worth a second kernel
+    return sample_symmetric(A, n0, n1, n2, n3, kind);
+}
+
+// T2 -> Pt hole part and Qt (hole part of Qt from the whole OOOV on the GPUs, dOOOV; empty on the density-fitted route)
+static int upload_t2(fpt_handle* h, const double* T2, const std::vector<const double*>& dOOOV)
+{
+    const int o = h->o, v = h->v;
+    const size_t o2 = (size_t)o * o;
+    std::vector<const double*> dT2;
+    const bool half = use_half(h, T2, o, o, v, v, 1);
+    if (half) {
+        View vw;
+        for (int b = 0; b < v; b++) vw.add((size_t)b * o2 * v * sizeof(double), 1, o2 * (b + 1) * sizeof(double), o2 * (b + 1) * sizeof(double));
+        std::vector<const double*> dTri;
+        if (distribute(h, [](Dev& d) -> DevBuf& { return d.sTri; }, T2, vw.total / sizeof(double), dTri, &vw)) return 1;
+        dT2.resize(h->devs.size());
+        for (size_t i = 0; i < h->devs.size(); i++) {
+            Dev& d = *h->devs[i];
+            CK(cudaSetDevice(d.dev));
+            if (d.sT2.ensure(o2 * v * v * sizeof(double))) return 1;
+            expand_t2_tri<<<grid1d((i64)o2 * v * v), 256, 0, d.stream>>>(o, v, d.sT2.d(), dTri[i]);
+            CK(cudaGetLastError());
+            dT2[i] = d.sT2.d();
+        }
+        h->launches += 1;
+    } else if (distribute(h, [](Dev& d) -> DevBuf& { return d.sT2; }, T2, o2 * v * v, dT2)) return 1;
+    for (size_t i = 0; i < h->devs.size(); i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        const Problem& P = d.prob;
+        prep_pt_hole<<<grid1d((i64)o2 * v * v), 256, 0, d.stream>>>(P, d.Pt.d(), dT2[i]);
+        prep_qt<<<grid1d((i64)o2 * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], dOOOV.empty() ? nullptr : dOOOV[i]);
         CK(cudaGetLastError());
     }
     h->launches += 2;
+    return 0;
+}
+
+// OVOV -> OV2
+static int upload_ovov(fpt_handle* h, const double* OVOV)
+{
+    const int o = h->o, v = h->v;
+    const size_t o2 = (size_t)o * o;
+    std::vector<const double*> dOVOV;
+    const bool half = use_half(h, OVOV, o, v, o, v, 2);
+    if (half) {
+        View vw;   // for every (b, j): the prefix a <= b of the (i, a) plane
+        for (int b = 0; b < v; b++)
+            vw.add((size_t)b * o2 * v * sizeof(double), (size_t)o, (size_t)o * (b + 1) * sizeof(double), (size_t)o * v * sizeof(double));
+        std::vector<const double*> dTri;
+        if (distribute(h, [](Dev& d) -> DevBuf& { return d.sTri2; }, OVOV, vw.total / sizeof(double), dTri, &vw)) return 1;
+        dOVOV.resize(h->devs.size());
+        for (size_t i = 0; i < h->devs.size(); i++) {
+            Dev& d = *h->devs[i];
+            CK(cudaSetDevice(d.dev));
+            if (d.sOVOV.ensure(o2 * v * v * sizeof(double))) return 1;
+            expand_ovov_tri<<<grid1d((i64)o2 * v * v), 256, 0, d.stream>>>(o, v, d.sOVOV.d(), dTri[i]);
+            CK(cudaGetLastError());
+            dOVOV[i] = d.sOVOV.d();
+        }
+        h->launches += 1;
+    } else if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOVOV; }, OVOV, o2 * v * v, dOVOV)) return 1;
+    for (size_t i = 0; i < h->devs.size(); i++) {
+        Dev& d = *h->devs[i];
+        CK(cudaSetDevice(d.dev));
+        prep_ov2<<<grid1d(ov2_elems(d.prob)), 256, 0, d.stream>>>(d.prob, d.OV2.d(), dOVOV[i]);
+        CK(cudaGetLastError());
+    }
+    h->launches += 1;
     return 0;
 }
 
 // OVVV[p0 : p0+np, :, :, :] -> Pt particle part on every GPU.
-//  * chunked: in chunks over the slowest index d; chunk c is staged (and gathered) into buffer c & 1 while the prep kernel of chunk
-//    c-1 runs out of the other one;
-//  * !chunked: one transfer of the whole sub-block into its own buffer (second phase of a split call, see triples_conv: nothing on
-//    the compute stream can run before the first phase's kernel has finished, so the buffer cannot be recycled anyway).
-// A proper sub-range of p is a row view of the host array (rows of np doubles, o apart) and arrives packed.
-static int upload_ovvv(fpt_handle* h, const double* OVVV, int p0, int np, bool chunked)
+//  * phase 0: in chunks of at most 64 MB over the slowest index c; chunk n is staged (and gathered) into buffer n & 1 while the prep
+//    kernel of chunk n-1 runs out of the other one;
+//  * phase > 0 (later phases of a split call, see triples_conv): one transfer of the whole sub-block into the phase's own buffer --
+//    nothing on the compute stream can run before the previous phase's kernel has finished, so a buffer could not be recycled anyway.
+//  * half: only the prefix b <= c of every c crosses PCIe, the mirror image is written on the device (see use_half).
+// A proper sub-range of p is a view of rows of np doubles, o apart, and arrives packed.
+static int upload_ovvv(fpt_handle* h, const double* OVVV, int p0, int np, int phase, bool half)
 {
+    const bool chunked = phase == 0;
     const int o = h->o, v = h->v, L = (int)h->devs.size();
-    const size_t slab = (size_t)o * v * v;            // doubles per d in the caller's array
-    const size_t cslab = (size_t)np * v * v;          // doubles per d as they arrive
+    const size_t ov = (size_t)o * v, npv = (size_t)np * v;
     const bool whole = (p0 == 0 && np == o);
     const bool on_dev = classify(OVVV) == PK_DEVICE;
+    if (on_dev && (!whole || half)) return fail("internal: views of device-resident arrays are not supported");
+    const size_t budget = (chunked && (!on_dev || L > 1)) ? (size_t)64 << 20 : ~(size_t)0;
     std::vector<const double*> dChunk;
-    int dchunk = v;
-    if (chunked && (!on_dev || L > 1)) {
-        const size_t budget = (size_t)64 << 20;
-        dchunk = (int)std::max<size_t>(1, budget / (cslab * sizeof(double)));
-        if (dchunk > v) dchunk = v;
-    }
-    int c = 0;
-    for (int d0 = 0; d0 < v; d0 += dchunk, c++) {
-        const int dn = std::min(dchunk, v - d0);
-        const int bsel = c & 1;
-        if (chunked && c >= 2)
+    int n = 0;
+    for (int c0 = 0; c0 < v; n++) {
+        // chunk [c0, c0 + cn): as many c as fit the budget (at least one)
+        int cn = 0;
+        size_t elems = 0;
+        while (c0 + cn < v) {
+            const size_t add = npv * (half ? (size_t)(c0 + cn + 1) : (size_t)v);
+            if (cn > 0 && (elems + add) * sizeof(double) > budget) break;
+            elems += add;
+            cn++;
+        }
+        const int bsel = n & 1;
+        if (chunked && n >= 2)
             for (Dev* dp : h->devs) {   // the buffer's previous content has been consumed
                 CK(cudaSetDevice(dp->dev));
                 CK(cudaStreamWaitEvent(dp->copy, dp->ev_free[bsel], 0));
             }
-        auto buf = [bsel, chunked](Dev& d) -> DevBuf& { return chunked ? d.sChunk[bsel] : d.sPhaseB; };
-        if (whole) {
-            if (distribute(h, buf, OVVV + (size_t)d0 * slab, (size_t)dn * slab, dChunk)) return 1;
+        auto buf = [bsel, phase](Dev& d) -> DevBuf& { return phase == 0 ? d.sChunk[bsel] : d.sPhase[phase]; };
+        if (whole && !half) {
+            if (distribute(h, buf, OVVV + (size_t)c0 * ov * v, elems, dChunk)) return 1;
         } else {
-            if (distribute(h, buf, OVVV + (size_t)d0 * slab + p0, (size_t)dn * cslab, dChunk, (size_t)np, (size_t)o)) return 1;
+            View vw;
+            for (int c = c0; c < c0 + cn; c++)
+                vw.add(((size_t)c * ov * v + p0) * sizeof(double), (size_t)v * (half ? c + 1 : v), (size_t)np * sizeof(double), (size_t)o * sizeof(double));
+            if (distribute(h, buf, OVVV, elems, dChunk, &vw)) return 1;
         }
         for (int i = 0; i < L; i++) {
             Dev& d = *h->devs[i];
             CK(cudaSetDevice(d.dev));
-            dim3 grid((unsigned)(((size_t)np * v + 31) / 32), (unsigned)((dn + 31) / 32), (unsigned)v);
-            prep_pt_particle<<<grid, dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], d0, dn, p0, np);
+            const unsigned gx = (unsigned)((npv + 31) / 32);
+            if (half) {
+                prep_pt_particle_tri<<<dim3(gx, (unsigned)((cn + 31) / 32), (unsigned)(c0 + cn)), dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], c0, cn, p0, np, 0);
+                prep_pt_particle_tri<<<dim3(gx, (unsigned)((c0 + cn + 30) / 32 + 1), (unsigned)cn), dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], c0, cn, p0, np, 1);
+            } else {
+                prep_pt_particle<<<dim3(gx, (unsigned)((cn + 31) / 32), (unsigned)v), dim3(32, 8), 0, d.stream>>>(d.prob, d.Pt.d(), dChunk[i], c0, cn, p0, np);
+            }
             CK(cudaGetLastError());
             if (chunked) CK(cudaEventRecord(d.ev_free[bsel], d.stream));
         }
-        h->launches += 1;
+        h->launches += half ? 2 : 1;
+        c0 += cn;
     }
     return 0;
 }
 
-// everything of a conventional upload except OVVV
-static int upload_conv_small(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OOOV, const double* OVOV,
-                             const double* fo, const double* fv)
+// Conventional upload, OVVV in the occupied slices pb[0] = 0 < pb[1] < ... < pb[nph] = o, one after the other; after slice t,
+// `after_slice(t)` may enqueue work on the compute streams (the kernel over the triplets with i < pb[t+1], see triples_conv).
+// Everything else goes first, whole.
+template <class After>
+static int upload_conv_slices(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
+                              const double* OVOV, const double* fo, const double* fv, const int* pb, int nph, After after_slice)
 {
     if (setup_problem(h, o, v)) return 1;
-    const int L = (int)h->devs.size();
-    std::vector<const double*> dT2, dOOOV, dOVOV;
-    if (upload_common(h, T1, T2, fo, fv, dT2)) return 1;
+    if (upload_t1_f(h, T1, fo, fv)) return 1;
+    std::vector<const double*> dOOOV;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOOOV; }, OOOV, (size_t)o * o * o * v, dOOOV)) return 1;
-    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sOVOV; }, OVOV, (size_t)o * v * o * v, dOVOV)) return 1;
-    for (int i = 0; i < L; i++) {
-        Dev& d = *h->devs[i];
-        CK(cudaSetDevice(d.dev));
-        const Problem& P = d.prob;
-        prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], dOOOV[i]);
-        prep_ov2<<<grid1d(ov2_elems(P)), 256, 0, d.stream>>>(P, d.OV2.d(), dOVOV[i]);
-        CK(cudaGetLastError());
+    if (upload_t2(h, T2, dOOOV)) return 1;
+    if (upload_ovov(h, OVOV)) return 1;
+    const bool half = use_half(h, OVVV, o, v, v, v, 0);
+    for (int t = 0; t < nph; t++) {
+        if (upload_ovvv(h, OVVV, pb[t], pb[t + 1] - pb[t], t, half)) return 1;
+        if (after_slice(t)) return 1;
     }
-    h->launches += 2;
     return 0;
 }
 
 static int upload_conv_impl(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,
                             const double* OOOV, const double* OVOV, const double* fo, const double* fv, bool sync)
 {
-    if (upload_conv_small(h, o, v, T1, T2, OOOV, OVOV, fo, fv)) return 1;
-    if (upload_ovvv(h, OVVV, 0, o, true)) return 1;
+    const int pb[2] = {0, o};
+    if (upload_conv_slices(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, pb, 1, [](int) { return 0; })) return 1;
     return upload_end(h, sync);
 }
 
@@ -604,8 +745,10 @@ static int upload_df_impl(fpt_handle* h, int o, int v, int naux, const double* T
 {
     if (setup_problem(h, o, v)) return 1;
     const int L = (int)h->devs.size(), W = h->world;
-    std::vector<const double*> dT2, dBOO, dBOV, dBVV;
-    if (upload_common(h, T1, T2, fo, fv, dT2)) return 1;
+    std::vector<const double*> dBOO, dBOV, dBVV;
+    if (upload_t1_f(h, T1, fo, fv)) return 1;
+    // Pt hole part and Qt particle part from T2; Qt's hole part OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z] below   (DFERI.jl:88-112)
+    if (upload_t2(h, T2, {})) return 1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOO; }, BOO, (size_t)naux * o * o, dBOO)) return 1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOV; }, BOV, (size_t)naux * o * v, dBOV)) return 1;
     if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBVV; }, BVV, (size_t)naux * v * v, dBVV)) return 1;
@@ -615,9 +758,6 @@ static int upload_df_impl(fpt_handle* h, int o, int v, int naux, const double* T
         const Problem& P = d.prob;
         GemmOut out{};
         out.P = P;
-        // Qt: particle part from T2, hole part OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z]          (DFERI.jl:88-112)
-        prep_qt<<<grid1d((i64)o * o * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], nullptr);
-        CK(cudaGetLastError());
         out.C = d.Qt.d();
         CK(gemm_tn_launch<EPI_QT_HOLE>(d.stream, dBOO[i], rowmap_identity(), dBOV[i], rowmap_identity(), (i64)o * o, o * v, naux, out));
         // OV2: OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z]                                            (DFERI.jl:139-154)
@@ -632,7 +772,7 @@ static int upload_df_impl(fpt_handle* h, int o, int v, int naux, const double* T
         const RowMap mB{0, v, 1, v};    // n = d + v*x   ->  BVV row x + v*d
         CK(gemm_tn_launch<EPI_PT>(d.stream, dBOV[i], mA, dBVV[i], mB, (i64)(p1 - p0) * v, v * v, naux, out));
     }
-    h->launches += 4;
+    h->launches += 3;
     if (W > 1) {
         const size_t pslab = (size_t)h->devs[0]->prob.vp * h->devs[0]->prob.vp * h->devs[0]->prob.Kp;
         NCK(nccl_api().GroupStart());
@@ -701,7 +841,7 @@ static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begi
     int grid = d.n_sm;
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
     CK(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
-    CK(cudaEventRecord(phase ? d.ev0b : d.ev0, d.stream));
+    CK(cudaEventRecord(d.ev0[phase], d.stream));
     unsigned long long* ctr = (unsigned long long*)d.counter.p;
 #ifdef FPT_WITH_VARIANT2
     if (h->kernel_variant == 2) {
@@ -715,7 +855,7 @@ static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begi
         triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
     d.last_grid = grid;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(phase ? d.ev1b : d.ev1, d.stream));
+    CK(cudaEventRecord(d.ev1[phase], d.stream));
     reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), phase);
     CK(cudaGetLastError());
     d.shard_b = item_begin;
@@ -761,7 +901,7 @@ static int compute_enqueue(fpt_handle* h, i64 item_begin, i64 item_end)
     if (item_end < 0 || item_end > h->nitems) item_end = h->nitems;
     if (item_begin < 0) item_begin = 0;
     if (item_begin > item_end) item_begin = item_end;
-    h->split = false;
+    h->nphase = 1;
     if (compute_launch_all(h, h->tw_begin, h->tw_count, item_begin, item_end, 0)) return 1;
     return compute_collect(h, item_end - item_begin);
 }
@@ -772,10 +912,13 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
     for (Dev* dp : h->devs) {
         CK(cudaSetDevice(dp->dev));
         CK(cudaStreamSynchronize(dp->stream));
-        float ms = 0.f, msb = 0.f;
-        CK(cudaEventElapsedTime(&ms, dp->ev0, dp->ev1));
-        if (h->split) CK(cudaEventElapsedTime(&msb, dp->ev0b, dp->ev1b));
-        if (ms + msb > ms_max) ms_max = ms + msb;
+        float sum = 0.f;
+        for (int t = 0; t < h->nphase; t++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, dp->ev0[t], dp->ev1[t]));
+            sum += ms;
+        }
+        if (sum > ms_max) ms_max = sum;
     }
     if (Et) *Et = *h->res_pinned;
     // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
@@ -785,14 +928,14 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
     h->last.n_items = h->pend_items;
     h->last.n_triplets = (long long)ntrip;
     h->last.flops = 12.0 * v * (double)v * v * (v + o) * ntrip * (h->nitems ? (double)h->pend_items / (double)h->nitems : 0.0);
-    h->last.n_launches = h->launches + (h->split ? 4 : 2) * (int)h->devs.size();
+    h->last.n_launches = h->launches + 2 * h->nphase * (int)h->devs.size();
     h->last.n_sm = h->devs[0]->n_sm;
     // timeline of the first GPU, milliseconds since the upload began (entries stay 0 when the compute followed an older upload)
     Dev& d0 = *h->devs[0];
     CK(cudaSetDevice(d0.dev));
     for (double& t : h->timeline) t = 0.0;
     h->timeline[0] = h->stage_host_ms;
-    cudaEvent_t marks[5] = {d0.tl[1], d0.tl[2], d0.ev0, h->split ? d0.ev1b : d0.ev1, d0.tl[5]};
+    cudaEvent_t marks[5] = {d0.tl[1], d0.tl[2], d0.ev0[0], d0.ev1[h->nphase - 1], d0.tl[5]};
     for (int t = 0; t < 5; t++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, d0.tl[0], marks[t]) == cudaSuccess) h->timeline[1 + t] = ms;
@@ -850,20 +993,34 @@ static int finish_call(fpt_handle* h, bool async, wall::time_point t0, double* E
     return finish_tail(h, async, t0, Et, st);
 }
 
-// Where to split a one-call conventional evaluation (0: do not): host-resident OVVV small enough that the second phase's packed copy
-// (half of it, on every GPU) is cheap to hold, enough occupied orbitals for two phases, and a full default work list.  pA is a multiple
-// of 4 (32-byte rows for the streaming copies) near o/2: the first phase is then (pA/o)^3 = 1/8 of the triplets -- long enough to
-// cover the staging of the other half of OVVV.  FERMI_PT_B200_SPLIT=0 switches it off.
-static int split_point(fpt_handle* h, int o, int v, const double* OVVV)
+// Phases of a one-call conventional evaluation.  The triplets with i < pb only read the operands of the occupied indices p < pb, and
+// they are the first num_triplets(pb) entries of the reference's triplet list (ijk.jl:49,63,83 loops i slowest).  So the call is cut
+// at occupied boundaries 0 = pb[0] < pb[1] < ... < pb[n] = o:  upload everything but OVVV, then OVVV[p < pb[1]]; launch the kernel over
+// that window; while it runs, the host threads and the DMA engines bring OVVV[pb[1] <= p < pb[2]]; and so on.  The kernel starts after
+// 1/n of OVVV has arrived, and the rest of the host-bound staging time -- the part of an 8-GPU call that does not shrink with the
+// number of GPUs -- disappears behind the kernels: phase t holds (pb[t+1]^3 - pb[t]^3) / o^3 of the work, which covers the staging
+// of slice t+1 as long as the whole kernel takes longer than the whole upload.
+// Conditions: host-resident OVVV small enough that the later slices (packed copies on every GPU) are cheap to hold, enough occupied
+// orbitals, a full default work list.  Boundaries are multiples of 4 (32-byte rows for the streaming copies).
+// FERMI_PT_B200_SPLIT = number of phases wanted (default 2; 0 or 1: no split; more phases start the kernel earlier but re-read
+// more of the host array's cache lines -- a slice is 8 (o / nph) bytes of every 8 o-byte row; measured at C4: no gain beyond 2).
+static int split_points(fpt_handle* h, int o, int v, const double* T2, const double* OVVV, const double* OVOV, int* pb)
 {
-    if (const char* e = getenv("FERMI_PT_B200_SPLIT"))
-        if (atoi(e) == 0) return 0;
-    if (o < 8 || classify(OVVV) == PK_DEVICE) return 0;
-    if ((double)o * v * v * v * sizeof(double) > 4e9) return 0;
-    if (h->dbg_flags || h->profiling || h->item_order != 1) return 0;
-    int pA = ((o / 2) + 3) & ~3;
-    if (pA >= o) pA = o / 2;
-    return pA;
+    int want = 2;
+    if (const char* e = getenv("FERMI_PT_B200_SPLIT")) want = atoi(e);
+    if (want > MAX_PHASES) want = MAX_PHASES;
+    pb[0] = 0;
+    pb[1] = o;
+    if (want < 2 || o < 8 || classify(OVVV) == PK_DEVICE) return 1;
+    if ((double)o * v * v * v * sizeof(double) > 4e9) return 1;
+    if (h->dbg_flags || h->profiling || h->item_order != 1) return 1;
+    int n = 0;
+    for (int t = 1; t < want; t++) {
+        const int b = (int)(((i64)o * t / want + 2) & ~3);
+        if (b > pb[n] && b < o) pb[++n] = b;
+    }
+    pb[++n] = o;
+    return n;
 }
 
 static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV, const double* OOOV,
@@ -875,27 +1032,24 @@ static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const dou
     const auto t0 = wall::now();
     if (admit_device_inputs(h, who, {T1, T2, OVVV, OOOV, OVOV, fo, fv})) return 1;
     upload_begin(h);
-    const int pA = split_point(h, o, v, OVVV);
-    if (pA <= 0) {
+    int pb[MAX_PHASES + 1];
+    const int nph = split_points(h, o, v, T2, OVVV, OVOV, pb);
+    if (nph <= 1) {
         if (upload_conv_impl(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, false)) return 1;
         return finish_call(h, async, t0, Et, st);
     }
-    // Split call.  The triplets with i < pA only read the operands of the occupied indices p < pA, and they are the first uA entries of
-    // the reference's triplet list (ijk.jl:49,63,83 loops i slowest).  So: upload everything but OVVV, then OVVV[p < pA]; launch the
-    // kernel over that window; while it runs, the host threads and the DMA engines bring OVVV[p >= pA]; then the rest of the list.
-    // The second half of the host-bound staging time -- the part of an 8-GPU call that does not shrink with the number of GPUs --
-    // disappears behind the first kernel.
-    if (upload_conv_small(h, o, v, T1, T2, OOOV, OVOV, fo, fv)) return 1;
-    if (upload_ovvv(h, OVVV, 0, pA, true)) return 1;
-    const i64 uA = num_triplets(pA), uAll = num_triplets(o), nb = h->devs[0]->prob.nb;
-    h->split = true;
-    if (compute_launch_all(h, 0, uA, 0, nb * uA, 0)) return 1;
-    if (upload_ovvv(h, OVVV, pA, o - pA, false)) return 1;
-    if (upload_end(h, false)) return 1;
-    if (compute_launch_all(h, uA, uAll - uA, 0, nb * (uAll - uA), 1)) return 1;
+    h->nphase = nph;
+    auto launch_phase = [&](int t) -> int {
+        if (t == nph - 1 && upload_end(h, false)) return 1;
+        const i64 nb = h->devs[0]->prob.nb;
+        const i64 u0 = num_triplets(pb[t]), u1 = num_triplets(pb[t + 1]);
+        return compute_launch_all(h, u0, u1 - u0, 0, nb * (u1 - u0), t);
+    };
+    if (upload_conv_slices(h, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv, pb, nph, launch_phase)) return 1;
+    const i64 nb = h->devs[0]->prob.nb;
     h->last = fpt_stats{};
     h->last.h2d_bytes = h->h2d;
-    if (compute_collect(h, nb * uAll)) return 1;
+    if (compute_collect(h, nb * num_triplets(o))) return 1;
     return finish_tail(h, async, t0, Et, st);
 }
 
@@ -975,12 +1129,12 @@ static int upload_ao_impl(fpt_handle* h, int nbf, int o, int v, const double* T1
     const double *dCo = Co, *dCv = Cv;
     if (classify(Co) != PK_DEVICE) {
         if (d.sCo.ensure((size_t)nbf * o * sizeof(double))) return 1;
-        if (stage_to(h, d, d.sCo.p, Co, (size_t)nbf * o * sizeof(double), classify(Co))) return 1;
+        if (stage_now(h, d, d.sCo.p, Co, (size_t)nbf * o * sizeof(double), classify(Co))) return 1;
         dCo = d.sCo.d();
     }
     if (classify(Cv) != PK_DEVICE) {
         if (d.sCv.ensure((size_t)nbf * v * sizeof(double))) return 1;
-        if (stage_to(h, d, d.sCv.p, Cv, (size_t)nbf * v * sizeof(double), classify(Cv))) return 1;
+        if (stage_now(h, d, d.sCv.p, Cv, (size_t)nbf * v * sizeof(double), classify(Cv))) return 1;
         dCv = d.sCv.d();
     }
     if (copy_then_stream(d)) return 1;
@@ -1003,7 +1157,7 @@ static int upload_ao_impl(fpt_handle* h, int nbf, int o, int v, const double* T1
             if (kind != PK_DEVICE) {
                 const int bsel = c & 1;
                 if (c >= 2) CK(cudaStreamWaitEvent(d.copy, d.ev_free[bsel], 0));
-                if (stage_to(h, d, d.sChunk[bsel].p, src, (size_t)sn * n3 * sizeof(double), kind)) return 1;
+                if (stage_now(h, d, d.sChunk[bsel].p, src, (size_t)sn * n3 * sizeof(double), kind)) return 1;
                 if (copy_then_stream(d)) return 1;
                 src = d.sChunk[bsel].d();
             }
@@ -1097,12 +1251,12 @@ static int upload_ao_sparse_impl(fpt_handle* h, int nbf, int o, int v, const dou
         const double* dvals = vals;
         if (classify(idx) != PK_DEVICE) {
             if (d.sIdx.ensure((size_t)nint * 4 * index_bytes)) return 1;
-            if (stage_to(h, d, d.sIdx.p, idx, (size_t)nint * 4 * index_bytes, classify(idx))) return 1;
+            if (stage_now(h, d, d.sIdx.p, idx, (size_t)nint * 4 * index_bytes, classify(idx))) return 1;
             didx = d.sIdx.p;
         }
         if (classify(vals) != PK_DEVICE) {
             if (d.sVals.ensure((size_t)nint * sizeof(double))) return 1;
-            if (stage_to(h, d, d.sVals.p, vals, (size_t)nint * sizeof(double), classify(vals))) return 1;
+            if (stage_now(h, d, d.sVals.p, vals, (size_t)nint * sizeof(double), classify(vals))) return 1;
             dvals = d.sVals.d();
         }
         if (copy_then_stream(d)) return 1;
@@ -1185,21 +1339,21 @@ extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, doubl
     CK(cudaStreamSynchronize(d.stream));
     CK(cudaGetLastError());
     // calibrate launch count
-    CK(cudaEventRecord(d.ev0, d.stream));
+    CK(cudaEventRecord(d.ev0[0], d.stream));
     launch();
-    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaEventRecord(d.ev1[0], d.stream));
     CK(cudaStreamSynchronize(d.stream));
     float ms1 = 0.f;
-    CK(cudaEventElapsedTime(&ms1, d.ev0, d.ev1));
+    CK(cudaEventElapsedTime(&ms1, d.ev0[0], d.ev1[0]));
     int reps = (int)(ms_target / (ms1 > 1e-3f ? ms1 : 1e-3f));
     if (reps < 1) reps = 1;
     if (reps > 20000) reps = 20000;
-    CK(cudaEventRecord(d.ev0, d.stream));
+    CK(cudaEventRecord(d.ev0[0], d.stream));
     for (int t = 0; t < reps; t++) launch();
-    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaEventRecord(d.ev1[0], d.stream));
     CK(cudaStreamSynchronize(d.stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    CK(cudaEventElapsedTime(&ms, d.ev0[0], d.ev1[0]));
     *tflops = fl * reps / (ms * 1e-3) / 1e12;
     return 0;
 }
@@ -1225,13 +1379,13 @@ extern "C" int fpt_gemm_bench(fpt_handle* h, long long M, int N, int K, int reps
     out.C = C.d();
     out.ldc = M;
     cudaError_t e = gemm_tn_launch<EPI_COLMAJOR>(d.stream, A.d(), rowmap_identity(), B.d(), rowmap_identity(), M, N, K, out);
-    cudaEventRecord(d.ev0, d.stream);
+    cudaEventRecord(d.ev0[0], d.stream);
     for (int r = 0; r < reps && e == cudaSuccess; r++)
         e = gemm_tn_launch<EPI_COLMAJOR>(d.stream, A.d(), rowmap_identity(), B.d(), rowmap_identity(), M, N, K, out);
-    cudaEventRecord(d.ev1, d.stream);
+    cudaEventRecord(d.ev1[0], d.stream);
     cudaError_t e2 = cudaStreamSynchronize(d.stream);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, d.ev0, d.ev1);
+    cudaEventElapsedTime(&ms, d.ev0[0], d.ev1[0]);
     A.release(); B.release(); C.release();
     if (e != cudaSuccess || e2 != cudaSuccess) return fail("fpt_gemm_bench: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     *tflops = 2.0 * (double)M * N * K * reps / (ms * 1e-3) / 1e12;
@@ -1346,13 +1500,13 @@ extern "C" int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* 
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<d.n_sm, threads, smem, d.stream>>>(d.out.d(), iters, 1e-3);
     CK(cudaStreamSynchronize(d.stream));
-    CK(cudaEventRecord(d.ev0, d.stream));
+    CK(cudaEventRecord(d.ev0[0], d.stream));
     for (int r = 0; r < 5; r++) k<<<d.n_sm, threads, smem, d.stream>>>(d.out.d(), iters, 1e-3);
-    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaEventRecord(d.ev1[0], d.stream));
     CK(cudaStreamSynchronize(d.stream));
     CK(cudaGetLastError());
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+    CK(cudaEventElapsedTime(&ms, d.ev0[0], d.ev1[0]));
     *tflops = 5.0 * d.n_sm * warps_per_sm * (double)iters * ilp * 512.0 / (ms * 1e-3) / 1e12;
     return 0;
 }

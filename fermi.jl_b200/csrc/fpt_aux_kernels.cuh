@@ -106,6 +106,76 @@ __global__ void prep_ov2(Problem P, double* OV2, const double* __restrict__ OVOV
     }
 }
 
+// ---- symmetry-unique halves (host inputs cross PCIe as the half the index symmetry leaves free, fpt_api.cu) -----------------------
+FPT_HD i64 tri(i64 c) { return c * (c + 1) / 2; }
+
+// OVVV[i,a,b,c] = OVVV[i,a,c,b]: the packed source holds, for c in [c0, c0+cn), the prefix b <= c of the slice p in [p0, p0+np):
+//     src[np v (tri(c) - tri(c0)) + pl + np (y + v b)] = OVVV[p0+pl, y, b, c].
+// mirror = 0: Pt[p][y][x=b][kappa=c] (one block row per b, tiled transpose over (p y, c));
+// mirror = 1: Pt[p][y][x=c][kappa=b] for b < c (one block row per c, tiled transpose over (p y, b)).
+__global__ void prep_pt_particle_tri(Problem P, double* Pt, const double* __restrict__ src, int c0, int cn, int p0, int np, int mirror)
+{
+    __shared__ double tile[32][33];
+    const int v = P.v;
+    const i64 npv = (i64)np * v;
+    const i64 py0 = (i64)blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (!mirror) {
+        const int b = blockIdx.z, cc0 = blockIdx.y * 32;
+        if (c0 + cc0 + 31 < b) return;
+        for (int kk = 0; kk < 32; kk += 8) {
+            const int cc = cc0 + ty + kk, c = c0 + cc;
+            const i64 py = py0 + tx;
+            if (cc < cn && c >= b && py < npv) tile[ty + kk][tx] = src[npv * (tri(c) - tri(c0) + b) + py];
+        }
+        __syncthreads();
+        for (int kk = 0; kk < 32; kk += 8) {
+            const i64 py = py0 + ty + kk;
+            const int cc = cc0 + tx, c = c0 + cc;
+            if (cc < cn && c >= b && py < npv) Pt[pt_row(P, p0 + (int)(py % np), (int)(py / np), b) + c] = tile[tx][ty + kk];
+        }
+    } else {
+        const int c = c0 + blockIdx.z, b0 = blockIdx.y * 32;
+        if (b0 >= c) return;
+        for (int kk = 0; kk < 32; kk += 8) {
+            const int b = b0 + ty + kk;
+            const i64 py = py0 + tx;
+            if (b < c && py < npv) tile[ty + kk][tx] = src[npv * (tri(c) - tri(c0) + b) + py];
+        }
+        __syncthreads();
+        for (int kk = 0; kk < 32; kk += 8) {
+            const i64 py = py0 + ty + kk;
+            const int b = b0 + tx;
+            if (b < c && py < npv) Pt[pt_row(P, p0 + (int)(py % np), (int)(py / np), c) + b] = tile[tx][ty + kk];
+        }
+    }
+}
+
+// T2[i,j,a,b] = T2[j,i,b,a]: src holds a <= b, src[o^2 (tri(b) + a) + i + o j] = T2[i,j,a,b]; writes the full array
+__global__ void expand_t2_tri(int o, int v, double* __restrict__ T2, const double* __restrict__ src)
+{
+    const i64 o2 = (i64)o * o, n = o2 * v * v;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % o), j = (int)((idx / o) % o);
+        const i64 t = idx / o2;
+        const int a = (int)(t % v), b = (int)(t / v);
+        T2[idx] = a <= b ? src[o2 * (tri(b) + a) + i + (i64)o * j] : src[o2 * (tri(a) + b) + j + (i64)o * i];
+    }
+}
+
+// OVOV[i,a,j,b] = OVOV[j,b,i,a]: src holds a <= b, src[o^2 tri(b) + j o (b+1) + i + o a] = OVOV[i,a,j,b]; writes the full array
+__global__ void expand_ovov_tri(int o, int v, double* __restrict__ OVOV, const double* __restrict__ src)
+{
+    const i64 o2 = (i64)o * o, n = o2 * v * v;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % o);
+        i64 t = idx / o;
+        const int a = (int)(t % v); t /= v;
+        const int j = (int)(t % o), b = (int)(t / o);
+        OVOV[idx] = a <= b ? src[o2 * tri(b) + (i64)j * o * (b + 1) + i + (i64)o * a] : src[o2 * tri(a) + (i64)i * o * (a + 1) + j + (i64)o * b];
+    }
+}
+
 // T1d[p][x] = T1[p,x]
 __global__ void prep_t1(Problem P, double* T1d, const double* __restrict__ T1)
 {

@@ -117,6 +117,7 @@ inline int nccl_load()
     } while (0)
 
 // ---- one GPU of a handle -----------------------------------------------------------------------------------------------
+constexpr int MAX_PHASES = 4;   // kernels of one split call (triples_conv in fpt_api.cu)
 constexpr int NTL = 6;   // timeline events: upload begin, last H2D done, operands ready, kernel begin, kernel end, result ready
 struct Dev {
     int dev = 0;
@@ -125,8 +126,7 @@ struct Dev {
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // kernels + collectives
     cudaStream_t copy = nullptr;     // host -> device DMAs
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;            // around the fused kernel
-    cudaEvent_t ev0b = nullptr, ev1b = nullptr;          // around the second kernel of a split call
+    cudaEvent_t ev0[MAX_PHASES] = {}, ev1[MAX_PHASES] = {};   // around the fused kernel of each phase of a call (one phase unless split)
     cudaEvent_t ev_copy = nullptr, ev_start = nullptr;   // copy -> stream / stream -> copy hand-offs
     cudaEvent_t ev_free[2] = {nullptr, nullptr};         // OVVV chunk buffer c&1 has been consumed by its prep kernel
     cudaEvent_t tl[NTL] = {};
@@ -134,7 +134,7 @@ struct Dev {
     // resident operands
     DevBuf Pt, Qt, OV2, T1d, fo, fv, partials, counter, out, prof, blocktab;
     // raw inputs (staging)
-    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sPhaseB, sBOO, sBOV, sBVV;
+    DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sPhase[MAX_PHASES], sTri, sTri2, sBOO, sBOV, sBVV;
     // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
     DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
     Problem prob{};
@@ -162,11 +162,12 @@ struct fpt_handle {
     fpt::i64 tw_begin = 0, tw_count = 0, nitems = 0;
     int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
     int dbg_flags = 0;
+    int sym_inputs = 1;       // pageable host inputs cross PCIe as their symmetry-unique halves (fpt_set_symmetric_inputs)
     bool profiling = false, last_profiled = false;
     int kernel_variant = 1;
     bool loaded = false;
     bool pending = false;     // an asynchronous call is in flight (fpt_wait has to collect it)
-    bool split = false;       // the evaluation in flight / last finished ran as two kernels (triples_conv, split call)
+    int nphase = 1;           // kernels per GPU of the evaluation in flight / last finished (> 1: split call, see triples_conv)
     fpt::i64 pend_items = 0;
     fpt_stats last{};
     int launches = 0;

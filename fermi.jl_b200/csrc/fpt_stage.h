@@ -5,11 +5,18 @@
 // the PCIe rate.  Here a pool of host threads does it: a transfer is cut into pieces of 2 MB, thread t takes pieces
 // t, t + T, ...; for each it copies the piece into one of its own two pinned slots (non-temporal stores: the data is read next by
 // the DMA engine, not by the CPU) and enqueues the slot's cudaMemcpyAsync itself.  No barrier per piece -- the threads only meet
-// once per transfer -- and the copy of piece n+1 overlaps the DMA of piece n.  With several GPUs in one process the transfers to
-// different GPUs are issued back to back, so their DMAs run concurrently on their own PCIe links.
+// once per transfer -- and the copy of piece n+1 overlaps the DMA of piece n.  With several GPUs in one process the parts of an
+// array that go to different GPUs form ONE transfer whose pieces are dealt round-robin over the GPUs, so all PCIe links are
+// busy at once and the threads still meet only once per array.
+//
+// What is copied is a *view* of the caller's array: a list of slabs, each a run of equally long rows a fixed pitch apart.  A plain
+// array is one slab of one row; a slice of an array's fastest index is one slab of short rows; the symmetry-unique half of
+// OVVV[i,a,b,c] = OVVV[i,a,c,b] is one slab per c holding the prefix b <= c.  The view's rows arrive back to back ("packed") on the
+// device, and a transfer may cover any byte range of the packed stream (one GPU's share of a sharded upload).
 #pragma once
 #include <cuda_runtime.h>
 #include <immintrin.h>
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -45,22 +52,58 @@ inline void copy_to_pinned(void* dst, const void* src, size_t bytes, bool nt)
     if (nt && avx2 && ((uintptr_t)dst % 32) == 0) copy_stream_avx2(dst, src, bytes);
     else memcpy(dst, src, bytes);
 }
-// gather `nrows` rows of `row_bytes` (source pitch `pitch`) into a contiguous pinned buffer
-__attribute__((target("avx2"))) inline void copy_rows_stream_avx2(char* d, const char* s, size_t nrows, size_t row_bytes, size_t pitch)
-{
-    for (size_t r = 0; r < nrows; r++, s += pitch) {
-        for (size_t b = 0; b < row_bytes; b += 32, d += 32)
-            _mm256_stream_si256((__m256i*)d, _mm256_loadu_si256((const __m256i*)(s + b)));
+// A strided view of host memory (all sizes in bytes)
+struct Slab {
+    size_t src_off;      // first row, relative to the array
+    size_t nrows, row_bytes, pitch;
+    size_t packed_off;   // where the slab starts in the packed stream
+};
+struct View {
+    std::vector<Slab> slabs;
+    size_t total = 0;
+    void add(size_t src_off, size_t nrows, size_t row_bytes, size_t pitch)
+    {
+        if (nrows == 0 || row_bytes == 0) return;
+        if (pitch == row_bytes) { row_bytes *= nrows; pitch = row_bytes; nrows = 1; }   // contiguous rows are one row
+        slabs.push_back(Slab{src_off, nrows, row_bytes, pitch, total});
+        total += nrows * row_bytes;
     }
-    _mm_sfence();
+    static View contiguous(size_t bytes) { View v; v.add(0, 1, bytes, bytes); return v; }
+};
+
+// copy bytes [off, off + nb) of the packed stream of `view` (over the array at `src`) to `dst` (a pinned slot, 32-byte aligned)
+__attribute__((target("avx2"))) inline void copy_seg_avx2(char* d, const char* s, size_t n)
+{
+    size_t b = 0;
+    for (; b + 32 <= n; b += 32) _mm256_stream_si256((__m256i*)(d + b), _mm256_loadu_si256((const __m256i*)(s + b)));
+    if (b < n) memcpy(d + b, s + b, n - b);
 }
-inline void copy_rows_to_pinned(void* dst, const void* src, size_t nrows, size_t row_bytes, size_t pitch, bool nt)
+inline void copy_view_to_pinned(char* dst, const char* src, const View& view, size_t off, size_t nb, bool nt)
 {
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (nt && avx2 && ((uintptr_t)dst % 32) == 0 && row_bytes % 32 == 0) { copy_rows_stream_avx2((char*)dst, (const char*)src, nrows, row_bytes, pitch); return; }
-    char* d = (char*)dst;
-    const char* s = (const char*)src;
-    for (size_t r = 0; r < nrows; r++, s += pitch, d += row_bytes) memcpy(d, s, row_bytes);
+    // slab that holds packed offset `off`
+    size_t lo = 0, hi = view.slabs.size();
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) / 2;
+        if (view.slabs[mid].packed_off <= off) lo = mid; else hi = mid;
+    }
+    char* d = dst;
+    bool streamed = false;
+    for (size_t si = lo; nb > 0 && si < view.slabs.size(); si++) {
+        const Slab& sl = view.slabs[si];
+        const size_t within = off - sl.packed_off;
+        size_t row = within / sl.row_bytes, col = within % sl.row_bytes;
+        for (; row < sl.nrows && nb > 0; row++, col = 0) {
+            const size_t n = std::min(sl.row_bytes - col, nb);
+            const char* from = src + sl.src_off + row * sl.pitch + col;
+            if (nt && avx2 && ((uintptr_t)d % 32) == 0) {
+                if (n >= 4096) copy_stream_avx2(d, from, n); else { copy_seg_avx2(d, from, n); streamed = true; }
+            }
+            else memcpy(d, from, n);
+            d += n; off += n; nb -= n;
+        }
+    }
+    if (streamed) _mm_sfence();
 }
 
 class StagePool {
@@ -68,11 +111,11 @@ public:
     size_t PIECE = (size_t)2 << 20;   // bytes per piece = per pinned slot (set before start())
     static constexpr int SLOTS_PER_THREAD = 2;
     struct Job {
-        char* dst = nullptr;          // device
-        const char* src = nullptr;    // pageable host
-        size_t bytes = 0;             // total bytes that arrive at dst (contiguous there)
-        size_t row_bytes = 0;         // 0: `src` is contiguous too; else the source is a set of rows of row_bytes ...
-        size_t src_pitch = 0;         // ... src_pitch bytes apart (a sub-range of the fastest index of a column-major array)
+        char* dst = nullptr;          // device address of the job's first byte
+        const char* src = nullptr;    // the caller's array (pageable host memory)
+        const View* view = nullptr;   // what of it is copied (must outlive the transfer)
+        size_t begin = 0;             // packed range [begin, begin + bytes) of the view
+        size_t bytes = 0;
         int dev = 0;                  // CUDA ordinal
         int idev = 0;                 // index of the GPU inside the handle (event bank)
         cudaStream_t stream = nullptr;
@@ -90,7 +133,7 @@ public:
         slots_.assign((size_t)nthreads_ * SLOTS_PER_THREAD, Slot{});
         for (auto& s : slots_) {
             s.ev.assign(ndev, nullptr);
-            cudaError_t e = cudaHostAlloc((void**)&s.p, PIECE, cudaHostAllocPortable);   // rows never exceed PIECE (o * 8 bytes)
+            cudaError_t e = cudaHostAlloc((void**)&s.p, PIECE, cudaHostAllocPortable);
             if (e != cudaSuccess) return e;
         }
         next_.assign(nthreads_, 0);
@@ -116,21 +159,25 @@ public:
         slots_.clear();
         nthreads_ = 1;
     }
-    // enqueue the whole transfer (returns when every piece has been copied out of `src` and its DMA is enqueued)
-    cudaError_t transfer(const Job& job)
+    // enqueue a set of transfers (returns when every piece has been copied out of its `src` and its DMA is enqueued)
+    cudaError_t transfer(const std::vector<Job>& jobs)
     {
-        const size_t np = (job.bytes + piece_bytes(job) - 1) / piece_bytes(job);
-        const int active = (int)(np < (size_t)nthreads_ ? np : (size_t)nthreads_);
+        // piece list: local piece lp of job j, jobs interleaved (lp slowest) so that concurrent pieces go to different GPUs
+        plan_.clear();
+        size_t maxnp = 0;
+        for (const Job& j : jobs) maxnp = std::max(maxnp, npieces(j));
+        for (size_t lp = 0; lp < maxnp; lp++)
+            for (size_t j = 0; j < jobs.size(); j++)
+                if (lp < npieces(jobs[j])) plan_.push_back({(int)j, lp});
+        if (plan_.empty()) return cudaSuccess;
+        const int active = (int)(plan_.size() < (size_t)nthreads_ ? plan_.size() : (size_t)nthreads_);
         err_.store((int)cudaSuccess);
-        if (active > 1) {
+        {
             std::lock_guard<std::mutex> lk(m_);
-            job_ = job;
+            jobs_ = &jobs;
             active_ = active;
             pending_ = active - 1;
-            gen_++;
-        } else {
-            job_ = job;
-            active_ = 1;
+            if (active > 1) gen_++;
         }
         if (active > 1) cv_.notify_all();
         work(0);
@@ -140,21 +187,25 @@ public:
         }
         return (cudaError_t)err_.load();
     }
+    cudaError_t transfer(const Job& job) { const std::vector<Job> one(1, job); return transfer(one); }
 
 private:
-    // bytes per piece: PIECE, or the whole number of rows that fits into it
-    size_t piece_bytes(const Job& j) const { return j.row_bytes ? (PIECE / j.row_bytes ? PIECE / j.row_bytes : 1) * j.row_bytes : PIECE; }
     struct Slot { char* p = nullptr; std::vector<cudaEvent_t> ev; int busy = -1; };
     void note(cudaError_t e) { if (e != cudaSuccess) { int ok = (int)cudaSuccess; err_.compare_exchange_strong(ok, (int)e); } }
+    size_t npieces(const Job& j) const { return (j.bytes + PIECE - 1) / PIECE; }
     void work(int t)
     {
-        const Job job = job_;
+        const std::vector<Job>& jobs = *jobs_;
         const int T = active_;
         if (t >= T) return;
-        if (cudaSetDevice(job.dev) != cudaSuccess) { note(cudaGetLastError()); return; }
-        const size_t pb = piece_bytes(job);
-        const size_t np = (job.bytes + pb - 1) / pb;
-        for (size_t p = t; p < np; p += T) {
+        int cur_dev = -1;
+        for (size_t g = t; g < plan_.size(); g += T) {
+            const Job& job = jobs[plan_[g].job];
+            if (job.dev != cur_dev) {
+                if (cudaSetDevice(job.dev) != cudaSuccess) { note(cudaGetLastError()); return; }
+                cur_dev = job.dev;
+            }
+            const size_t pb = PIECE, p = plan_[g].piece;
             Slot& s = slots_[(size_t)t * SLOTS_PER_THREAD + next_[t]];
             next_[t] = (next_[t] + 1) % SLOTS_PER_THREAD;
             if (s.busy >= 0) {   // the DMA that last read this slot must have finished
@@ -162,8 +213,7 @@ private:
                 s.busy = -1;
             }
             const size_t off = p * pb, nb = job.bytes - off < pb ? job.bytes - off : pb;
-            if (job.row_bytes) copy_rows_to_pinned(s.p, job.src + (off / job.row_bytes) * job.src_pitch, nb / job.row_bytes, job.row_bytes, job.src_pitch, nt_stores);
-            else copy_to_pinned(s.p, job.src + off, nb, nt_stores);
+            copy_view_to_pinned(s.p, job.src, *job.view, job.begin + off, nb, nt_stores);
             note(cudaMemcpyAsync(job.dst + off, s.p, nb, cudaMemcpyHostToDevice, job.stream));
             if (!s.ev[job.idev]) note(cudaEventCreateWithFlags(&s.ev[job.idev], cudaEventDisableTiming));
             if (s.ev[job.idev]) {
@@ -193,7 +243,9 @@ private:
     std::mutex m_;
     std::condition_variable cv_, done_;
     std::atomic<int> err_{0};
-    Job job_;
+    struct Piece { int job; size_t piece; };
+    std::vector<Piece> plan_;
+    const std::vector<Job>* jobs_ = nullptr;
     unsigned long long gen_ = 0;
     int active_ = 1, pending_ = 0;
     int nthreads_ = 1, ndev_ = 1;

@@ -23,7 +23,11 @@
  * valid for the duration of the call.
  *   - pageable host memory (what a Julia ccall or numpy hands over) is copied by a pool of host threads into a ring of pinned
  *     bounce buffers and sent from there, so it moves at the PCIe rate; with several GPUs every GPU pulls only its own 1/N of
- *     each array over its own PCIe link and the parts are exchanged with one ncclAllGather over NVLink;
+ *     each array over its own PCIe link and the parts are exchanged with one ncclAllGather over NVLink.  The arrays carry the
+ *     index symmetries OVVV[i,a,b,c] = OVVV[i,a,c,b], T2[i,j,a,b] = T2[j,i,b,a], OVOV[i,a,j,b] = OVOV[j,b,i,a] (the reference's
+ *     own algorithms agree with each other only then); the library reads just the half those leave free (b <= c, a <= b) and
+ *     writes the mirror images on the GPU, which halves the bytes the host has to move.  Each array is spot-checked first and
+ *     read in full if it does not look symmetric; fpt_set_symmetric_inputs(h, 0) reads everything in full;
  *   - device memory must live on the handle's (first) GPU and is consumed in place on the library's own streams: the library
  *     issues one cudaDeviceSynchronize() on that GPU before the first read, so work queued on ANY stream of the caller
  *     (PyTorch's or CUDA.jl's current stream) that produced the arrays is complete -- no caller-side synchronisation needed.
@@ -73,6 +77,8 @@ int fpt_create_rank(int device, int rank, int world, const void* id128, fpt_hand
 /* host threads that copy pageable memory into the pinned ring (default: the process's CPU affinity count, divided by `world`
  * on rank handles, at most 16; environment override FERMI_PT_B200_THREADS) */
 int fpt_set_host_threads(fpt_handle* h, int n);
+/* on (default): pageable host inputs cross PCIe as their symmetry-unique halves (see the top of this file); 0: always in full */
+int fpt_set_symmetric_inputs(fpt_handle* h, int on);
 
 /* replaces RCCSDpT(ccsd, moints, ::ijk) for conventional integrals (ijk.jl:20-150): Et = E(T) */
 int fpt_triples_conv(fpt_handle* h, int o, int v, const double* T1, const double* T2, const double* OVVV,

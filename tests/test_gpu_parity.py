@@ -14,6 +14,16 @@ def _args(x):
     return (x.T1, x.T2, x.OVVV, x.OOOV, x.OVOV, x.fo, x.fv)
 
 
+def _expected_h2d(x, halves=True):
+    """Bytes a conventional upload from pageable host arrays moves: arrays of 4 MB and more cross PCIe as their symmetry-unique half."""
+    o, v = x.o, x.v
+    tri = v * (v + 1) // 2
+    n = (x.T1.size + x.OOOV.size + x.fo.size + x.fv.size) * 8
+    for full, half in ((x.T2.size, o * o * tri), (x.OVOV.size, o * o * tri), (x.OVVV.size, o * v * tri)):
+        n += 8 * (half if halves and full * 8 >= (4 << 20) else full)
+    return n
+
+
 @pytest.mark.parametrize("o", [1, 2, 3, 5])
 @pytest.mark.parametrize("v", [1, 2, 7, 16, 19, 33, 53])
 def test_shape_sweep_conv_and_df(engine, o, v):
@@ -181,7 +191,7 @@ def test_pageable_pinned_and_async_calls(engine):
     ref = oracle.pt_gemm(*_args(x))
     e_pg, st = engine.triples_conv(o, v, *_args(x))
     assert abs(e_pg - ref) < TOL, (e_pg, ref)
-    assert st["h2d_bytes"] == sum(a.size * 8 for a in _args(x))
+    assert st["h2d_bytes"] == _expected_h2d(x)        # OVVV (22.7 MB) crosses PCIe as its b <= c half
     pinned = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in _args(x)]
     e_pin, _ = engine.triples_conv(o, v, *pinned)
     assert abs(e_pin - e_pg) < 1e-13
@@ -436,22 +446,62 @@ def test_randomised_sweep(engine):
 @pytest.mark.parametrize("o,v", [(8, 30), (9, 70), (13, 41), (24, 57)])
 def test_split_call_matches_single_launch(engine, o, v):
     """fpt_triples_conv with o >= 8 runs as a split call (operands of the occupied indices p < pA first, kernel over the triplets with
-    i < pA, the rest of OVVV staged behind it, second kernel): same E(T) as the oracle and as the unsplit call, from pageable and from
-    pinned host arrays (the latter take the cudaMemcpy2DAsync row gather)."""
+    i < pA, the rest of OVVV staged behind it, second kernel): same E(T) as the oracle and as the unsplit call, with two, three and
+    four phases, from pageable and from pinned host arrays (the latter take the cudaMemcpy2DAsync row gather)."""
     import os
     import torch
     x = fb.synth.make_inputs(o, v, naux=12, seed=40 + o)
     ref = oracle.pt_gemm(*_args(x))
     e_split, st = engine.triples_conv(o, v, *_args(x))
     assert st["n_launches"] >= 9          # two fused kernels + two reductions among them
-    os.environ["FERMI_PT_B200_SPLIT"] = "0"
-    try:
-        e_whole, st0 = engine.triples_conv(o, v, *_args(x))
-    finally:
-        del os.environ["FERMI_PT_B200_SPLIT"]
+    res = {}
+    for nph in ("0", "3", "4"):
+        os.environ["FERMI_PT_B200_SPLIT"] = nph
+        try:
+            res[nph] = engine.triples_conv(o, v, *_args(x))
+        finally:
+            del os.environ["FERMI_PT_B200_SPLIT"]
+    e_whole, st0 = res["0"]
     assert abs(e_split - ref) < TOL and abs(e_whole - ref) < TOL, (e_split, e_whole, ref)
-    assert abs(e_split - e_whole) < 1e-13
-    assert st["h2d_bytes"] == st0["h2d_bytes"] == sum(a.size * 8 for a in _args(x))
+    assert abs(e_split - e_whole) < 1e-13 and abs(res["3"][0] - e_whole) < 1e-13 and abs(res["4"][0] - e_whole) < 1e-13
+    assert res["3"][1]["n_launches"] >= st["n_launches"] > st0["n_launches"]      # (o = 8 has no room for a third multiple-of-4 slice)
+    assert st["h2d_bytes"] == st0["h2d_bytes"] == res["4"][1]["h2d_bytes"] == _expected_h2d(x)
     pinned = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory() for a in _args(x)]
-    e_pin, _ = engine.triples_conv(o, v, *pinned)
+    e_pin, stp = engine.triples_conv(o, v, *pinned)
     assert abs(e_pin - e_split) < 1e-13
+    assert stp["h2d_bytes"] == _expected_h2d(x, halves=False)      # pinned arrays are read by the DMA engines, in full
+
+
+@pytest.mark.parametrize("o,v", [(15, 93), (9, 70), (3, 127)])
+def test_symmetry_unique_halves(engine, o, v):
+    """Pageable host arrays of 4 MB and more cross PCIe as the half their index symmetry leaves free (b <= c of OVVV, a <= b of T2 and
+    OVOV), the mirror images are written on the GPU: same E(T) as the full upload and as the oracle, about half the bytes.  An array
+    that is not symmetric is detected by the spot check and read in full."""
+    x = fb.synth.make_inputs(o, v, naux=16, seed=7 + o)
+    ref = oracle.pt_gemm(*_args(x))
+    e_half, st = engine.triples_conv(o, v, *_args(x))
+    engine.set_symmetric_inputs(False)
+    try:
+        e_full, st_full = engine.triples_conv(o, v, *_args(x))
+    finally:
+        engine.set_symmetric_inputs(True)
+    assert abs(e_half - ref) < TOL and abs(e_full - ref) < TOL, (e_half, e_full, ref)
+    assert abs(e_half - e_full) < 1e-13
+    assert st["h2d_bytes"] == _expected_h2d(x) and st_full["h2d_bytes"] == _expected_h2d(x, halves=False)
+    assert st["h2d_bytes"] < 0.62 * st_full["h2d_bytes"]
+    # upload + compute (the staged form) takes the same route
+    engine.upload_conv(o, v, *_args(x))
+    e_staged, _ = engine.compute(0, -1)
+    assert abs(e_staged - e_half) < 1e-13
+    # break the (b, c) symmetry of OVVV: the spot check must notice, the array goes in full, and what is computed is what the full
+    # upload computes from the same array
+    y = fb.synth.make_inputs(o, v, naux=16, seed=7 + o)
+    y.OVVV = np.asfortranarray(y.OVVV * (1.0 + 0.25 * np.arange(v)[None, None, None, :] / v))
+    e_asym, st_asym = engine.triples_conv(o, v, *_args(y))
+    engine.set_symmetric_inputs(False)
+    try:
+        e_asym_full, _ = engine.triples_conv(o, v, *_args(y))
+    finally:
+        engine.set_symmetric_inputs(True)
+    assert abs(e_asym - e_asym_full) < 1e-13 and abs(e_asym - e_half) > 1e-6
+    assert st_asym["h2d_bytes"] == _expected_h2d(y) + 8 * (y.OVVV.size - o * v * (v * (v + 1) // 2))
