@@ -9,9 +9,9 @@
 from . import build as _build_mod
 from . import synth
 from ._lib import Engine, FermiException, Stats, load_library, library_path, nccl_unique_id, EXPORTS
-from .host import B200, FermiSparse, IntegralHelper, Options, RCCSD, RCCSDpT, RpTAlgorithm, get_rpt_alg, output
+from .host import B200, FermiSparse, IntegralHelper, Options, RCCSD, RCCSDa, RCCSDpT, RMP2_energy, RpTAlgorithm, cc_update_T2_v4_term, get_rpt_alg, output
 
 build_library = _build_mod.build
 
 __all__ = ["Engine", "FermiException", "FermiSparse", "Stats", "load_library", "library_path", "nccl_unique_id", "EXPORTS", "B200", "IntegralHelper",
-           "Options", "RCCSD", "RCCSDpT", "RpTAlgorithm", "get_rpt_alg", "output", "synth", "build_library"]
+           "Options", "RCCSD", "RCCSDa", "RCCSDpT", "RMP2_energy", "cc_update_T2_v4_term", "RpTAlgorithm", "get_rpt_alg", "output", "synth", "build_library"]

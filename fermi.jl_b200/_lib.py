@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao", "fpt_triples_ao_sparse", "fpt_upload_ao_sparse",
-           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_gemm_bench", "fpt_last_timeline",
+           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_ccsd_ladder_df", "fpt_mp2_df", "fpt_mp2_conv", "fpt_gemm_bench", "fpt_last_timeline",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -76,6 +76,9 @@ def load_library():
     L.fpt_triples_conv_async.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7
     L.fpt_triples_df_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
     L.fpt_wait.argtypes = [vp, _dp, ctypes.POINTER(Stats)]
+    L.fpt_ccsd_ladder_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.POINTER(Stats)]
+    L.fpt_mp2_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, _dp, ctypes.POINTER(Stats)]
+    L.fpt_mp2_conv.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, _dp, ctypes.POINTER(Stats)]
     L.fpt_gemm_bench.argtypes = [vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp]
     L.fpt_last_timeline.argtypes = [vp, _dp]
     for f in EXPORTS:
@@ -181,6 +184,30 @@ class Engine:
         ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
         e, st = ctypes.c_double(), Stats()
         self._check(self._L.fpt_triples_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def ccsd_ladder_df(self, o, v, naux, T1, T2, BVV, newT2):
+        """newT2[i,j,a,b] += sum_cd (T2 + T1 T1)[i,j,c,d] sum_Q BVV[Q,c,a] BVV[Q,d,b]  (RCCSDHelper.jl:204-220), in place: newT2 must be a
+        Fortran-ordered float64 numpy array."""
+        if not (isinstance(newT2, np.ndarray) and newT2.dtype == np.float64 and newT2.flags.f_contiguous and newT2.flags.writeable):
+            raise FermiException("ccsd_ladder_df: newT2 must be a writeable Fortran-ordered float64 array (it is updated in place)")
+        if tuple(newT2.shape) != (o, o, v, v):
+            raise FermiException(f"ccsd_ladder_df: newT2 has shape {tuple(newT2.shape)}, expected {(o, o, v, v)}")
+        ps = [_ptr(a) for a in (T1, T2, BVV)]
+        st = Stats()
+        self._check(self._L.fpt_ccsd_ladder_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.c_void_p(newT2.ctypes.data), ctypes.byref(st)))
+        return st.asdict()
+
+    def mp2_df(self, o, v, naux, BOV, fo, fv):
+        ps = [_ptr(a) for a in (BOV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_mp2_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def mp2_conv(self, o, v, OVOV, fo, fv):
+        ps = [_ptr(a) for a in (OVOV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_mp2_conv(self._h, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
         return e.value, st.asdict()
 
     def triples_ao(self, nbf, o, v, T1, T2, AOERI, Co, Cv, fo, fv):

@@ -282,3 +282,58 @@ __global__ void expand_sparse_eri_kernel(double* __restrict__ AO, const Ti* __re
 }
 
 }  // namespace fpt
+
+namespace fpt {
+
+// ---------------------------------------------------------------------------------------------------
+// Section 8(f) rows beside the (T) path: DF-CCSD particle-particle ladder and MP2 energy
+// ---------------------------------------------------------------------------------------------------
+// tauT[(c,d) + v^2 (i + o j)] = T2[i,j,c,d] + T1[i,c] T1[j,d]      (RCCSDHelper.jl:208, stored with the contracted pair (c,d) fastest)
+__global__ void ladder_tau_kernel(int o, int v, double* __restrict__ tauT, const double* __restrict__ T1, const double* __restrict__ T2)
+{
+    __shared__ double tile[32][33];
+    const i64 o2 = (i64)o * o, v2 = (i64)v * v;
+    const i64 ij0 = (i64)blockIdx.x * 32, cd0 = (i64)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int kk = 0; kk < 32; kk += 8) {
+        const i64 cd = cd0 + ty + kk, ij = ij0 + tx;
+        if (cd < v2 && ij < o2) {
+            const int i = (int)(ij % o), j = (int)(ij / o), c = (int)(cd % v), d = (int)(cd / v);
+            tile[ty + kk][tx] = T2[ij + o2 * cd] + T1[i + (i64)o * c] * T1[j + (i64)o * d];
+        }
+    }
+    __syncthreads();
+    for (int kk = 0; kk < 32; kk += 8) {
+        const i64 ij = ij0 + ty + kk, cd = cd0 + tx;
+        if (cd < v2 && ij < o2) tauT[cd + v2 * ij] = tile[tx][ty + kk];
+    }
+}
+
+// E(MP2) = sum_{i,a,j,b} (ia|jb) [2 (ia|jb) - (ib|ja)] / (e_i + e_j - e_a - e_b)        (RMP2a.jl:155-166; the DF form RMP2a.jl:118-133
+// is the same sum over i <= j with weight 2).  One block sums a fixed stretch of the index space, a second launch adds the block
+// partials in order: the result does not depend on scheduling.
+__global__ void __launch_bounds__(256) mp2_energy_kernel(int o, int v, const double* __restrict__ OVOV, const double* __restrict__ fo,
+                                                         const double* __restrict__ fv, double* __restrict__ partials)
+{
+    __shared__ double red[8];
+    const i64 ov = (i64)o * v, n = ov * ov;
+    double e = 0.0;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % o);
+        i64 t = idx / o;
+        const int a = (int)(t % v); t /= v;
+        const int j = (int)(t % o), b = (int)(t / o);
+        const double x = OVOV[idx], y = OVOV[i + (i64)o * (b + (i64)v * (j + (i64)o * a))];
+        e += x * (2.0 * x - y) / (fo[i] + fo[j] - fv[a] - fv[b]);
+    }
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += red[w];
+        partials[blockIdx.x] = s;
+    }
+}
+
+}  // namespace fpt

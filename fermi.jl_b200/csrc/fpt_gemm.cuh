@@ -59,12 +59,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // EPI_PT        m = y + v*pl, n = d + v*x  ->  Pt[p0+pl][y][x][d]                 (OVVV[p,y,x,d] = sum_Q BOV[Q,p,y] BVV[Q,x,d], DFERI.jl:156-180)
 // EPI_QT_HOLE   m = l + o*q,  n = r + o*z  ->  Qt[(q,r)][g][z][kappa = v + l]     (OOOV[l,q,r,z] = sum_Q BOO[Q,l,q] BOV[Q,r,z], DFERI.jl:88-112)
 // EPI_OV2       m = q + o*y,  n = r + o*z  ->  OV2[(q,r)] tile (y,z)              (OVOV[q,y,r,z] = sum_Q BOV[Q,q,y] BOV[Q,r,z], DFERI.jl:139-154)
-enum { EPI_COLMAJOR = 0, EPI_PT = 1, EPI_QT_HOLE = 2, EPI_OV2 = 3 };
+// EPI_LADDER_SLAB  m = c + v*al, n = d + v*b  ->  X[c + v*d + v^2*b + v^3*al]    ((ca|db) = sum_Q BVV[Q,c,a] BVV[Q,d,b] for a = a0 + al,
+//                                                                               RCCSDHelper.jl:216; X_a is the B operand of the next GEMM)
+// EPI_LADDER_OUT   m = i + o*j,  n = b + v*al  ->  C[m + o^2*((a0+al) + v*b)] += val   (newT2[:,:,a,:] += tau . X_a, RCCSDHelper.jl:217-218)
+enum { EPI_COLMAJOR = 0, EPI_PT = 1, EPI_QT_HOLE = 2, EPI_OV2 = 3, EPI_LADDER_SLAB = 4, EPI_LADDER_OUT = 5 };
 struct GemmOut {
     double* C;
     i64 ldc;       // EPI_COLMAJOR
     Problem P;     // the layout epilogues
     int p0;        // EPI_PT: first occupied index of this launch (the assembly is sharded over p across GPUs)
+    int lv, lo2, la0;   // EPI_LADDER_*: v, o^2, first a of this group
 };
 template <int EPI>
 __device__ __forceinline__ void gemm_store(const GemmOut& out, i64 m, int n, double val)
@@ -79,6 +83,12 @@ __device__ __forceinline__ void gemm_store(const GemmOut& out, i64 m, int n, dou
         const int l = (int)(m % P.o), q = (int)(m / P.o), r = n % P.o, z = n / P.o;
         const int kappa = P.v + l;
         out.C[qt_row(P, q, r, kappa / KGROUP, z) + (kappa % KGROUP)] = val;
+    } else if (EPI == EPI_LADDER_SLAB) {
+        const i64 v = out.lv;
+        out.C[(m % v) + v * (i64)n + v * v * v * (m / v)] = val;
+    } else if (EPI == EPI_LADDER_OUT) {
+        const int b = n % out.lv, al = n / out.lv;
+        out.C[m + (i64)out.lo2 * ((out.la0 + al) + (i64)out.lv * b)] += val;
     } else {
         const int q = (int)(m % P.o), y = (int)(m / P.o), r = n % P.o, z = n / P.o;
         out.C[ov2_idx(P, q, r, y, z)] = val;

@@ -137,6 +137,8 @@ struct Dev {
     DevBuf sT1, sT2, sOOOV, sOVOV, sChunk[2], sPhase[MAX_PHASES], sTri, sTri2, sBOO, sBOV, sBVV;
     // AO -> MO route: coefficient blocks, quarter-transformed intermediates, the MO blocks the (T) path consumes
     DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
+    // CCSD ladder / MP2: tau^T, the (vv|vv) slabs of one group of a, newT2 on the device, (ia|jb)
+    DevBuf xTau, xSlab, xNew, xOVOV;
     Problem prob{};
     int tab_vp = -1;          // the block table on this device was built for this padded virtual dimension
     // Pt holds zeros in its padding (x,y >= v, kappa >= v+o) for this shape: a new upload of the same shape may skip the memset

@@ -191,6 +191,38 @@ class RCCSDpT:
         self.stats = st
 
 
+# ---- beside the (T) path: the DF-CCSD particle-particle ladder and the MP2 energy ----------------------------------
+class RCCSDa:
+    """Mirror of the reference's CCSD algorithm singleton (RCCSD.jl); only the ladder term is offloaded."""
+
+
+def cc_update_T2_v4_term(newT2, T1, T2, moints: IntegralHelper, alg=None, device=None, engine=None):
+    """`cc_update_T2_v4_term!(newT2, T1, T2, moints::IntegralHelper{T,<:AbstractDFERI}, alg::RCCSDa)` (RCCSDHelper.jl:204-220) on the
+    GPU: newT2 is updated in place with the particle-particle ladder contraction; returns the call's stats."""
+    if not moints.is_df:
+        raise FermiException("cc_update_T2_v4_term: the B200 path offloads the density-fitted ladder (moints must hold BVV)")
+    o, v = T1.shape
+    Bvv = moints["BVV"]
+    eng = engine if engine is not None else _engine(device)
+    return eng.ccsd_ladder_df(o, v, Bvv.shape[0], T1, T2, Bvv, newT2)
+
+
+def RMP2_energy(ints: IntegralHelper, alg=None, device=None, engine=None) -> float:
+    """`RMP2_energy(ints, alg)` for RHF orbitals: density-fitted (RMP2a.jl:91-143) when the helper is a DF helper, conventional
+    (RMP2a.jl:146-169, from ints["OVOV"]) otherwise.  Returns the MP2 correlation energy."""
+    fo, fv = ints["Fii"], ints["Faa"]
+    o, v = len(fo), len(fv)
+    eng = engine if engine is not None else _engine(device)
+    if ints.is_df:
+        output(" Computing DF-MP2 Energy!")
+        Bov = ints["BOV"]
+        e, _ = eng.mp2_df(o, v, Bov.shape[0], Bov, fo, fv)
+    else:
+        output(" Computing MP2 Energy... ", ending="")
+        e, _ = eng.mp2_conv(o, v, ints["OVOV"], fo, fv)
+    return e
+
+
 # ---- static work list helpers (mirror of fpt_layout.h) ---------------------------------------------------------
 def num_blocks(v: int) -> int:
     """Tile triples A >= B >= C of the virtual range (tiles of 16 over roundup4(v))."""

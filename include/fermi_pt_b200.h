@@ -123,6 +123,19 @@ int fpt_upload_ao_sparse(fpt_handle* h, int nbf, int o, int v, const double* T1,
                          const void* idx, int index_bytes, const double* vals, const double* Co, const double* Cv,
                          const double* fo, const double* fv);
 
+/* ---- beside the (T) path ----
+ * DF-CCSD particle-particle ladder, the hot spot of a DF-CCSD iteration: replaces
+ *     cc_update_T2_v4_term!(newT2, T1, T2, moints::IntegralHelper{T,<:AbstractDFERI}, ::RCCSDa)      RCCSDHelper.jl:204-220
+ * newT2[i,j,a,b] += sum_cd (T2[i,j,c,d] + T1[i,c] T1[j,d]) sum_Q BVV[Q,c,a] BVV[Q,d,b].  newT2 (o,o,v,v) is host memory, read and
+ * updated in place; T1, T2, BVV as above.  The (vv|vv) block is assembled slab by slab on the GPU and never stored. */
+int fpt_ccsd_ladder_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BVV,
+                       double* newT2, fpt_stats* stats);
+/* MP2 correlation energy: replaces RMP2_energy for density-fitted (RMP2a.jl:91-143) and conventional (RMP2a.jl:146-169) integrals,
+ * E = sum_iajb (ia|jb) [2 (ia|jb) - (ib|ja)] / (fo[i] + fo[j] - fv[a] - fv[b]). */
+int fpt_mp2_df(fpt_handle* h, int o, int v, int naux, const double* BOV, const double* fo, const double* fv, double* Emp2,
+               fpt_stats* stats);
+int fpt_mp2_conv(fpt_handle* h, int o, int v, const double* OVOV, const double* fo, const double* fv, double* Emp2, fpt_stats* stats);
+
 /* Staged form of the calls above (kernel-only timing, partial evaluations):
  * upload = copy + layout prep, operands stay resident on the GPU(s); compute = fused kernel over the item range
  * [item_begin, item_end) of the static work list (item_end < 0: to the end), returning that range's share of E(T).  A handle

@@ -1,0 +1,88 @@
+"""SURVEY.md 8(f) rows beside the (T) path: the DF-CCSD particle-particle ladder (RCCSDHelper.jl:204-220) and the MP2 energy
+(RMP2a.jl:91-169).  CPU: the numpy restatements against each other (DF loop form vs the one-line VVVV form, pair loop vs the flat sum).
+GPU: fpt_ccsd_ladder_df / fpt_mp2_df / fpt_mp2_conv through the C ABI against them."""
+import os
+
+import numpy as np
+import pytest
+
+import fermi_jl_b200 as fb
+from oracle import cc_numpy as C
+
+
+def _case(o, v, naux, seed):
+    x = fb.synth.make_inputs(o, v, naux=naux, seed=seed, conventional=False)
+    rng = np.random.default_rng(seed + 1)
+    new0 = np.asfortranarray(0.01 * rng.standard_normal((o, o, v, v)))
+    return x, new0
+
+
+@pytest.mark.parametrize("o,v,naux", [(2, 3, 4), (3, 7, 9), (4, 12, 20)])
+def test_ladder_restatements_agree(o, v, naux):
+    x, new0 = _case(o, v, naux, 5)
+    vvvv = np.einsum("Qca,Qdb->cadb", x.BVV, x.BVV, optimize=True)
+    a = C.ladder_df(new0.copy(order="F"), x.T1, x.T2, x.BVV)
+    b = C.ladder_conv(new0.copy(order="F"), x.T1, x.T2, vvvv)
+    assert np.abs(a - b).max() < 1e-13 * max(1.0, np.abs(a).max())
+    assert np.abs(a - new0).max() > 1e-6           # the term is not trivially zero
+
+
+@pytest.mark.parametrize("o,v,naux", [(2, 3, 4), (3, 7, 9), (5, 19, 30)])
+def test_mp2_restatements_agree(o, v, naux):
+    x, _ = _case(o, v, naux, 6)
+    ovov = np.einsum("Qia,Qjb->iajb", x.BOV, x.BOV, optimize=True)
+    e_df, e_cv = C.mp2_df(x.BOV, x.fo, x.fv), C.mp2_conv(ovov, x.fo, x.fv)
+    assert abs(e_df - e_cv) < 1e-13 * max(1.0, abs(e_cv)) and e_cv < 0.0
+
+
+def test_mp2_restatement_on_the_stored_water_run():
+    """water / STO-3G of the reference's printed run (tests/golden/water_sto3g.npz, oracle/mini_ccsd.py): the MP2 energy from the stored
+    (ia|jb) equals the first CCSD iteration's energy with the MP2 guess amplitudes, E = sum (2 (ia|jb) - (ib|ja)) t_ij^ab."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "water_sto3g.npz"))
+    ovov, fo, fv = G["OVOV"], G["fo"], G["fv"]
+    D = fo[:, None, None, None] + fo[None, :, None, None] - fv[None, None, :, None] - fv[None, None, None, :]
+    t2 = np.transpose(ovov, (0, 2, 1, 3)) / D                             # RCCSDa.jl:55,87
+    e_guess = float(np.einsum("iajb,ijab->", 2.0 * ovov - np.transpose(ovov, (0, 3, 2, 1)), t2))
+    assert abs(C.mp2_conv(ovov, fo, fv) - e_guess) < 1e-14
+
+
+# ---- GPU parity ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("o,v,naux", [(1, 1, 1), (2, 3, 4), (3, 7, 9), (5, 19, 33), (6, 37, 64), (4, 70, 131), (15, 93, 420)])
+def test_gpu_ladder_matches_restatement(engine, o, v, naux):
+    x, new0 = _case(o, v, naux, 11)
+    ref = C.ladder_df(new0.copy(order="F"), x.T1, x.T2, x.BVV)
+    got = new0.copy(order="F")
+    st = engine.ccsd_ladder_df(o, v, naux, x.T1, x.T2, x.BVV, got)
+    scale = max(1e-30, float(np.abs(ref - new0).max()))
+    assert np.abs(got - ref).max() < 1e-12 * max(1.0, scale) + 1e-13 * scale, (np.abs(got - ref).max(), scale)
+    assert st["flops"] == 2.0 * v ** 4 * (naux + o * o)
+    # through the interface mirror, twice in a row on the same array (two CCSD iterations accumulate)
+    moints = fb.IntegralHelper({"BVV": x.BVV}, eri_type="RIFIT")
+    fb.cc_update_T2_v4_term(got, x.T1, x.T2, moints, fb.RCCSDa())
+    assert np.abs(got - (2.0 * ref - new0)).max() < 2e-12 * max(1.0, scale) + 1e-13 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("o,v,naux", [(1, 1, 1), (2, 3, 4), (3, 7, 9), (5, 19, 33), (5, 53, 131), (15, 93, 420), (24, 114, 64)])
+def test_gpu_mp2_matches_restatement(engine, o, v, naux):
+    x, _ = _case(o, v, naux, 12)
+    ref = C.mp2_df(x.BOV, x.fo, x.fv)
+    e_df, st = engine.mp2_df(o, v, naux, x.BOV, x.fo, x.fv)
+    assert abs(e_df - ref) < 1e-12 * max(1.0, abs(ref)), (e_df, ref)
+    ovov = np.asfortranarray(np.einsum("Qia,Qjb->iajb", x.BOV, x.BOV, optimize=True))
+    e_cv, _ = engine.mp2_conv(o, v, ovov, x.fo, x.fv)
+    assert abs(e_cv - ref) < 1e-12 * max(1.0, abs(ref)), (e_cv, ref)
+    assert fb.RMP2_energy(fb.IntegralHelper({"BOV": x.BOV, "Fii": x.fo, "Faa": x.fv}, eri_type="RIFIT")) == e_df
+    assert abs(fb.RMP2_energy(fb.IntegralHelper({"OVOV": ovov, "Fii": x.fo, "Faa": x.fv})) - e_cv) < 1e-15
+
+
+@pytest.mark.gpu
+def test_gpu_ladder_and_mp2_errors(engine):
+    x, new0 = _case(3, 5, 4, 1)
+    with pytest.raises(fb.FermiException):
+        engine.ccsd_ladder_df(3, 5, 4, x.T1, x.T2, x.BVV, np.ascontiguousarray(new0))      # not Fortran-ordered
+    with pytest.raises(fb.FermiException):
+        engine.mp2_df(0, 5, 4, x.BOV, x.fo, x.fv)
+    with pytest.raises(fb.FermiException):
+        fb.cc_update_T2_v4_term(new0, x.T1, x.T2, fb.IntegralHelper({"VVVV": None}))
