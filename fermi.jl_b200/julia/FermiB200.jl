@@ -149,4 +149,44 @@ function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T
     return RCCSDpT{T}(ccsd, T(Et[] + ccsd.energy), T(Et[]))  # ijk.jl:149
 end
 
+# ---- beside the (T) path (SURVEY 8f): the DF-CCSD particle-particle ladder and the DF-MP2 energy on the GPU ------------------------
+# ladder_df!(newT2, T1, T2, moints) does what cc_update_T2_v4_term!(newT2, T1, T2, moints::IntegralHelper{T,<:AbstractDFERI}, ::RCCSDa)
+# does (RCCSDHelper.jl:204-220), mp2_df(ints) what RMP2_energy(ints::IntegralHelper{T,<:AbstractDFERI,RHFOrbitals}, alg) does
+# (RMP2a.jl:91-143).  FermiB200.offload_ccsd_ladder!() / offload_mp2!() redefine those two reference methods to call them.
+function ladder_df!(newT2::Array{Float64,4}, T1, T2, moints::IntegralHelper)
+    o, v = size(T1)
+    BVV = dense(moints["BVV"])
+    st = Ref{FptStats}()
+    check(ccall((:fpt_ccsd_ladder_df, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{FptStats}),
+                handle(), o, v, size(BVV, 1), dense(T1), dense(T2), BVV, newT2, st))
+    return newT2
+end
+
+function mp2_df(ints::IntegralHelper)
+    BOV = dense(ints["BOV"]); fo = dense(ints["Fii"]); fv = dense(ints["Faa"])
+    E = Ref{Cdouble}(0.0)
+    st = Ref{FptStats}()
+    check(ccall((:fpt_mp2_df, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{FptStats}),
+                handle(), length(fo), length(fv), size(BOV, 1), BOV, fo, fv, E, st))
+    return E[]
+end
+
+function offload_ccsd_ladder!()
+    @eval function Fermi.CoupledCluster.cc_update_T2_v4_term!(newT2::Array{Float64,4}, T1::AbstractArray{Float64,2}, T2::AbstractArray{Float64,4},
+                                                              moints::IntegralHelper{Float64,E,O}, alg::Fermi.CoupledCluster.RCCSDa) where {
+                                                              E<:AbstractDFERI,O<:AbstractRestrictedOrbitals}
+        FermiB200.ladder_df!(newT2, T1, T2, moints)
+    end
+end
+
+function offload_mp2!()
+    @eval function Fermi.MollerPlesset.RMP2_energy(ints::IntegralHelper{Float64,<:AbstractDFERI,Fermi.Orbitals.RHFOrbitals},
+                                                   Alg::Fermi.MollerPlesset.RMP2Algorithm)
+        output(" Computing DF-MP2 Energy!")
+        return FermiB200.mp2_df(ints)
+    end
+end
+
 end # module
