@@ -36,7 +36,7 @@ static void dev_destroy(Dev* d)
     cudaSetDevice(d->dev);
     if (d->comm) nccl_api().CommDestroy(d->comm);
     DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab, &d->sBOO, &d->sBOV, &d->sBVV,
                       &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
                       &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
     for (DevBuf* b : bufs) b->release();
@@ -72,6 +72,7 @@ static int dev_init(Dev* d)
     for (int t = 0; t < NTL; t++) CK(cudaEventCreate(&d->tl[t]));
     CK(cudaFuncSetAttribute(triples_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
     CK(cudaFuncSetAttribute(triples_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(triples_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES_SMEM_BYTES));
 #ifdef FPT_WITH_VARIANT2
     CK(cudaFuncSetAttribute(triples_kernel2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
     CK(cudaFuncSetAttribute(triples_kernel2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIPLES2_SMEM_BYTES));
@@ -224,6 +225,28 @@ extern "C" int fpt_set_symmetric_inputs(fpt_handle* h, int on)
 {
     if (!h) return fail("fpt_set_symmetric_inputs: NULL handle");
     h->sym_inputs = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int fpt_set_df_ring(fpt_handle* h, int block)
+{
+    if (!h) return fail("fpt_set_df_ring: NULL handle");
+    if (block < -1 || block > 64) return fail("fpt_set_df_ring: block=%d out of range (-1 .. 64)", block);
+    h->df_ring = block;
+    return 0;
+}
+
+extern "C" int fpt_device_bytes(fpt_handle* h, double* bytes)
+{
+    if (!h || !bytes) return fail("fpt_device_bytes: NULL argument");
+    Dev* d = h->devs[0];
+    DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab, &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
+                      &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
+    double n = 0.0;
+    for (DevBuf* b : bufs) n += (double)b->cap;
+    *bytes = n;
     return 0;
 }
 
@@ -413,7 +436,7 @@ static int check_idle(fpt_handle* h, const char* who)
 
 // Dimensions, work list and device buffers of a new problem on every GPU of the handle; the copy streams are ordered after
 // whatever the compute streams still have in flight (the previous problem's kernels read the buffers about to be overwritten).
-static int setup_problem(fpt_handle* h, int o, int v)
+static int setup_problem(fpt_handle* h, int o, int v, int pt_slabs = 0)   // pt_slabs: slabs Pt has room for (0: all o)
 {
     if (o < 1 || v < 1) return fail("invalid dimensions o=%d v=%d", o, v);
     Problem P{};
@@ -448,7 +471,8 @@ static int setup_problem(fpt_handle* h, int o, int v)
     for (Dev* dp : h->devs) {
         Dev& d = *dp;
         CK(cudaSetDevice(d.dev));
-        if (d.Pt.ensure((size_t)o * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
+        if (d.Pt.ensure((size_t)(pt_slabs ? pt_slabs : o) * P.vp * P.vp * P.Kp * sizeof(double))) return 1;
+        d.pt_slabs = pt_slabs ? pt_slabs : o;
         if (d.Qt.ensure((size_t)o * o * P.G * P.vp * KGROUP * sizeof(double))) return 1;
         if (d.OV2.ensure((size_t)ov2_elems(P) * sizeof(double))) return 1;
         if (d.T1d.ensure((size_t)o * v * sizeof(double))) return 1;
@@ -479,8 +503,8 @@ static int setup_problem(fpt_handle* h, int o, int v)
 static int pt_zero_padding(Dev& d)
 {
     const Problem& P = d.prob;
-    if (d.clean_o == P.o && d.clean_v == P.v && d.clean_ptr == d.Pt.p) return 0;
-    CK(cudaMemsetAsync(d.Pt.p, 0, (size_t)P.o * P.vp * P.vp * P.Kp * sizeof(double), d.stream));
+    if (d.clean_o == P.o && d.clean_v == P.v && d.clean_ptr == d.Pt.p && d.clean_slabs >= d.pt_slabs) return 0;
+    CK(cudaMemsetAsync(d.Pt.p, 0, (size_t)d.pt_slabs * P.vp * P.vp * P.Kp * sizeof(double), d.stream));
     return 0;
 }
 static void upload_begin(fpt_handle* h)
@@ -504,7 +528,7 @@ static int upload_end(fpt_handle* h, bool sync)
             CK(cudaStreamSynchronize(d.copy));
             CK(cudaStreamSynchronize(d.stream));
         }
-        d.clean_o = d.prob.o; d.clean_v = d.prob.v; d.clean_ptr = d.Pt.p;
+        d.clean_o = d.prob.o; d.clean_v = d.prob.v; d.clean_ptr = d.Pt.p; d.clean_slabs = d.pt_slabs;
     }
     h->loaded = true;
     return 0;
@@ -563,7 +587,7 @@ static bool use_half(const fpt_handle* h, const double* A, size_t n0, size_t n1,
 }
 
 // T2 -> Pt hole part and Qt (hole part of Qt from the whole OOOV on the GPUs, dOOOV; empty on the density-fitted route)
-static int upload_t2(fpt_handle* h, const double* T2, const std::vector<const double*>& dOOOV)
+static int upload_t2(fpt_handle* h, const double* T2, const std::vector<const double*>& dOOOV, bool with_pt_hole = true)
 {
     const int o = h->o, v = h->v;
     const size_t o2 = (size_t)o * o;
@@ -589,7 +613,8 @@ static int upload_t2(fpt_handle* h, const double* T2, const std::vector<const do
         Dev& d = *h->devs[i];
         CK(cudaSetDevice(d.dev));
         const Problem& P = d.prob;
-        prep_pt_hole<<<grid1d((i64)o2 * v * v), 256, 0, d.stream>>>(P, d.Pt.d(), dT2[i]);
+        d.cur_T2 = dT2[i];
+        if (with_pt_hole) prep_pt_hole<<<grid1d((i64)o2 * v * v), 256, 0, d.stream>>>(P, d.Pt.d(), dT2[i], 0, o, nullptr);
         prep_qt<<<grid1d((i64)o2 * P.G * P.vp * KGROUP), 256, 0, d.stream>>>(P, d.Qt.d(), dT2[i], dOOOV.empty() ? nullptr : dOOOV[i]);
         CK(cudaGetLastError());
     }
@@ -836,14 +861,17 @@ static void shard_range(const fpt_handle* h, const Problem& P, i64 b, i64 e, int
 
 // launch the fused kernel + reduction for [item_begin, item_end) of the work list described by P on one GPU (asynchronous; the result
 // is stored in d.out, or added to it for the second phase of a split call, which also has its own pair of timing events)
-static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begin, i64 item_end, int phase)
+static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begin, i64 item_end, int phase, int accumulate = -1,
+                          RingMap ring = RingMap{nullptr, nullptr})
 {
+    // phase >= 0: the launch is timed with event pair `phase`; accumulate (default: phase > 0): add to d.out instead of storing
+    if (accumulate < 0) accumulate = phase > 0;
     CK(cudaSetDevice(d.dev));
     const i64 n = item_end - item_begin;
     int grid = d.n_sm;
     if ((i64)grid > n) grid = (int)(n > 0 ? n : 1);
     CK(cudaMemsetAsync(d.counter.p, 0, sizeof(unsigned long long), d.stream));
-    CK(cudaEventRecord(d.ev0[phase], d.stream));
+    if (phase >= 0) CK(cudaEventRecord(d.ev0[phase], d.stream));
     unsigned long long* ctr = (unsigned long long*)d.counter.p;
 #ifdef FPT_WITH_VARIANT2
     if (h->kernel_variant == 2) {
@@ -851,14 +879,16 @@ static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begi
         else triples_kernel2<false><<<grid, NTHREADS2, TRIPLES2_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
     } else
 #endif
-    if (h->profiling)
-        triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
+    if (ring.trips)   // slab ring of the DF route: explicit triplet list, Pt through the slot map
+        triples_kernel<false, true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p, ring);
+    else if (h->profiling)
+        triples_kernel<true><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p, ring);
     else
-        triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p);
+        triples_kernel<false><<<grid, NTHREADS, TRIPLES_SMEM_BYTES, d.stream>>>(P, item_begin, item_end, ctr, d.partials.d(), (long long*)d.prof.p, ring);
     d.last_grid = grid;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(d.ev1[phase], d.stream));
-    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), phase);
+    if (phase >= 0) CK(cudaEventRecord(d.ev1[phase], d.stream));
+    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), accumulate);
     CK(cudaGetLastError());
     d.shard_b = item_begin;
     d.shard_e = item_end;
@@ -1055,6 +1085,131 @@ static int triples_conv(fpt_handle* h, int o, int v, const double* T1, const dou
     return finish_tail(h, async, t0, Et, st);
 }
 
+// ---- DF route without the full (ov|vv) block: a ring of occupied slabs (north star: "assembling (bd|ai) slices on the fly") ---------
+// Pt holds o slabs of vp^2 Kp doubles (22.9 GB at C5; o = 100, v = 800 would need 467 GB).  Every slab is a GEMM away from the B
+// factors (2 naux v^3 flops), so Pt need not be resident: the occupied range is cut into blocks of `ob`, the triplet list is walked
+// block triple by block triple (I >= J >= K; i in I, j in J, k in K), and the ring holds just the 3 ob slabs of the current block
+// triple -- slot group 0 for I, 1 for J (or I's when J = I), 2 for K (or J's when K = J).  Going to the next K assembles ob slabs;
+// a block triple of distinct blocks carries ob^3 triplets of 12 v^3 (v + o) flops each, so the re-assembly costs
+// naux / (6 ob^2 (v + o)) of the work: 4 % at C3 with ob = 4, 65 % with ob = 1 (three slabs in all).  Per block triple: one
+// assembly launch group + one launch of the fused kernel over its explicit triplet list (Problem::trips) with the slot map of that
+// block triple (Problem::pslot); E(T) accumulates on the device.  Several GPUs: everyone assembles the same slabs and takes its
+// cost-weighted shard of every launch.
+struct RingPhase { int I, J, K; i64 trip_off, ntrip; };
+
+static int assemble_slabs(fpt_handle* h, Dev& d, const Problem& P, const int* pslot, int naux, const double* dBOV, const double* dBVV, int p0, int p1)
+{
+    if (p1 <= p0) return 0;
+    const int o = P.o, v = P.v;
+    prep_pt_hole<<<grid1d((i64)(p1 - p0) * o * v * v), 256, 0, d.stream>>>(P, d.Pt.d(), d.cur_T2, p0, p1 - p0, pslot);
+    CK(cudaGetLastError());
+    GemmOut out{};
+    out.P = P;
+    out.C = d.Pt.d();
+    out.p0 = p0;
+    out.pslot = pslot;
+    const RowMap mA{p0, o, 1, v};   // m = y + v*pl  ->  BOV row (p0+pl) + o*y
+    const RowMap mB{0, v, 1, v};    // n = d + v*x   ->  BVV row x + v*d
+    CK(gemm_tn_launch<EPI_PT>(d.stream, dBOV, mA, dBVV, mB, (i64)(p1 - p0) * v, v * v, naux, out, d.n_sm));
+    h->launches += 2;
+    return 0;
+}
+
+static int triples_df_ring(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO, const double* BOV,
+                           const double* BVV, const double* fo, const double* fv, int ob)
+{
+    const int nblk = (o + ob - 1) / ob, L = (int)h->devs.size();
+    if (setup_problem(h, o, v, 3 * ob)) return 1;
+    std::vector<const double*> dBOO, dBOV, dBVV;
+    if (upload_t1_f(h, T1, fo, fv)) return 1;
+    if (upload_t2(h, T2, {}, false)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOO; }, BOO, (size_t)naux * o * o, dBOO)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBOV; }, BOV, (size_t)naux * o * v, dBOV)) return 1;
+    if (distribute(h, [](Dev& d) -> DevBuf& { return d.sBVV; }, BVV, (size_t)naux * v * v, dBVV)) return 1;
+    // the phases: block triples in the order I, J <= I, K <= J; triplet lists in the reference's loop order inside each
+    std::vector<RingPhase> phases;
+    std::vector<int> trips, pslots;
+    auto blk_lo = [&](int B) { return B * ob; };
+    auto blk_hi = [&](int B) { return std::min(o, (B + 1) * ob); };
+    for (int I = 0; I < nblk; I++)
+        for (int J = 0; J <= I; J++)
+            for (int K = 0; K <= J; K++) {
+                RingPhase ph{I, J, K, (i64)trips.size() / 3, 0};
+                for (int i = blk_lo(I); i < blk_hi(I); i++)
+                    for (int j = blk_lo(J); j < blk_hi(J) && j <= i; j++)
+                        for (int k = blk_lo(K); k < blk_hi(K) && k <= j; k++)
+                            if (!(i == j && j == k)) { trips.push_back(i); trips.push_back(j); trips.push_back(k); ph.ntrip++; }
+                if (ph.ntrip == 0) continue;
+                // slot map of this block triple: I -> group 0, J -> group 1 unless J == I, K -> group 2 unless K == J (or I)
+                std::vector<int> m((size_t)o, 0);
+                const int gJ = (J == I) ? 0 : 1, gK = (K == J) ? gJ : 2;
+                for (int p = blk_lo(I); p < blk_hi(I); p++) m[p] = 0 * ob + (p - blk_lo(I));
+                for (int p = blk_lo(J); p < blk_hi(J); p++) m[p] = gJ * ob + (p - blk_lo(J));
+                for (int p = blk_lo(K); p < blk_hi(K); p++) m[p] = gK * ob + (p - blk_lo(K));
+                pslots.insert(pslots.end(), m.begin(), m.end());
+                phases.push_back(ph);
+            }
+    i64 total = 0;
+    for (const RingPhase& ph : phases) total += ph.ntrip;
+    if (total != num_triplets(o)) return fail("internal: ring phases hold %lld triplets, expected %lld", (long long)total, (long long)num_triplets(o));
+    for (int g = 0; g < L; g++) {
+        Dev& d = *h->devs[g];
+        CK(cudaSetDevice(d.dev));
+        const Problem& P0 = d.prob;
+        // Qt hole part and OV2 as on the materialised route                                       (DFERI.jl:88-112, 139-154)
+        GemmOut out{};
+        out.P = P0;
+        out.C = d.Qt.d();
+        CK(gemm_tn_launch<EPI_QT_HOLE>(d.stream, dBOO[g], rowmap_identity(), dBOV[g], rowmap_identity(), (i64)o * o, o * v, naux, out, d.n_sm));
+        CK(cudaMemsetAsync(d.OV2.p, 0, (size_t)ov2_elems(P0) * sizeof(double), d.stream));
+        out.C = d.OV2.d();
+        CK(gemm_tn_launch<EPI_OV2>(d.stream, dBOV[g], rowmap_identity(), dBOV[g], rowmap_identity(), (i64)o * v, o * v, naux, out, d.n_sm));
+        if (d.ringtab.ensure((trips.size() + pslots.size()) * sizeof(int))) return 1;
+        int* dtr = (int*)d.ringtab.p;
+        int* dps = dtr + trips.size();
+        // pageable sources: the copies are staged by the driver before the call returns, the vectors may go out of scope
+        CK(cudaMemcpyAsync(dtr, trips.data(), trips.size() * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(dps, pslots.data(), pslots.size() * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        if (g == 0) { CK(cudaEventRecord(d.tl[1], d.copy)); CK(cudaEventRecord(d.tl[2], d.stream)); }
+        CK(cudaEventRecord(d.ev0[0], d.stream));
+        int curI = -1, curJ = -1, curK = -1;
+        for (size_t t = 0; t < phases.size(); t++) {
+            const RingPhase& ph = phases[t];
+            Problem P = current_problem(h, d);
+            const RingMap ring{dps + t * (size_t)o, dtr + 3 * ph.trip_off};
+            P.tw_begin = 0;
+            P.tw_count = ph.ntrip;
+            P.nitems = P.nb * ph.ntrip;
+            if (ph.I != curI) { if (assemble_slabs(h, d, P, ring.pslot, naux, dBOV[g], dBVV[g], blk_lo(ph.I), blk_hi(ph.I))) return 1; curI = ph.I; curJ = curK = -1; }
+            if (ph.J != curJ) { if (ph.J != ph.I && assemble_slabs(h, d, P, ring.pslot, naux, dBOV[g], dBVV[g], blk_lo(ph.J), blk_hi(ph.J))) return 1; curJ = ph.J; curK = -1; }
+            if (ph.K != curK) { if (ph.K != ph.J && assemble_slabs(h, d, P, ring.pslot, naux, dBOV[g], dBVV[g], blk_lo(ph.K), blk_hi(ph.K))) return 1; curK = ph.K; }
+            i64 sb, se;
+            shard_range(h, P, 0, P.nitems, d.grank, h->world, &sb, &se);
+            if (compute_launch(h, d, P, sb, se, -1, t > 0, ring)) return 1;
+        }
+        CK(cudaEventRecord(d.ev1[0], d.stream));
+        d.clean_o = -1;   // the ring's slabs are not the layout a later materialised upload expects to find clean
+    }
+    h->launches += 2 * (int)phases.size() - 2;   // compute_finish counts one kernel + one reduction per GPU itself
+    h->nphase = 1;
+    h->last_profiled = false;
+    return 0;
+}
+
+// Block size of the slab ring for this problem (0: materialise all o slabs).  fpt_set_df_ring: -1 never, 0 automatic -- ring
+// with blocks of 4 when the full Pt would take more than 40 % of the device's memory --, n >= 1 ring with blocks of n.
+static int df_ring_block(fpt_handle* h, int o, int v)
+{
+    if (h->dbg_flags || h->profiling || h->item_order != 1) return 0;
+    if (h->df_ring > 0) return std::min(h->df_ring, o);
+    if (h->df_ring < 0) return 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaSetDevice(h->devs[0]->dev) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const double vp = padded_v(v), Kp = roundup(v + o, KGROUP);
+    const double full = (double)o * vp * vp * Kp * sizeof(double);
+    return (full > 0.4 * (double)total_b && o > 12) ? 4 : 0;
+}
+
 static int triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, const double* T2, const double* BOO, const double* BOV,
                       const double* BVV, const double* fo, const double* fv, double* Et, fpt_stats* st, bool async, const char* who)
 {
@@ -1065,6 +1220,14 @@ static int triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, c
     const auto t0 = wall::now();
     if (admit_device_inputs(h, who, {T1, T2, BOO, BOV, BVV, fo, fv})) return 1;
     upload_begin(h);
+    const int ob = df_ring_block(h, o, v);
+    if (ob > 0) {
+        if (triples_df_ring(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, ob)) return 1;
+        h->last = fpt_stats{};
+        h->last.h2d_bytes = h->h2d;
+        if (compute_collect(h, h->nitems)) return 1;
+        return finish_tail(h, async, t0, Et, st);
+    }
     if (upload_df_impl(h, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv, false)) return 1;
     return finish_call(h, async, t0, Et, st);
 }

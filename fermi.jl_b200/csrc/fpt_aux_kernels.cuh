@@ -50,18 +50,18 @@ __global__ void prep_pt_particle(Problem P, double* Pt, const double* __restrict
     }
 }
 
-// Pt[p][y][x][v+l] = -T2[p,l,y,x]
-__global__ void prep_pt_hole(Problem P, double* Pt, const double* __restrict__ T2)
+// Pt[slot(p)][y][x][v+l] = -T2[p,l,y,x] for p in [p0, p0 + np)   (pslot: slab ring of the DF route, else nullptr)
+__global__ void prep_pt_hole(Problem P, double* Pt, const double* __restrict__ T2, int p0, int np, const int* __restrict__ pslot)
 {
     const int o = P.o, v = P.v;
-    const i64 n = (i64)o * v * v * o;
+    const i64 n = (i64)np * v * v * o;
     for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) {
         const int l = (int)(idx % o);
         i64 t = idx / o;
         const int x = (int)(t % v); t /= v;
         const int y = (int)(t % v);
-        const int p = (int)(t / v);
-        Pt[pt_row(P, p, y, x) + v + l] = -T2[p + (i64)o * (l + (i64)o * (y + (i64)v * x))];
+        const int p = p0 + (int)(t / v);
+        Pt[pt_row_slot(P, pslot, p, y, x) + v + l] = -T2[p + (i64)o * (l + (i64)o * (y + (i64)v * x))];
     }
 }
 

@@ -69,6 +69,7 @@ struct GemmOut {
     Problem P;     // the layout epilogues
     int p0;        // EPI_PT: first occupied index of this launch (the assembly is sharded over p across GPUs)
     int lv, lo2, la0;   // EPI_LADDER_*: v, o^2, first a of this group
+    const int* pslot;   // EPI_PT: slab position of every occupied index (slab ring of the DF route), nullptr = identity
 };
 template <int EPI>
 __device__ __forceinline__ void gemm_store(const GemmOut& out, i64 m, int n, double val)
@@ -78,7 +79,7 @@ __device__ __forceinline__ void gemm_store(const GemmOut& out, i64 m, int n, dou
         out.C[m + out.ldc * n] = val;
     } else if (EPI == EPI_PT) {
         const int y = (int)(m % P.v), pl = (int)(m / P.v), d = n % P.v, x = n / P.v;
-        out.C[pt_row(P, out.p0 + pl, y, x) + d] = val;
+        out.C[pt_row_slot(P, out.pslot, out.p0 + pl, y, x) + d] = val;
     } else if (EPI == EPI_QT_HOLE) {
         const int l = (int)(m % P.o), q = (int)(m / P.o), r = n % P.o, z = n / P.o;
         const int kappa = P.v + l;

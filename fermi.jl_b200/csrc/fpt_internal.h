@@ -139,10 +139,13 @@ struct Dev {
     DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
     // CCSD ladder / MP2: tau^T, the (vv|vv) slabs of one group of a, newT2 on the device, (ia|jb)
     DevBuf xTau, xSlab, xNew, xOVOV;
+    DevBuf ringtab;           // slab-ring mode of the DF route: triplet lists and slot maps of all block triples
+    const double* cur_T2 = nullptr;   // T2 of the current problem on this GPU (the ring re-assembles Pt's hole part from it)
+    int pt_slabs = 0;         // occupied slabs Pt has room for (o, or 3 ob in ring mode)
     Problem prob{};
     int tab_vp = -1;          // the block table on this device was built for this padded virtual dimension
     // Pt holds zeros in its padding (x,y >= v, kappa >= v+o) for this shape: a new upload of the same shape may skip the memset
-    int clean_o = -1, clean_v = -1;
+    int clean_o = -1, clean_v = -1, clean_slabs = 0;
     void* clean_ptr = nullptr;
     int last_grid = 0;
     i64 shard_b = 0, shard_e = 0;
@@ -164,6 +167,7 @@ struct fpt_handle {
     fpt::i64 tw_begin = 0, tw_count = 0, nitems = 0;
     int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
     int dbg_flags = 0;
+    int df_ring = 0;          // fpt_set_df_ring: -1 never, 0 automatic, n >= 1 slab ring with occupied blocks of n
     int sym_inputs = 1;       // pageable host inputs cross PCIe as their symmetry-unique halves (fpt_set_symmetric_inputs)
     bool profiling = false, last_profiled = false;
     int kernel_variant = 1;

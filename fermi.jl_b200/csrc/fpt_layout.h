@@ -393,6 +393,12 @@ struct Problem {
 };
 
 FPT_HD i64 pt_row(const Problem& P, int p, int y, int x) { return (((i64)p * P.vp + y) * P.vp + x) * P.Kp; }
+// Slab-ring mode of the density-fitted route (fpt_api.cu, triples_df_ring): Pt holds only a few occupied slabs at a time --
+// pslot[p] = slab position of occupied p (nullptr: Pt holds all o slabs, position p) -- and the triplets of a launch are an explicit
+// list, trips[3u .. 3u+2] = (i, j, k) of entry u (nullptr: entry u of the reference's list, decoded arithmetically).  Kept out of
+// `Problem`: the fused kernel's default instantiation must not change with it (its k-loops are sensitive to every register).
+struct RingMap { const int* pslot; const int* trips; };
+FPT_HD i64 pt_row_slot(const Problem& P, const int* pslot, int p, int y, int x) { return pt_row(P, pslot ? pslot[p] : p, y, x); }
 FPT_HD i64 qt_row(const Problem& P, int q, int r, int g, int z) { return ((((i64)q * P.o + r) * P.G + g) * P.vp + z) * KGROUP; }
 
 struct ItemDesc { int i, j, k; int A, B, C; };
@@ -441,12 +447,13 @@ FPT_HD i64 triplets_before(int o, i64 t)
     return t - ndiag;
 }
 
-FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block)
+FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block, const int* trips = nullptr)
 {
     i64 u;
     if (P.order == 1) { block = item / P.tw_count; u = item - block * P.tw_count; }
     else              { u = item / P.nb; block = item - u * P.nb; }
-    triplet_decode(P.o, P.tw_begin + u, it.i, it.j, it.k);
+    if (trips) { it.i = trips[3 * u]; it.j = trips[3 * u + 1]; it.k = trips[3 * u + 2]; }
+    else triplet_decode(P.o, P.tw_begin + u, it.i, it.j, it.k);
     tetra_decode(block, it.A, it.B, it.C);
 }
 

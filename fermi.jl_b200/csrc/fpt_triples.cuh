@@ -80,7 +80,8 @@ __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 // ---------------------------------------------------------------------------------------------------
 // Fetch the next item, decode it arithmetically and pull its block's descriptor table entry into ctl->ent with one TMA
 // bulk copy that completes on item_full (the scalar fields are ordinary stores released by the same barrier).
-__device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
+template <bool RING>
+__device__ __forceinline__ void producer_decode(const Problem& P, const RingMap& ring, i64 item_begin, i64 item_end, unsigned long long* counter,
                                                 Ctl* ctl, uint64_t* item_full)
 {
     const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
@@ -90,7 +91,7 @@ __device__ __forceinline__ void producer_decode(const Problem& P, i64 item_begin
         return;
     }
     i64 block;
-    item_decode_cf(P, it, ctl->item, block);
+    item_decode_cf(P, it, ctl->item, block, RING ? ring.trips : nullptr);
     ctl->cur_item = it;
     // ctl->ent was last read by the consumers with ordinary loads (generic proxy); the bulk copy below writes it through the
     // async proxy.  The mbarrier hand-off (item_empty) orders the two only within the generic proxy: a proxy fence is required.
@@ -131,8 +132,8 @@ __device__ __forceinline__ int seq_gemm(const Ctl* ctl, int mode, int t) { retur
 __device__ __forceinline__ int seq_first(const Ctl* ctl, int mode, int t) { return mode == 1 ? ctl->ent.ffirst[t] : ctl->ent.sfirst[mode - 2][t]; }
 __device__ __forceinline__ int seq_emask(const Ctl* ctl, int mode, int g) { return mode == 1 ? 3 : sym_emask(mode - 2, ctl->ent.gemm[g].p); }
 
-template <bool FASTOK, class Tail>
-__device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, i64 item_end, unsigned long long* counter,
+template <bool FASTOK, bool RING, class Tail>
+__device__ __forceinline__ void producer_loop(const Problem& P, const RingMap& ring, i64 item_begin, i64 item_end, unsigned long long* counter,
                                               double* Qsm, Tail* tail)
 {
     const int nchunks = (P.G + CHUNK_GROUPS - 1) / CHUNK_GROUPS;
@@ -140,7 +141,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
     int stage = 0;
     uint32_t sphase = 0;
     mbar_wait((uint64_t*)&tail->item_empty[0], 1);
-    producer_decode(P, item_begin, item_end, counter, &tail->ctl[0], (uint64_t*)&tail->item_full[0]);
+    producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[0], (uint64_t*)&tail->item_full[0]);
     for (uint32_t n = 0;; n++) {
         const int slot = n & 1;
         const Ctl* ctl = &tail->ctl[slot];
@@ -178,7 +179,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, i64 item_begin, 
             if (t == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
                 const uint32_t m = n + 1;
                 mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
-                producer_decode(P, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
+                producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
             }
         }
         // Energy stage of this item: the ring area is reused for the 12 OV2 tiles whose row index is a, so that the a-loop of the
@@ -223,10 +224,11 @@ __device__ __forceinline__ void warp_rows(int rt_total, int w, int& rt0, int& nv
     rt0 = w * base + min(w, extra);
 }
 
-__device__ __forceinline__ void rows_setup2(const Problem& P, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
+template <bool RING>
+__device__ __forceinline__ void rows_setup2(const Problem& P, const RingMap& ring, const GemmDesc& gd, int p_orb, int warp, int lane, RowSet& rs)
 {
     const int r = lane >> 2, kk = lane & 3;
-    rs.base = P.Pt + pt_row(P, p_orb, gd.y0, gd.x0) + 4 * kk;
+    rs.base = P.Pt + pt_row(P, RING ? ring.pslot[p_orb] : p_orb, gd.y0, gd.x0) + 4 * kk;
     warp_rows(gd.rt_total, warp, rs.rt0, rs.nvalid);
 #pragma unroll
     for (int mt = 0; mt < MTW_MAX; mt++) {
@@ -405,8 +407,8 @@ __device__ __forceinline__ void gemm_wslots(const GemmDesc& gd, const RowSet& rs
 }
 
 // one GEMM of an item: k-loop, then (overlapped with the RMW epilogue) the next GEMM's row setup and first A loads
-template <int MTW, int NT, bool PROF>
-__device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int g, RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
+template <int MTW, int NT, bool PROF, bool RING>
+__device__ __forceinline__ void gemm_body(const Problem& P, const RingMap& ring, const Ctl* ctl, int g, RowSet& rs, double4x (&a)[ABUF][MTW_MAX],
                                           double* Wsm, const double* Qsm, SmemTail* tail, int& stage, uint32_t& sphase,
                                           uint32_t& gcount, int warp, int lane, long long* prof)
 {
@@ -422,7 +424,7 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
     const int gnext = g + (dup_next ? 2 : 1);
     if (gnext < ctl->ent.ngemm) {
         const GemmDesc& gn = ctl->ent.gemm[gnext];
-        rows_setup2(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        rows_setup2<RING>(P, ring, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue2(P, rs, a);
     }
     for (int rep = 0; rep <= (dup_next ? 1 : 0); rep++) {
@@ -446,8 +448,8 @@ __device__ __forceinline__ void gemm_body(const Problem& P, const Ctl* ctl, int 
 }
 
 // load-accumulate-store form of one GEMM (see the comment at the top): g = forder[t], gnext = forder[t+1] or -1
-template <int MTW, int NT, bool PROF>
-__device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl, int g, int gnext, int first_bits, int emask, RowSet& rs,
+template <int MTW, int NT, bool PROF, bool RING>
+__device__ __forceinline__ void gemm_body_fast(const Problem& P, const RingMap& ring, const Ctl* ctl, int g, int gnext, int first_bits, int emask, RowSet& rs,
                                                double4x (&a)[ABUF][MTW_MAX], double* Wsm, const double* Qsm, SmemTail* tail,
                                                int& stage, uint32_t& sphase, uint32_t& gcount, int warp, int lane, long long* prof)
 {
@@ -469,7 +471,7 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
     const RowSet rs_cur = rs;
     if (gnext >= 0) {
         const GemmDesc& gn = ctl->ent.gemm[gnext];
-        rows_setup2(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        rows_setup2<RING>(P, ring, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue2(P, rs, a);
     }
     if constexpr (MTW > 0) {
@@ -503,9 +505,9 @@ __device__ __forceinline__ void gemm_body_fast(const Problem& P, const Ctl* ctl,
 // {wait-for-item, zero, k-loops, RMW (+token wait, next prologue), energy, total, token wait, -} for warp 0 (entries 0-7)
 // and for the first warp of the last group (entries 8-15).
 // ---------------------------------------------------------------------------------------------------
-template <bool PROF>
+template <bool PROF, bool RING = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
-triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* counter, double* partials, long long* prof_out)
+triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* counter, double* partials, long long* prof_out, RingMap ring)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Wsm = reinterpret_cast<double*>(smem_raw);
@@ -527,7 +529,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
 
     if (warp >= NCWARPS) {   // producer warpgroup
         setmaxnreg_dec<PRODUCER_REGS>();
-        if (warp == NCWARPS && lane == 0) producer_loop<true>(P, item_begin, item_end, counter, Qsm, tail);
+        if (warp == NCWARPS && lane == 0) producer_loop<true, RING>(P, ring, item_begin, item_end, counter, Qsm, tail);
         return;
     }
     setmaxnreg_inc<CONSUMER_REGS>();
@@ -554,7 +556,7 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
         const int mode = item_mode(P, ctl);
         const int gfirst = mode ? seq_gemm(ctl, mode, 0) : 0;
         RowSet rs;
-        rows_setup2(P, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
+        rows_setup2<RING>(P, ring, ctl->ent.gemm[gfirst], occ_pick(ctl->item, ctl->ent.gemm[gfirst].p), warp, lane, rs);
         a_prologue2(P, rs, a);
         // the W slots are not zeroed: the first GEMM that reaches a slot stores into it (GemmDesc::dfirst / ffirst / sfirst);
         // the barrier at the end of the previous item's energy stage already ordered those stores after its reads
@@ -572,14 +574,14 @@ triples_kernel(Problem P, i64 item_begin, i64 item_end, unsigned long long* coun
                 // compiler that the value is warp-uniform: without it the k-loops are compiled as potentially divergent code
                 // (BSSY / WARPSYNC / BRA.DIV in the hot loop, no uniform-datapath instructions: -1.5 % on full-tile shapes)
                 const int nv = __shfl_sync(0xffffffffu, rs.nvalid, 0);
-                FPT_DISPATCH(nv, nt, (gemm_body_fast<MTW, NT, PROF>(P, ctl, g, gnext, fbits, emask, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                FPT_DISPATCH(nv, nt, (gemm_body_fast<MTW, NT, PROF, RING>(P, ring, ctl, g, gnext, fbits, emask, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         } else {
             for (int g = 0; g < ngemm; g++) {
                 if (gemm_is_dup(ctl->item, g)) continue;   // handled by its twin (second RMW in gemm_body)
                 const int nt = ctl->ent.gemm[g].TZ >> 2;
                 const int nv = __shfl_sync(0xffffffffu, rs.nvalid, 0);   // warp-uniform, see above
-                FPT_DISPATCH(nv, nt, (gemm_body<MTW, NT, PROF>(P, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
+                FPT_DISPATCH(nv, nt, (gemm_body<MTW, NT, PROF, RING>(P, ring, ctl, g, rs, a, Wsm, Qsm, tail, stage, sphase, gcount, warp, lane, prof)));
             }
         }
         if (PROF) t1 = clock64();

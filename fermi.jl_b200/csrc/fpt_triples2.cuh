@@ -66,7 +66,7 @@ __device__ __forceinline__ void gemm_body2(const Problem& P, const Ctl* ctl, int
     const int gnext = g + (dup_next ? 2 : 1);
     if (gnext < ctl->ent.ngemm) {
         const GemmDesc& gn = ctl->ent.gemm[gnext];
-        rows_setup2(P, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
+        rows_setup2<false>(P, RingMap{nullptr, nullptr}, gn, occ_pick(ctl->item, gn.p), warp, lane, rs);
         a_prologue2(P, rs, a);
     }
     if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
@@ -239,7 +239,7 @@ triples_kernel2(Problem P, i64 item_begin, i64 item_end, unsigned long long* cou
 
     if (warp >= NCWARPS + NEWARPS) {   // producer warpgroup
         setmaxnreg_dec<PRODUCER_REGS2>();
-        if (warp == NCWARPS + NEWARPS && lane == 0) producer_loop<false>(P, item_begin, item_end, counter, Qsm, tail);
+        if (warp == NCWARPS + NEWARPS && lane == 0) producer_loop<false, false>(P, RingMap{nullptr, nullptr}, item_begin, item_end, counter, Qsm, tail);
         return;
     }
     if (warp >= NCWARPS) {             // epilogue warpgroup
@@ -271,7 +271,7 @@ triples_kernel2(Problem P, i64 item_begin, i64 item_end, unsigned long long* cou
 
         const int ngemm = ctl->ent.ngemm;
         RowSet rs;
-        rows_setup2(P, ctl->ent.gemm[0], occ_pick(ctl->item, ctl->ent.gemm[0].p), warp, lane, rs);
+        rows_setup2<false>(P, RingMap{nullptr, nullptr}, ctl->ent.gemm[0], occ_pick(ctl->item, ctl->ent.gemm[0].p), warp, lane, rs);
         a_prologue2(P, rs, a);
         if (PROF) { t0 = clock64(); prof[1] += t0 - t1; }
 

@@ -91,6 +91,14 @@ int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, cons
                    const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
                    fpt_stats* stats);
 
+/* Slab ring of the density-fitted route: instead of all o slabs (p.|..) -- o vp^2 Kp doubles, 22.9 GB at o = 40, v = 400 -- only the
+ * 3 * block slabs of the current block triple of occupied indices are resident and are re-assembled from the B factors on the fly
+ * (cost: naux / (6 block^2 (v + o)) of the (T) work).  block = -1: never; 0 (default): automatic, blocks of 4 when the full set would
+ * take more than 40 % of the device memory; n >= 1: always, with blocks of n (n = 1: three slabs in all).  Applies to fpt_triples_df
+ * and fpt_triples_df_async; fpt_upload_df always materialises.  fpt_device_bytes: device memory the handle holds on its first GPU. */
+int fpt_set_df_ring(fpt_handle* h, int block);
+int fpt_device_bytes(fpt_handle* h, double* bytes);
+
 /* Asynchronous forms (gradient_findif makes 6 N_atoms (T) calls, FiniteDifferences.jl:48-74): the call returns
  * as soon as the caller's arrays have been consumed -- they may be freed or overwritten, the next CCSD can start on the CPU --
  * while the GPU is still computing; fpt_wait blocks for E(T).  One call may be in flight per handle. */

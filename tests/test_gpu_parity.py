@@ -505,3 +505,37 @@ def test_symmetry_unique_halves(engine, o, v):
         engine.set_symmetric_inputs(True)
     assert abs(e_asym - e_asym_full) < 1e-13 and abs(e_asym - e_half) > 1e-6
     assert st_asym["h2d_bytes"] == _expected_h2d(y) + 8 * (y.OVVV.size - o * v * (v * (v + 1) // 2))
+
+
+@pytest.mark.parametrize("o,v,naux,blocks", [(5, 19, 9, (1, 2, 4)), (9, 31, 37, (1, 4)), (13, 41, 64, (2, 5)), (15, 93, 420, (4,))])
+def test_df_slab_ring(built, o, v, naux, blocks):
+    """DF route with only 3 * block occupied slabs resident (re-assembled from the B factors on the fly, block triple by block triple,
+    explicit triplet lists + slot maps): same E(T) as the materialised route and as the oracle; the handle's device memory shrinks
+    accordingly.  Fresh handles, so that the buffer pool shows what each mode needs."""
+    x = fb.synth.make_inputs(o, v, naux=naux, seed=3 * o + v)
+    ref = oracle.pt_gemm(*_args(x))
+    df = (o, v, naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+    full = fb.Engine(0)
+    full.set_df_ring(-1)
+    e_full, _ = full.triples_df(*df)
+    bytes_full = full.device_bytes()
+    full.close()
+    assert abs(e_full - ref) < TOL
+    vp, Kp = (v + 3) // 4 * 4, (v + o + 15) // 16 * 16
+    slab = vp * vp * Kp * 8
+    for ob in blocks:
+        ring = fb.Engine(0)
+        ring.set_df_ring(ob)
+        e_ring, st = ring.triples_df(*df)
+        assert abs(e_ring - ref) < TOL, (ob, e_ring, ref)
+        assert abs(e_ring - e_full) < 1e-12
+        assert st["n_items"] == fb.host.num_items(o, v)
+        if 3 * ob < o:
+            # (+ the ring's triplet lists and slot maps)
+            assert ring.device_bytes() <= bytes_full - (o - 3 * ob) * slab + 65536, (ob, ring.device_bytes(), bytes_full)
+        ring.triples_df_async(*df)               # the asynchronous form takes the same route
+        e_async, _ = ring.wait()
+        assert abs(e_async - e_ring) < 1e-13
+        with pytest.raises(fb.FermiException):
+            ring.compute(0, -1)                  # nothing is left resident after a ring evaluation
+        ring.close()
