@@ -60,14 +60,16 @@ def test_c3_benzene_df_shape(engine):
 
 
 def test_c4_h2o6_shape_partial_and_sharded(engine):
-    """(H2O)6 shape: the oracle checks the last two (i,j) pairs' triplets; the full run is checked through
-    size-independent properties: shards add up to the whole, and the DF route reproduces the conventional one."""
+    """(H2O)6 shape: the oracle checks the triplets of i = 21, 22, 23 -- 829 of the 2600 positions of the reference's list, 32 % -- in one
+    window; the full run is checked through size-independent properties: shards add up to the whole, and the DF route reproduces
+    the conventional one."""
     o, v = 24, 114
     x = fb.synth.make_inputs(o, v, naux=64)
     engine.upload_conv(o, v, *_args(x))
     n = engine.num_items()
     npair = o * (o + 1) // 2
-    tb, te = fb.host.pair_range_triplets(o, npair - 2, npair)
+    tb, te = fb.host.pair_range_triplets(o, 21 * 22 // 2, npair)
+    assert te - tb == 829 and te == 2600
     engine.set_triplet_window(tb, te)
     part, _ = engine.compute(0, -1)
     ref = oracle.pt_gemm(*_args(x), t_begin=tb, t_end=te)
