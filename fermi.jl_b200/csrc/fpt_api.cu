@@ -228,6 +228,13 @@ extern "C" int fpt_set_symmetric_inputs(fpt_handle* h, int on)
     return 0;
 }
 
+extern "C" int fpt_set_deterministic(fpt_handle* h, int on)
+{
+    if (!h) return fail("fpt_set_deterministic: NULL handle");
+    h->deterministic = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int fpt_set_df_ring(fpt_handle* h, int block)
 {
     if (!h) return fail("fpt_set_df_ring: NULL handle");
@@ -845,7 +852,7 @@ static Problem current_problem(const fpt_handle* h, const Dev& d)
 {
     Problem P = d.prob;
     P.order = h->item_order;
-    P.dbg_flags = h->dbg_flags;
+    P.dbg_flags = h->dbg_flags | (h->deterministic ? 512 : 0);
     P.tw_begin = h->tw_begin;
     P.tw_count = h->tw_count;
     P.nitems = h->nitems;

@@ -167,6 +167,7 @@ struct fpt_handle {
     fpt::i64 tw_begin = 0, tw_count = 0, nitems = 0;
     int item_order = 1;       // 1: block-major (default), 0: triplet-major (see Problem::order)
     int dbg_flags = 0;
+    int deterministic = 0;    // fpt_set_deterministic: static item -> CTA deal, E(T) bitwise reproducible from run to run
     int df_ring = 0;          // fpt_set_df_ring: -1 never, 0 automatic, n >= 1 slab ring with occupied blocks of n
     int sym_inputs = 1;       // pageable host inputs cross PCIe as their symmetry-unique halves (fpt_set_symmetric_inputs)
     bool profiling = false, last_profiled = false;

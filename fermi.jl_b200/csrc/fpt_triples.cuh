@@ -82,9 +82,12 @@ __device__ __forceinline__ void consumer_bar() { named_bar_sync(1, NCTHREADS); }
 // bulk copy that completes on item_full (the scalar fields are ordinary stores released by the same barrier).
 template <bool RING>
 __device__ __forceinline__ void producer_decode(const Problem& P, const RingMap& ring, i64 item_begin, i64 item_end, unsigned long long* counter,
-                                                Ctl* ctl, uint64_t* item_full)
+                                                Ctl* ctl, uint64_t* item_full, uint32_t& nfetch)
 {
-    const i64 it = item_begin + (i64)atomicAdd(counter, 1ULL);
+    // dynamic: the next item off the global counter (which CTA sums which items then varies from run to run, and E(T) with it in the
+    // last bits); deterministic (fpt_set_deterministic, dbg_flags bit 512): CTA b takes items b, b + grid, b + 2 grid, ... -- in the
+    // block-major list neighbouring items cost the same, so the static deal is balanced up to the block boundaries
+    const i64 it = (P.dbg_flags & 512) ? item_begin + blockIdx.x + (i64)(nfetch++) * gridDim.x : item_begin + (i64)atomicAdd(counter, 1ULL);
     if (it >= item_end) {
         ctl->cur_item = -1;
         mbar_arrive(item_full);
@@ -140,8 +143,9 @@ __device__ __forceinline__ void producer_loop(const Problem& P, const RingMap& r
     const i64 gstride = (i64)P.vp * KGROUP;   // doubles between consecutive kappa groups of one (q,r) in Qt
     int stage = 0;
     uint32_t sphase = 0;
+    uint32_t nfetch = 0;
     mbar_wait((uint64_t*)&tail->item_empty[0], 1);
-    producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[0], (uint64_t*)&tail->item_full[0]);
+    producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[0], (uint64_t*)&tail->item_full[0], nfetch);
     for (uint32_t n = 0;; n++) {
         const int slot = n & 1;
         const Ctl* ctl = &tail->ctl[slot];
@@ -179,7 +183,7 @@ __device__ __forceinline__ void producer_loop(const Problem& P, const RingMap& r
             if (t == 0) {   // consumers are inside item n now, so ctl[slot^1] (item n-1) is, or soon will be, released
                 const uint32_t m = n + 1;
                 mbar_wait((uint64_t*)&tail->item_empty[m & 1], ((m >> 1) & 1) ^ 1);
-                producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1]);
+                producer_decode<RING>(P, ring, item_begin, item_end, counter, &tail->ctl[m & 1], (uint64_t*)&tail->item_full[m & 1], nfetch);
             }
         }
         // Energy stage of this item: the ring area is reused for the 12 OV2 tiles whose row index is a, so that the a-loop of the

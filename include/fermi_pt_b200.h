@@ -91,6 +91,12 @@ int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, cons
                    const double* BOV, const double* BVV, const double* fo, const double* fv, double* Et,
                    fpt_stats* stats);
 
+/* E(T) is a sum of per-CTA partial sums added in a fixed order; by default the CTAs pull work items off a global counter, so which
+ * CTA sums which items -- and with it the last bits of E(T), ~1e-16 relative -- varies from run to run.  on = 1: items are dealt
+ * statically (CTA b takes items b, b + grid, ...): the same call on the same GPU type returns the same bits every time, at the cost of
+ * the dynamic balance (measured at C4: see DESIGN.md). */
+int fpt_set_deterministic(fpt_handle* h, int on);
+
 /* Slab ring of the density-fitted route: instead of all o slabs (p.|..) -- o vp^2 Kp doubles, 22.9 GB at o = 40, v = 400 -- only the
  * 3 * block slabs of the current block triple of occupied indices are resident and are re-assembled from the B factors on the fly
  * (cost: naux / (6 block^2 (v + o)) of the (T) work).  block = -1: never; 0 (default): automatic, blocks of 4 when the full set would

@@ -541,3 +541,21 @@ def test_df_slab_ring(built, o, v, naux, blocks):
         with pytest.raises(fb.FermiException):
             ring.compute(0, -1)                  # nothing is left resident after a ring evaluation
         ring.close()
+
+
+def test_deterministic_mode_is_bitwise_reproducible(engine):
+    """fpt_set_deterministic: items are dealt statically to the CTAs, so repeated evaluations return the same bits (the default dynamic
+    counter only promises ~1e-16 relative); the value itself agrees with the dynamic mode to the usual noise."""
+    o, v = 6, 70
+    x = fb.synth.make_inputs(o, v, naux=12, seed=77)
+    engine.upload_conv(o, v, *_args(x))
+    e_dyn, _ = engine.compute(0, -1)
+    engine.set_deterministic(True)
+    try:
+        runs = [engine.compute(0, -1)[0] for _ in range(6)]
+        one_call = [engine.triples_conv(o, v, *_args(x))[0] for _ in range(3)]
+    finally:
+        engine.set_deterministic(False)
+    assert len(set(runs)) == 1 and len(set(one_call)) == 1, (runs, one_call)
+    assert abs(runs[0] - e_dyn) < 1e-13 and abs(one_call[0] - e_dyn) < 1e-13
+    assert abs(runs[0] - oracle.pt_gemm(*_args(x))) < TOL
