@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao", "fpt_triples_ao_sparse", "fpt_upload_ao_sparse",
-           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_set_df_ring", "fpt_device_bytes", "fpt_set_deterministic", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_ccsd_ladder_df", "fpt_mp2_df", "fpt_mp2_conv", "fpt_gemm_bench", "fpt_last_timeline",
+           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_set_df_ring", "fpt_device_bytes", "fpt_set_deterministic", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_ccsd_ladder_df", "fpt_mp2_df", "fpt_mp2_conv", "fpt_triples_conv_f32", "fpt_triples_df_f32", "fpt_gemm_bench", "fpt_last_timeline",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -82,6 +82,8 @@ def load_library():
     L.fpt_ccsd_ladder_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.POINTER(Stats)]
     L.fpt_mp2_df.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, _dp, ctypes.POINTER(Stats)]
     L.fpt_mp2_conv.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, _dp, ctypes.POINTER(Stats)]
+    L.fpt_triples_conv_f32.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
+    L.fpt_triples_df_f32.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7 + [_dp, ctypes.POINTER(Stats)]
     L.fpt_gemm_bench.argtypes = [vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp]
     L.fpt_last_timeline.argtypes = [vp, _dp]
     for f in EXPORTS:
@@ -200,6 +202,24 @@ class Engine:
         ps = [_ptr(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
         e, st = ctypes.c_double(), Stats()
         self._check(self._L.fpt_triples_df(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    @staticmethod
+    def _ptr32(a):
+        arr = np.asfortranarray(a, dtype=np.float32)
+        return ctypes.c_void_p(arr.ctypes.data), arr
+
+    def triples_conv_f32(self, o, v, T1, T2, OVVV, OOOV, OVOV, fo, fv):
+        """Float32 arrays as they are (half the PCIe bytes), widened on the GPU, FP64 arithmetic."""
+        ps = [self._ptr32(a) for a in (T1, T2, OVVV, OOOV, OVOV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_conv_f32(self._h, o, v, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
+        return e.value, st.asdict()
+
+    def triples_df_f32(self, o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv):
+        ps = [self._ptr32(a) for a in (T1, T2, BOO, BOV, BVV, fo, fv)]
+        e, st = ctypes.c_double(), Stats()
+        self._check(self._L.fpt_triples_df_f32(self._h, o, v, naux, *[p for p, _ in ps], ctypes.byref(e), ctypes.byref(st)))
         return e.value, st.asdict()
 
     def ccsd_ladder_df(self, o, v, naux, T1, T2, BVV, newT2):

@@ -36,7 +36,9 @@ static void dev_destroy(Dev* d)
     cudaSetDevice(d->dev);
     if (d->comm) nccl_api().CommDestroy(d->comm);
     DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab, &d->sBOO, &d->sBOV, &d->sBVV,
+                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab,
+                      &d->f32in[0], &d->f32in[1], &d->f32in[2], &d->f32in[3], &d->f32in[4], &d->f32in[5], &d->f32in[6],
+                      &d->f32wide[0], &d->f32wide[1], &d->f32wide[2], &d->f32wide[3], &d->f32wide[4], &d->f32wide[5], &d->f32wide[6], &d->sBOO, &d->sBOV, &d->sBVV,
                       &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
                       &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
     for (DevBuf* b : bufs) b->release();
@@ -1271,6 +1273,89 @@ extern "C" int fpt_wait(fpt_handle* h, double* Et, fpt_stats* st)
     h->last.total_ms = h->last.upload_ms + ms_since(t0);   // host time inside the two calls
     if (st) *st = h->last;
     return 0;
+}
+
+// ---- single-precision callers -------------------------------------------------------------------------------
+// `@set precision single` makes every array of the reference Float32 (IntegralHelper.jl:58-68).  The f32 entry points take those
+// arrays as they are: they cross PCIe in 4-byte form (half the bytes of the Float64 call), are widened on the handle's first GPU
+// (widen_f32_kernel) and then take the device-input route of the Float64 call -- the arithmetic is FP64 throughout, so the result is
+// the exact (T) energy of the rounded inputs, which the reference's Float32 loops only approximate.
+static int widen_inputs(fpt_handle* h, const char* who, std::initializer_list<std::pair<const float*, size_t>> arrays, const double** out)
+{
+    Dev& d = *h->devs[0];
+    CK(cudaSetDevice(d.dev));
+    CK(cudaEventRecord(d.ev_start, d.stream));
+    CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));
+    std::vector<View> views;
+    views.reserve(arrays.size());
+    std::vector<StagePool::Job> jobs;
+    int k = 0;
+    for (const auto& a : arrays) {
+        if (k >= Dev::NF32) return fail("internal: too many arrays for %s", who);
+        if (classify(a.first) == PK_DEVICE) return fail("%s: Float32 inputs must be host memory", who);
+        if (d.f32in[k].ensure(a.second * sizeof(float)) || d.f32wide[k].ensure(a.second * sizeof(double))) return 1;
+        views.push_back(View::contiguous(a.second * sizeof(float)));
+        if (stage_to(h, d, d.f32in[k].p, a.first, views.back(), 0, a.second * sizeof(float), classify(a.first), jobs)) return 1;
+        k++;
+    }
+    if (stage_flush(h, jobs)) return 1;
+    if (copy_then_stream(d)) return 1;
+    k = 0;
+    for (const auto& a : arrays) {
+        widen_f32_kernel<<<grid1d((i64)a.second), 256, 0, d.stream>>>(d.f32wide[k].d(), (const float*)d.f32in[k].p, (i64)a.second);
+        out[k] = d.f32wide[k].d();
+        k++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d.stream));   // the Float64 call that follows synchronises the device anyway (device-resident inputs)
+    return 0;
+}
+
+extern "C" int fpt_triples_conv_f32(fpt_handle* h, int o, int v, const float* T1, const float* T2, const float* OVVV, const float* OOOV,
+                                    const float* OVOV, const float* fo, const float* fv, double* Et, fpt_stats* st)
+{
+    if (check_idle(h, "fpt_triples_conv_f32")) return 1;
+    if (!T1 || !T2 || !OVVV || !OOOV || !OVOV || !fo || !fv || !Et) return fail("fpt_triples_conv_f32: NULL argument");
+    if (o < 1 || v < 1) return fail("invalid dimensions o=%d v=%d", o, v);
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    const size_t so = o, sv = v;
+    const double* w[7];
+    const double h2d0 = 0.0;
+    upload_begin(h);
+    if (widen_inputs(h, "fpt_triples_conv_f32", {{T1, so * sv}, {T2, so * so * sv * sv}, {OVVV, so * sv * sv * sv}, {OOOV, so * so * so * sv},
+                                                  {OVOV, so * sv * so * sv}, {fo, so}, {fv, sv}}, w)) return 1;
+    const double moved = h->h2d - h2d0;
+    const int rc = triples_conv(h, o, v, w[0], w[1], w[2], w[3], w[4], w[5], w[6], Et, st, false, "fpt_triples_conv_f32");
+    if (!rc) {
+        h->last.h2d_bytes = moved;
+        h->last.total_ms = ms_since(t0);
+        if (st) *st = h->last;
+    }
+    return rc;
+}
+
+extern "C" int fpt_triples_df_f32(fpt_handle* h, int o, int v, int naux, const float* T1, const float* T2, const float* BOO, const float* BOV,
+                                  const float* BVV, const float* fo, const float* fv, double* Et, fpt_stats* st)
+{
+    if (check_idle(h, "fpt_triples_df_f32")) return 1;
+    if (!T1 || !T2 || !BOO || !BOV || !BVV || !fo || !fv || !Et) return fail("fpt_triples_df_f32: NULL argument");
+    if (o < 1 || v < 1 || naux < 1) return fail("invalid dimensions o=%d v=%d naux=%d", o, v, naux);
+    DeviceGuard guard;
+    const auto t0 = wall::now();
+    const size_t so = o, sv = v, sq = naux;
+    const double* w[7];
+    upload_begin(h);
+    if (widen_inputs(h, "fpt_triples_df_f32", {{T1, so * sv}, {T2, so * so * sv * sv}, {BOO, sq * so * so}, {BOV, sq * so * sv}, {BVV, sq * sv * sv},
+                                                {fo, so}, {fv, sv}}, w)) return 1;
+    const double moved = h->h2d;
+    const int rc = triples_df(h, o, v, naux, w[0], w[1], w[2], w[3], w[4], w[5], w[6], Et, st, false, "fpt_triples_df_f32");
+    if (!rc) {
+        h->last.h2d_bytes = moved;
+        h->last.total_ms = ms_since(t0);
+        if (st) *st = h->last;
+    }
+    return rc;
 }
 
 // ---- DF-CCSD particle-particle ladder ------------------------------------------------------------------------

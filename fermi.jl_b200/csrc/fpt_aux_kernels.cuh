@@ -176,6 +176,12 @@ __global__ void expand_ovov_tri(int o, int v, double* __restrict__ OVOV, const d
     }
 }
 
+// Float32 inputs (`@set precision single`, IntegralHelper.jl:58-68): the arrays cross PCIe as they are and are widened on the device
+__global__ void widen_f32_kernel(double* __restrict__ dst, const float* __restrict__ src, i64 n)
+{
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (i64)gridDim.x * blockDim.x) dst[idx] = (double)src[idx];
+}
+
 // T1d[p][x] = T1[p,x]
 __global__ void prep_t1(Problem P, double* T1d, const double* __restrict__ T1)
 {

@@ -139,6 +139,8 @@ struct Dev {
     DevBuf sCo, sCv, aoDense, sIdx, sVals, aoQ1, aoQ2v, aoQ2o, aoQ3vv, aoQ3vo, aoQ3oo, aoOVVV, aoOOOV, aoOVOV, aoFlag;
     // CCSD ladder / MP2: tau^T, the (vv|vv) slabs of one group of a, newT2 on the device, (ia|jb)
     DevBuf xTau, xSlab, xNew, xOVOV;
+    static constexpr int NF32 = 7;
+    DevBuf f32in[NF32], f32wide[NF32];   // Float32 callers: the arrays as they arrive and their widened images
     DevBuf ringtab;           // slab-ring mode of the DF route: triplet lists and slot maps of all block triples
     const double* cur_T2 = nullptr;   // T2 of the current problem on this GPU (the ring re-assembles Pt's hole part from it)
     int pt_slabs = 0;         // occupied slabs Pt has room for (o, or 3 ob in ring mode)

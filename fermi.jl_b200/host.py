@@ -165,10 +165,15 @@ class RCCSDpT:
         eng = engine if engine is not None else _engine(device)
         output("Computing energy contribution from occupied orbitals:")
         t0 = time.perf_counter()
+        # `@set precision single` (IntegralHelper{Float32}, IntegralHelper.jl:58-68): Float32 arrays go down as they are
+        single = lambda *arrs: all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in arrs)
         if moints.is_df and "OVVV" not in moints:
             BOO, BOV, BVV = moints["BOO"], moints["BOV"], moints["BVV"]
             naux = BOV.shape[0]
-            Et, st = eng.triples_df(o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)
+            if single(T1, T2, BOO, BOV, BVV, fo, fv):
+                Et, st = eng.triples_df_f32(o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)
+            else:
+                Et, st = eng.triples_df(o, v, naux, T1, T2, BOO, BOV, BVV, fo, fv)
         elif "OVVV" not in moints and moints.has_ao_route:
             # the reference would now run compute_OVVV!/OOOV!/OVOV! on the CPU (Chonky.jl:28-114); the AO tensor goes to the GPU
             Co, Cv = moints.orbital_blocks()
@@ -179,6 +184,8 @@ class RCCSDpT:
                 Et, st = eng.triples_ao_sparse(Co.shape[0], o, v, T1, T2, eri.indexes, eri.data, Co, Cv, fo, fv)
             else:
                 Et, st = eng.triples_ao(Co.shape[0], o, v, T1, T2, moints.aoints["ERI"], Co, Cv, fo, fv)
+        elif single(T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv):
+            Et, st = eng.triples_conv_f32(o, v, T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv)
         else:
             Et, st = eng.triples_conv(o, v, T1, T2, moints["OVVV"], moints["OOOV"], moints["OVOV"], fo, fv)
         t = time.perf_counter() - t0

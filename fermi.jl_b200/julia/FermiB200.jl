@@ -79,14 +79,40 @@ function RCCSDpT(mol::Molecule, Alg::B200)                    # ijk.jl:12-18
 end
 
 dense(A) = A isa Array{Float64} ? A : collect(Float64, A)
+dense32(A) = A isa Array{Float32} ? A : collect(Float32, A)
 
 function RCCSDpT(ccsd::RCCSD, moints::IntegralHelper{T,E,O}, Alg::B200) where {T<:AbstractFloat,
                                                                               E<:AbstractERI,O<:AbstractRestrictedOrbitals}
-    # `@set precision single` (T = Float32, IntegralHelper.jl:58-68): the arrays are widened once (dense() below) and the
-    # correction is evaluated in FP64 on the GPU -- at least as accurate as the reference's Float32 loops; the result struct
-    # keeps the caller's T
+    # `@set precision single` (T = Float32, IntegralHelper.jl:58-68): cached blocks / B factors go down in 4-byte form through the f32
+    # entry points (widened on the GPU); the correction is evaluated in FP64 -- the exact (T) energy of the rounded inputs, which the
+    # reference's Float32 loops only approximate; the result struct keeps the caller's T
     output("\n   • Perturbative Triples Started\n")
     output("   - Contraction Engine: B200 DMMA (libfermi_pt_b200)")
+    if T === Float32 && (haskey(moints.cache, "OVVV") || moints.eri_type isa AbstractDFERI)
+        o, v = size(ccsd.T1)
+        Et = Ref{Cdouble}(0.0)
+        st = Ref{FptStats}()
+        output("Computing energy contribution from occupied orbitals:")
+        t = @elapsed begin
+            T1 = dense32(ccsd.T1); T2 = dense32(ccsd.T2); fo = dense32(moints["Fii"]); fv = dense32(moints["Faa"])
+            if haskey(moints.cache, "OVVV")
+                check(ccall((:fpt_triples_conv_f32, LIB), Cint,
+                            (Ptr{Cvoid}, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat},
+                             Ref{Cdouble}, Ref{FptStats}),
+                            handle(), o, v, T1, T2, dense32(moints["OVVV"]), dense32(moints["OOOV"]), dense32(moints["OVOV"]), fo, fv, Et, st))
+            else
+                BOV = dense32(moints["BOV"])
+                check(ccall((:fpt_triples_df_f32, LIB), Cint,
+                            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat},
+                             Ref{Cdouble}, Ref{FptStats}),
+                            handle(), o, v, size(BOV, 1), T1, T2, dense32(moints["BOO"]), BOV, dense32(moints["BVV"]), fo, fv, Et, st))
+            end
+        end
+        output("Finished in {:5.5f} s", t)
+        output("Final (T) contribution: {:15.10f}", Et[])
+        output("CCSD(T) energy:         {:15.10f}", Et[] + ccsd.energy)
+        return RCCSDpT{T}(ccsd, T(Et[] + ccsd.energy), T(Et[]))
+    end
     T1 = dense(ccsd.T1); T2 = dense(ccsd.T2)
     o, v = size(T1)
     fo = dense(moints["Fii"]); fv = dense(moints["Faa"])

@@ -105,6 +105,14 @@ int fpt_set_deterministic(fpt_handle* h, int on);
 int fpt_set_df_ring(fpt_handle* h, int block);
 int fpt_device_bytes(fpt_handle* h, double* bytes);
 
+/* Single-precision callers (`@set precision single` makes every array of the reference Float32, IntegralHelper.jl:58-68): the same
+ * arrays as above in 4-byte form, host memory.  They cross PCIe as they are (half the bytes), are widened on the GPU and evaluated in
+ * FP64: Et is the exact (T) energy of the rounded inputs. */
+int fpt_triples_conv_f32(fpt_handle* h, int o, int v, const float* T1, const float* T2, const float* OVVV, const float* OOOV,
+                         const float* OVOV, const float* fo, const float* fv, double* Et, fpt_stats* stats);
+int fpt_triples_df_f32(fpt_handle* h, int o, int v, int naux, const float* T1, const float* T2, const float* BOO, const float* BOV,
+                       const float* BVV, const float* fo, const float* fv, double* Et, fpt_stats* stats);
+
 /* Asynchronous forms (gradient_findif makes 6 N_atoms (T) calls, FiniteDifferences.jl:48-74): the call returns
  * as soon as the caller's arrays have been consumed -- they may be freed or overwritten, the next CCSD can start on the CPU --
  * while the GPU is still computing; fpt_wait blocks for E(T).  One call may be in flight per handle. */

@@ -423,6 +423,25 @@ def test_single_precision_inputs_are_widened(engine):
     res = fb.RCCSDpT(fb.RCCSD(0.0, 0.0, -1.0, f32[0], f32[1]), moints, fb.B200())
     assert abs(res.correction - ref) < TOL
     assert abs(res.correction - oracle.pt_gemm(*_args(x))) < 1e-6 * abs(ref) * 100   # and close to the FP64 problem
+    assert res.stats["h2d_bytes"] == sum(a.size * 4 for a in f32)                    # the arrays crossed PCIe in 4-byte form
+    # the Float32 entry points directly, conventional and density-fitted, at a size that goes through the pinned ring
+    o, v, naux = 9, 70, 40
+    x = fb.synth.make_inputs(o, v, naux=naux, seed=5)
+    r = lambda a: np.asfortranarray(a.astype(np.float32))
+    w = lambda a: np.asfortranarray(a.astype(np.float64))
+    c32 = [r(a) for a in _args(x)]
+    e32, st = engine.triples_conv_f32(o, v, *c32)
+    assert abs(e32 - oracle.pt_gemm(*[w(a) for a in c32])) < TOL
+    assert st["h2d_bytes"] == sum(a.size * 4 for a in c32)
+    d32 = [r(a) for a in (x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)]
+    e32d, _ = engine.triples_df_f32(o, v, naux, *d32)
+    B = [w(a) for a in d32]
+    ref_df = oracle.pt_gemm(B[0], B[1], np.asfortranarray(np.einsum("Qia,Qbc->iabc", B[3], B[4], optimize=True)),
+                            np.asfortranarray(np.einsum("Qij,Qka->ijka", B[2], B[3], optimize=True)),
+                            np.asfortranarray(np.einsum("Qia,Qjb->iajb", B[3], B[3], optimize=True)), B[5], B[6])
+    assert abs(e32d - ref_df) < TOL
+    with pytest.raises(fb.FermiException):
+        engine.triples_conv_f32(0, v, *c32)
 
 
 @pytest.mark.parametrize("o,v", [(3, 127), (4, 126), (6, 124)])
