@@ -165,6 +165,18 @@ def workload_text(name, o, v, naux, route):
     return f"{name} (o={o}, v={v}, {integrals}, synthetic symmetric inputs, seed 20240517)"
 
 
+def config_dict(name, o, v, naux, route, world):
+    """The `config` object, identical in both arms (the driver compares them): what is computed, not how fast."""
+    import fermi_jl_b200 as fb
+    return {"workload": workload_text(name, o, v, naux, route),
+            "o": o, "v": v, "triplets": n_triplets(o), "work_items": fb.host.num_items(o, v), "route": route,
+            "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} GPU(s)",
+            "e2e_inputs": ("pageable host arrays; " + ("the symmetry-unique halves of OVVV, T2, OVOV cross PCIe; " if route == "conv" else
+                                                       "B factors and the a <= b half of T2 cross PCIe, the (ov|vv) slabs are assembled on the GPUs; ")
+                           + "sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)"),
+            "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 15) // 16 * 16) * 8 / 1e6)}
+
+
 def run_reference(args, name, o, v, naux, route):
     import fermi_jl_b200 as fb
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +195,7 @@ def run_reference(args, name, o, v, naux, route):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_text(name, o, v, naux, route), "o": o, "v": v, "route": route},
+            "config": config_dict(name, o, v, naux, route, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": s["threads"], "kind": "port", "blas": s["blas"], "other_blas": s["other"], "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU restatement of Fermi.jl ijk2.jl (oracle/pt_oracle.c: OpenMP over triplets, single-threaded dgemm per contraction "
@@ -390,11 +402,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": workload_text(name, o, v, naux, route),
-                           "o": o, "v": v, "triplets": ntrip, "work_items": n_items, "route": route,
-                           "parallelism": f"static contiguous, cost-weighted shards of the block-major (tile triple, triplet) work list over {world} GPU(s)",
-                           "e2e_inputs": "pageable host arrays (%.0f MB); the symmetry-unique halves of OVVV, T2, OVOV cross PCIe (%.0f MB); sharded H2D + ncclAllGather + scalar ncclAllReduce inside the library (no torch.distributed on the data path)" % (h2d_bytes / 1e6, moved / 1e6),
-                           "l2": "operands (P layout %.0f MB) exceed the 126 MB L2; no explicit flush" % (o * ((v + 3) // 4 * 4) ** 2 * ((v + o + 15) // 16 * 16) * 8 / 1e6)},
+                "config": config_dict(name, o, v, naux, route, world),
                 "triplets_per_s": ntrip / (step_ms * 1e-3), "E_T": e_gpu, "E_T_e2e": e_e2e,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(moved), "host_array_bytes": h2d_bytes, "d2h_bytes_per_step": 8,
                         "breakdown_ms": breakdown},
