@@ -30,17 +30,26 @@ extern "C" const char* fpt_last_error(void) { return err_text().c_str(); }
 extern "C" const char* fpt_version(void) { return "fermi_pt_b200 0.4 (sm_100a)"; }
 
 // ---- handle life cycle -----------------------------------------------------------------------------------------------------
+// every device buffer of one GPU of a handle
+static std::vector<DevBuf*> all_bufs(Dev* d)
+{
+    std::vector<DevBuf*> v = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
+                              &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sTri, &d->sTri2, &d->sBOO, &d->sBOV, &d->sBVV,
+                              &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab,
+                              &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
+                              &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
+    for (DevBuf& b : d->sPhase) v.push_back(&b);
+    for (DevBuf& b : d->f32in) v.push_back(&b);
+    for (DevBuf& b : d->f32wide) v.push_back(&b);
+    return v;
+}
+
 static void dev_destroy(Dev* d)
 {
     if (!d) return;
     cudaSetDevice(d->dev);
     if (d->comm) nccl_api().CommDestroy(d->comm);
-    DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab,
-                      &d->f32in[0], &d->f32in[1], &d->f32in[2], &d->f32in[3], &d->f32in[4], &d->f32in[5], &d->f32in[6],
-                      &d->f32wide[0], &d->f32wide[1], &d->f32wide[2], &d->f32wide[3], &d->f32wide[4], &d->f32wide[5], &d->f32wide[6], &d->sBOO, &d->sBOV, &d->sBVV,
-                      &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
-                      &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
+    const std::vector<DevBuf*> bufs = all_bufs(d);
     for (DevBuf* b : bufs) b->release();
     cudaEvent_t evs[] = {d->ev0[0], d->ev1[0], d->ev0[1], d->ev1[1], d->ev0[2], d->ev1[2], d->ev0[3], d->ev1[3], d->ev_copy, d->ev_start, d->ev_free[0], d->ev_free[1]};
     for (cudaEvent_t e : evs)
@@ -248,11 +257,7 @@ extern "C" int fpt_set_df_ring(fpt_handle* h, int block)
 extern "C" int fpt_device_bytes(fpt_handle* h, double* bytes)
 {
     if (!h || !bytes) return fail("fpt_device_bytes: NULL argument");
-    Dev* d = h->devs[0];
-    DevBuf* bufs[] = {&d->Pt, &d->Qt, &d->OV2, &d->T1d, &d->fo, &d->fv, &d->partials, &d->counter, &d->out, &d->prof, &d->blocktab,
-                      &d->sT1, &d->sT2, &d->sOOOV, &d->sOVOV, &d->sChunk[0], &d->sChunk[1], &d->sPhase[0], &d->sPhase[1], &d->sPhase[2], &d->sPhase[3], &d->sTri, &d->sTri2, &d->xTau, &d->xSlab, &d->xNew, &d->xOVOV, &d->ringtab, &d->sBOO, &d->sBOV, &d->sBVV,
-                      &d->sCo, &d->sCv, &d->aoDense, &d->sIdx, &d->sVals, &d->aoQ1, &d->aoQ2v, &d->aoQ2o, &d->aoQ3vv, &d->aoQ3vo,
-                      &d->aoQ3oo, &d->aoOVVV, &d->aoOOOV, &d->aoOVOV, &d->aoFlag};
+    const std::vector<DevBuf*> bufs = all_bufs(h->devs[0]);
     double n = 0.0;
     for (DevBuf* b : bufs) n += (double)b->cap;
     *bytes = n;
