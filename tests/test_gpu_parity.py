@@ -130,6 +130,22 @@ def test_single_process_multi_gpu_handle(built):
         dev = [torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda(0) for a in _args(x)]
         e3, _ = eng.triples_conv(o, v, *dev)
         assert abs(e3 - ref) < TOL, (o, v, e3, ref)
+        eng.set_df_ring(2)                       # slab ring on every GPU, each takes its shard of every block triple's launch
+        e4, _ = eng.triples_df(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
+        eng.set_df_ring(0)
+        assert abs(e4 - ref) < TOL, (o, v, e4, ref)
+        f32 = [np.asfortranarray(a.astype(np.float32)) for a in _args(x)]
+        e5, _ = eng.triples_conv_f32(o, v, *f32)  # widened on GPU 0, then the device-input route (broadcast to the peers)
+        assert abs(e5 - oracle.pt_gemm(*[np.asfortranarray(a.astype(np.float64)) for a in f32])) < TOL
+        # the 8(f) routines: the ladder splits the range of a over the GPUs, MP2 runs on the first one
+        from oracle import cc_numpy as C
+        new0 = np.asfortranarray(0.01 * np.random.default_rng(seed).standard_normal((o, o, v, v)))
+        want = C.ladder_df(new0.copy(order="F"), x.T1, x.T2, x.BVV)
+        got = new0.copy(order="F")
+        eng.ccsd_ladder_df(o, v, x.naux, x.T1, x.T2, x.BVV, got)
+        assert np.abs(got - want).max() < 1e-12 * max(1.0, float(np.abs(want - new0).max()))
+        e_mp2, _ = eng.mp2_df(o, v, x.naux, x.BOV, x.fo, x.fv)
+        assert abs(e_mp2 - C.mp2_df(x.BOV, x.fo, x.fv)) < 1e-12 * max(1.0, abs(e_mp2))
     eng.close()
 
 
@@ -153,7 +169,10 @@ def _rank_worker(rank, world, idfile, out):
         e2, _ = eng.triples_df(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)
         eng.upload_conv(o, v, *a)
         e3, _ = eng.compute(0, -1)
-        res.append((e, e2, e3))
+        eng.set_df_ring(2)
+        e4, _ = eng.triples_df(o, v, x.naux, x.T1, x.T2, x.BOO, x.BOV, x.BVV, x.fo, x.fv)   # slab ring, collective
+        eng.set_df_ring(0)
+        res.append((e, e2, e3, e4))
     eng.close()
     out.put((rank, res))
 
