@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfermi_pt_b200.so")
 SOURCES = ["fpt_api.cu"]
-HEADERS = ["fpt_triples.cuh", "fpt_triples2.cuh", "fpt_aux_kernels.cuh", "fpt_gemm.cuh", "fpt_internal.h", "fpt_stage.h", "fpt_ptx.cuh", "fpt_layout.h",
+HEADERS = ["fpt_api_handle.inl", "fpt_api_staging.inl", "fpt_api_upload.inl", "fpt_api_compute.inl", "fpt_api_ring.inl", "fpt_api_extras.inl", "fpt_api_ao.inl", "fpt_api_diag.inl",
+           "fpt_triples.cuh", "fpt_triples2.cuh", "fpt_aux_kernels.cuh", "fpt_gemm.cuh", "fpt_internal.h", "fpt_stage.h", "fpt_ptx.cuh", "fpt_layout.h",
            os.path.join("..", "..", "include", "fermi_pt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
