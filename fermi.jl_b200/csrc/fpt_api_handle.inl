@@ -40,6 +40,7 @@ static int dev_init(Dev* d)
     if (prop.major < 10)
         return fail("fpt_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", d->dev, prop.major, prop.minor);
     d->n_sm = prop.multiProcessorCount;
+    d->total_mem = prop.totalGlobalMem;
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
     static_assert(MAX_PHASES == 4, "dev_destroy lists the phase events and buffers one by one");

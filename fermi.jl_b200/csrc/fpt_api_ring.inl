@@ -118,8 +118,7 @@ static int df_ring_block(fpt_handle* h, int o, int v)
     if (h->dbg_flags || h->profiling || h->item_order != 1) return 0;
     if (h->df_ring > 0) return std::min(h->df_ring, o);
     if (h->df_ring < 0) return 0;
-    size_t free_b = 0, total_b = 0;
-    if (cudaSetDevice(h->devs[0]->dev) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const size_t total_b = h->devs[0]->total_mem;   // from the device properties: cudaMemGetInfo costs tens of milliseconds per call
     const double vp = padded_v(v), Kp = roundup(v + o, KGROUP);
     const double full = (double)o * vp * vp * Kp * sizeof(double);
     return (full > 0.4 * (double)total_b && o > 12) ? 4 : 0;

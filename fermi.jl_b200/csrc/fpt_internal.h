@@ -124,6 +124,7 @@ struct Dev {
     int idx = 0;          // position in fpt_handle::devs
     int grank = 0;        // rank in the NCCL communicator (= global shard number)
     int n_sm = 0;
+    size_t total_mem = 0;     // device memory (bytes)
     cudaStream_t stream = nullptr;   // kernels + collectives
     cudaStream_t copy = nullptr;     // host -> device DMAs
     cudaEvent_t ev0[MAX_PHASES] = {}, ev1[MAX_PHASES] = {};   // around the fused kernel of each phase of a call (one phase unless split)

@@ -17,12 +17,13 @@ for n in range(8):
     e, st = eng.triples_conv(o, v, *arr(xs[n % 3]))
     sync_ms.append((time.perf_counter() - t0) * 1e3)
     es.append(e)
-# asynchronous: the call returns when the inputs are consumed; 20 ms of CPU work (the next CCSD, here a numpy product) runs beside the GPU
-A = np.random.default_rng(0).standard_normal((700, 700))
+# asynchronous: the call returns when the inputs are consumed; 20 ms of CPU work (the next CCSD; here single-threaded numpy, so that no
+# BLAS thread pool keeps spinning on the cores the staging threads of the next call need) runs beside the GPU
+A = np.random.default_rng(0).standard_normal((200, 200))
 def cpu_work():
     t0 = time.perf_counter()
     while (time.perf_counter() - t0) < 0.020:
-        A @ A
+        np.sin(A)
 async_ms, ret_ms = [], []
 for n in range(8):
     t0 = time.perf_counter()
