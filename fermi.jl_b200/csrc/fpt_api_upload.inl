@@ -170,8 +170,7 @@ static int upload_t2(fpt_handle* h, const double* T2, const std::vector<const do
     std::vector<const double*> dT2;
     const bool half = use_half(h, T2, o, o, v, v, 1);
     if (half) {
-        View vw;
-        for (int b = 0; b < v; b++) vw.add((size_t)b * o2 * v * sizeof(double), 1, o2 * (b + 1) * sizeof(double), o2 * (b + 1) * sizeof(double));
+        const View vw = view_t2_half(o, v);
         std::vector<const double*> dTri;
         if (distribute(h, [](Dev& d) -> DevBuf& { return d.sTri; }, T2, vw.total / sizeof(double), dTri, &vw)) return 1;
         dT2.resize(h->devs.size());
@@ -206,9 +205,7 @@ static int upload_ovov(fpt_handle* h, const double* OVOV)
     std::vector<const double*> dOVOV;
     const bool half = use_half(h, OVOV, o, v, o, v, 2);
     if (half) {
-        View vw;   // for every (b, j): the prefix a <= b of the (i, a) plane
-        for (int b = 0; b < v; b++)
-            vw.add((size_t)b * o2 * v * sizeof(double), (size_t)o, (size_t)o * (b + 1) * sizeof(double), (size_t)o * v * sizeof(double));
+        const View vw = view_ovov_half(o, v);   // for every (b, j): the prefix a <= b of the (i, a) plane
         std::vector<const double*> dTri;
         if (distribute(h, [](Dev& d) -> DevBuf& { return d.sTri2; }, OVOV, vw.total / sizeof(double), dTri, &vw)) return 1;
         dOVOV.resize(h->devs.size());
@@ -270,9 +267,7 @@ static int upload_ovvv(fpt_handle* h, const double* OVVV, int p0, int np, int ph
         if (whole && !half) {
             if (distribute(h, buf, OVVV + (size_t)c0 * ov * v, elems, dChunk)) return 1;
         } else {
-            View vw;
-            for (int c = c0; c < c0 + cn; c++)
-                vw.add(((size_t)c * ov * v + p0) * sizeof(double), (size_t)v * (half ? c + 1 : v), (size_t)np * sizeof(double), (size_t)o * sizeof(double));
+            const View vw = view_ovvv_chunk(o, v, p0, np, c0, cn, half);
             if (distribute(h, buf, OVVV, elems, dChunk, &vw)) return 1;
         }
         for (int i = 0; i < L; i++) {

@@ -71,6 +71,31 @@ struct View {
     static View contiguous(size_t bytes) { View v; v.add(0, 1, bytes, bytes); return v; }
 };
 
+// The views the (T) uploads use (sizes in doubles; the packed layouts are what prep_pt_particle(_tri), expand_t2_tri and expand_ovov_tri
+// in fpt_aux_kernels.cuh read -- tests/test_stage_views.py checks both sides of that contract on the CPU):
+//   OVVV[i,a,b,c], c in [c0, c0+cn), occupied slice [p0, p0+np):  per c the rows (a, b) of np doubles, b < v -- or b <= c (half)
+inline View view_ovvv_chunk(size_t o, size_t v, size_t p0, size_t np, size_t c0, size_t cn, bool half)
+{
+    View vw;
+    for (size_t c = c0; c < c0 + cn; c++)
+        vw.add(((c * v * v * o) + p0) * sizeof(double), v * (half ? c + 1 : v), np * sizeof(double), o * sizeof(double));
+    return vw;
+}
+//   T2[i,j,a,b] = T2[j,i,b,a]: per b the prefix a <= b of the (i, j, a) block
+inline View view_t2_half(size_t o, size_t v)
+{
+    View vw;
+    for (size_t b = 0; b < v; b++) vw.add(b * o * o * v * sizeof(double), 1, o * o * (b + 1) * sizeof(double), o * o * (b + 1) * sizeof(double));
+    return vw;
+}
+//   OVOV[i,a,j,b] = OVOV[j,b,i,a]: per (b, j) the prefix a <= b of the (i, a) plane
+inline View view_ovov_half(size_t o, size_t v)
+{
+    View vw;
+    for (size_t b = 0; b < v; b++) vw.add(b * o * v * o * sizeof(double), o, o * (b + 1) * sizeof(double), o * v * sizeof(double));
+    return vw;
+}
+
 // copy bytes [off, off + nb) of the packed stream of `view` (over the array at `src`) to `dst` (a pinned slot, 32-byte aligned)
 __attribute__((target("avx2"))) inline void copy_seg_avx2(char* d, const char* s, size_t n)
 {
