@@ -28,7 +28,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["fpt_create", "fpt_destroy", "fpt_triples_conv", "fpt_triples_df", "fpt_upload_conv", "fpt_upload_df", "fpt_triples_ao", "fpt_upload_ao", "fpt_triples_ao_sparse", "fpt_upload_ao_sparse",
-           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_set_df_ring", "fpt_device_bytes", "fpt_set_deterministic", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_ccsd_ladder_df", "fpt_mp2_df", "fpt_mp2_conv", "fpt_triples_conv_f32", "fpt_triples_df_f32", "fpt_gemm_bench", "fpt_last_timeline",
+           "fpt_nccl_unique_id", "fpt_create_rank", "fpt_set_host_threads", "fpt_set_symmetric_inputs", "fpt_set_df_ring", "fpt_device_bytes", "fpt_set_deterministic", "fpt_set_adaptive_shards", "fpt_triples_conv_async", "fpt_triples_df_async", "fpt_wait", "fpt_ccsd_ladder_df", "fpt_mp2_df", "fpt_mp2_conv", "fpt_triples_conv_f32", "fpt_triples_df_f32", "fpt_gemm_bench", "fpt_last_timeline",
            "fpt_num_items", "fpt_compute", "fpt_set_triplet_window", "fpt_set_item_order", "fpt_shard_items", "fpt_fp64_peak", "fpt_set_profiling", "fpt_set_kernel_variant", "fpt_set_debug_flags", "fpt_last_profile", "fpt_dmma_sweep", "fpt_last_error", "fpt_version"]
 
 
@@ -75,6 +75,7 @@ def load_library():
     L.fpt_set_symmetric_inputs.argtypes = [vp, ctypes.c_int]
     L.fpt_set_df_ring.argtypes = [vp, ctypes.c_int]
     L.fpt_set_deterministic.argtypes = [vp, ctypes.c_int]
+    L.fpt_set_adaptive_shards.argtypes = [vp, ctypes.c_int]
     L.fpt_device_bytes.argtypes = [vp, _dp]
     L.fpt_triples_conv_async.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 7
     L.fpt_triples_df_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 7
@@ -169,6 +170,10 @@ class Engine:
 
     def set_host_threads(self, n: int):
         self._check(self._L.fpt_set_host_threads(self._h, n))
+
+    def set_adaptive_shards(self, on: bool):
+        """Multi-GPU handles: refine the shard boundaries from measured kernel times over repeated calls (default on)."""
+        self._check(self._L.fpt_set_adaptive_shards(self._h, int(bool(on))))
 
     def set_deterministic(self, on: bool):
         """Static item -> CTA deal: E(T) is bitwise reproducible from run to run (default: dynamic work counter)."""

@@ -14,9 +14,47 @@ static Problem current_problem(const fpt_handle* h, const Dev& d)
 
 // Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost (shard_items in fpt_layout.h,
 // shared with the CPU emulator so that the gloo tests exercise the very same split)
-static void shard_range(const fpt_handle* h, const Problem& P, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
+static void shard_range(const fpt_handle* h, const Problem& P, i64 b, i64 e, int rank, int world, i64* sb, i64* se, const double* frac = nullptr)
 {
-    shard_items(P, h->block_cost.data(), b, e, rank, world, sb, se);
+    shard_items(P, h->block_cost.data(), b, e, rank, world, sb, se, frac);
+}
+
+// Boundary fractions of phase `phase` for the split of [b, e) (see ShardCal): uniform until two calls with the same boundaries
+// have delivered every GPU's kernel time, then moved (damped) to where the measured time density puts equal times.
+static const double* shard_fractions(fpt_handle* h, const Problem& P, i64 b, i64 e, int phase)
+{
+    if (h->world < 2 || !h->adaptive || phase < 0 || phase >= MAX_PHASES || h->profiling || h->dbg_flags) return nullptr;
+    ShardCal& c = h->cal[phase];
+    const int W = h->world;
+    const bool same = c.o == P.o && c.v == P.v && c.world == W && c.order == P.order && c.tw_begin == P.tw_begin &&
+                      c.tw_count == P.tw_count && c.b == b && c.e == e && (int)c.frac.size() == W + 1;
+    if (!same) {
+        c = ShardCal{};
+        c.o = P.o; c.v = P.v; c.world = W; c.order = P.order; c.tw_begin = P.tw_begin; c.tw_count = P.tw_count; c.b = b; c.e = e;
+        c.frac.resize(W + 1);
+        for (int r = 0; r <= W; r++) c.frac[r] = (double)r / W;
+        c.gen = 1;
+    } else if (c.pending) {
+        // time density of the old segment r: ms[r] / (frac[r+1] - frac[r]); new boundary k where the cumulative time reaches k T / W
+        double T = 0.0;
+        for (int r = 0; r < W; r++) T += c.ms[r];
+        std::vector<double> nf(W + 1, 0.0);
+        nf[W] = 1.0;
+        int r = 0;
+        double acc = 0.0;   // time of the segments before r
+        for (int k = 1; k < W; k++) {
+            const double target = T * k / W;
+            while (r < W - 1 && acc + c.ms[r] < target) acc += c.ms[r++];
+            const double w = c.frac[r + 1] - c.frac[r];
+            const double u = c.ms[r] > 0.0 ? c.frac[r] + w * (target - acc) / c.ms[r] : c.frac[r];
+            nf[k] = c.frac[k] + 0.8 * (u - c.frac[k]);
+        }
+        bool ok = true;
+        for (int k = 0; k < W; k++) ok = ok && nf[k + 1] > nf[k];
+        if (ok) { c.frac = nf; c.gen++; }
+        c.pending = false;
+    }
+    return c.frac.data();
 }
 
 // launch the fused kernel + reduction for [item_begin, item_end) of the work list described by P on one GPU (asynchronous; the result
@@ -48,7 +86,13 @@ static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begi
     d.last_grid = grid;
     CK(cudaGetLastError());
     if (phase >= 0) CK(cudaEventRecord(d.ev1[phase], d.stream));
-    reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), accumulate);
+    {   // this GPU's kernel time of the previous call (if it was measured with the boundaries still in use) rides along, see ShardCal
+        const bool cal = phase >= 0 && h->world > 1 && h->adaptive && !ring.trips;
+        const int W = h->world;
+        const double prev = (cal && d.last_gen[phase] == h->cal[phase].gen) ? d.last_ms[phase] : 0.0;
+        reduce_partials<<<1, 32, 0, d.stream>>>(d.partials.d(), grid, d.out.d(), accumulate, cal ? MAX_PHASES * W : 0,
+                                                cal ? phase * W + d.grank : -1, prev);
+    }
     CK(cudaGetLastError());
     d.shard_b = item_begin;
     d.shard_e = item_end;
@@ -59,13 +103,15 @@ static int compute_launch(fpt_handle* h, Dev& d, const Problem& P, i64 item_begi
 // every GPU of the communicator takes its static, cost-weighted shard.
 static int compute_launch_all(fpt_handle* h, i64 tw_begin, i64 tw_count, i64 item_begin, i64 item_end, int phase)
 {
+    const double* frac = nullptr;
     for (Dev* dp : h->devs) {
         Problem P = current_problem(h, *dp);
         P.tw_begin = tw_begin;
         P.tw_count = tw_count;
         P.nitems = P.nb * tw_count;
+        if (dp == h->devs[0]) frac = shard_fractions(h, P, item_begin, item_end, phase);   // the same for every GPU of the handle
         i64 sb, se;
-        shard_range(h, P, item_begin, item_end, dp->grank, h->world, &sb, &se);
+        shard_range(h, P, item_begin, item_end, dp->grank, h->world, &sb, &se, frac);
         if (compute_launch(h, *dp, P, sb, se, phase)) return 1;
     }
     h->last_profiled = h->profiling;
@@ -77,12 +123,13 @@ static int compute_collect(fpt_handle* h, i64 n_items)
 {
     if (h->world > 1) {
         NCK(nccl_api().GroupStart());
-        for (Dev* dp : h->devs) NCK(nccl_api().AllReduce(dp->out.p, dp->out.p, 1, ncclDouble, ncclSum, dp->comm, dp->stream));
+        const size_t count = h->adaptive ? 1 + (size_t)MAX_PHASES * h->world : 1;   // E(T) + the time slots (ShardCal)
+        for (Dev* dp : h->devs) NCK(nccl_api().AllReduce(dp->out.p, dp->out.p, count, ncclDouble, ncclSum, dp->comm, dp->stream));
         NCK(nccl_api().GroupEnd());
     }
     Dev& d0 = *h->devs[0];
     CK(cudaSetDevice(d0.dev));
-    CK(cudaMemcpyAsync(h->res_pinned, d0.out.p, sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CK(cudaMemcpyAsync(h->res_pinned, d0.out.p, (h->world > 1 && h->adaptive ? OUT_DOUBLES : 1) * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
     CK(cudaEventRecord(d0.tl[5], d0.stream));
     h->pend_items = n_items;
     return 0;
@@ -109,10 +156,27 @@ static int compute_finish(fpt_handle* h, double* Et, fpt_stats* st)
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, dp->ev0[t], dp->ev1[t]));
             sum += ms;
+            dp->last_ms[t] = ms;                         // travels with the next call's all-reduce (ShardCal)
+            dp->last_gen[t] = h->cal[t].gen;
         }
         if (sum > ms_max) ms_max = sum;
     }
     if (Et) *Et = *h->res_pinned;
+    if (h->world > 1 && h->adaptive && !h->ring_call) {
+        // the reduced vector holds, per phase, every GPU's kernel time of the PREVIOUS call where that call used the boundaries
+        // still in use (else 0): once all are there, the next launch of the phase moves its boundaries
+        const int W = h->world;
+        for (int t = 0; t < h->nphase; t++) {
+            ShardCal& c = h->cal[t];
+            if ((int)c.frac.size() != W + 1 || c.pending) continue;
+            bool all = true;
+            for (int r = 0; r < W; r++) all = all && h->res_pinned[1 + t * W + r] > 0.0;
+            if (all) {
+                c.ms.assign(h->res_pinned + 1 + t * W, h->res_pinned + 1 + (t + 1) * W);
+                c.pending = true;
+            }
+        }
+    }
     // algorithmic flops of the triplets in the window, scaled by the share of the window's items that were computed
     const double ntrip = (double)h->tw_count;
     const int v = h->v, o = h->o;

@@ -8,7 +8,7 @@ extern "C" int fpt_fp64_peak(fpt_handle* h, int variant, double ms_target, doubl
     DeviceGuard guard;
     Dev& d = *h->devs[0];
     CK(cudaSetDevice(d.dev));
-    if (d.out.ensure(sizeof(double))) return 1;
+    if (d.out.ensure(OUT_DOUBLES * sizeof(double))) return 1;
     const int iters = 4096;
     const int grid = d.n_sm * 8;   // 8 CTAs x 8 warps per SM -> 16 warps per SMSP
     // flops per launch
@@ -165,7 +165,7 @@ extern "C" int fpt_dmma_sweep(fpt_handle* h, int ilp, int warps_per_sm, double* 
     DeviceGuard guard;
     Dev& d = *h->devs[0];
     CK(cudaSetDevice(d.dev));
-    if (d.out.ensure(sizeof(double))) return 1;
+    if (d.out.ensure(OUT_DOUBLES * sizeof(double))) return 1;
     const int iters = 20000 / ilp;
     const int threads = warps_per_sm * 32;
     if (threads < 32 || threads > 1024) return fail("fpt_dmma_sweep: warps_per_sm out of range");

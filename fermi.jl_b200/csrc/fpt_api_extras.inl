@@ -205,7 +205,7 @@ static int mp2_begin(fpt_handle* h, Dev& d, int o, int v)
     upload_begin(h);
     h->o = o; h->v = v;
     if (d.fo.ensure(o * sizeof(double)) || d.fv.ensure(v * sizeof(double)) || d.partials.ensure((size_t)d.n_sm * 4 * sizeof(double)) ||
-        d.out.ensure(sizeof(double)))
+        d.out.ensure(OUT_DOUBLES * sizeof(double)))
         return 1;
     CK(cudaEventRecord(d.ev_start, d.stream));
     CK(cudaStreamWaitEvent(d.copy, d.ev_start, 0));

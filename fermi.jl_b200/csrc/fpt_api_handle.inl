@@ -108,7 +108,7 @@ static int handle_finish(fpt_handle* h)
         if (n >= 64 && n <= 65536) h->pool.PIECE = (size_t)n << 10;
     }
     CK(h->pool.start(default_host_threads(h->rank_mode ? h->world : 1), (int)h->devs.size()));
-    CK(cudaHostAlloc((void**)&h->res_pinned, 64, cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&h->res_pinned, OUT_DOUBLES * sizeof(double), cudaHostAllocPortable));
     return 0;
 }
 
@@ -131,7 +131,7 @@ extern "C" int fpt_create(int ngpu, const int* devices, fpt_handle** out)
 {
     if (!out) return fail("fpt_create: out is NULL");
     *out = nullptr;
-    if (ngpu < 1 || ngpu > 16) return fail("fpt_create: ngpu=%d out of range", ngpu);
+    if (ngpu < 1 || ngpu > MAX_WORLD) return fail("fpt_create: ngpu=%d out of range", ngpu);
     if (ngpu > 1 && !devices) return fail("fpt_create: a device list is required for ngpu > 1");
     DeviceGuard guard;
     fpt_handle* h = new fpt_handle();
@@ -176,7 +176,7 @@ extern "C" int fpt_create_rank(int device, int rank, int world, const void* id12
 {
     if (!out) return fail("fpt_create_rank: out is NULL");
     *out = nullptr;
-    if (world < 1 || rank < 0 || rank >= world) return fail("fpt_create_rank: invalid rank %d of %d", rank, world);
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail("fpt_create_rank: invalid rank %d of %d (at most %d GPUs)", rank, world, MAX_WORLD);
     if (world > 1 && !id128) return fail("fpt_create_rank: the NCCL id is required for world > 1");
     DeviceGuard guard;
     fpt_handle* h = new fpt_handle();
@@ -208,6 +208,14 @@ extern "C" int fpt_set_symmetric_inputs(fpt_handle* h, int on)
 {
     if (!h) return fail("fpt_set_symmetric_inputs: NULL handle");
     h->sym_inputs = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int fpt_set_adaptive_shards(fpt_handle* h, int on)
+{
+    if (!h) return fail("fpt_set_adaptive_shards: NULL handle");
+    h->adaptive = on ? 1 : 0;
+    for (ShardCal& c : h->cal) c = ShardCal{};
     return 0;
 }
 

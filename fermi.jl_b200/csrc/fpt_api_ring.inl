@@ -107,6 +107,7 @@ static int triples_df_ring(fpt_handle* h, int o, int v, int naux, const double* 
     }
     h->launches += 2 * (int)phases.size() - 2;   // compute_finish counts one kernel + one reduction per GPU itself
     h->nphase = 1;
+    h->ring_call = true;
     h->last_profiled = false;
     return 0;
 }

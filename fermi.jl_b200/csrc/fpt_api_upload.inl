@@ -56,7 +56,7 @@ static int setup_problem(fpt_handle* h, int o, int v, int pt_slabs = 0)   // pt_
         if (d.fv.ensure((size_t)v * sizeof(double))) return 1;
         if (d.partials.ensure((size_t)d.n_sm * 4 * sizeof(double))) return 1;
         if (d.counter.ensure(sizeof(unsigned long long))) return 1;
-        if (d.out.ensure(sizeof(double))) return 1;
+        if (d.out.ensure(OUT_DOUBLES * sizeof(double))) return 1;
         if (d.prof.ensure((size_t)d.n_sm * NPROF * sizeof(long long))) return 1;
         if (d.blocktab.ensure(h->tab.size() * sizeof(BlockTabEntry))) return 1;
         if (d.tab_vp != P.vp) {
@@ -86,6 +86,7 @@ static int pt_zero_padding(Dev& d)
 static void upload_begin(fpt_handle* h)
 {
     h->loaded = false;
+    h->ring_call = false;
     h->launches = 0;
     h->h2d = 0.0;
     h->stage_host_ms = 0.0;

@@ -11,12 +11,18 @@
 
 namespace fpt {
 
-__global__ void reduce_partials(const double* partials, int n, double* out, int accumulate)
+// out[0] = (accumulate ? out[0] : 0) + sum of the partials.  out[1 .. nslots] carry one number per (phase, GPU) through the scalar
+// all-reduce of a multi-GPU handle -- this GPU's kernel time of the previous call, for the adaptive shard balance: a store
+// launch (accumulate = 0) clears them, every launch writes its own slot (slot < 0: none).
+__global__ void reduce_partials(const double* partials, int n, double* out, int accumulate, int nslots = 0, int slot = -1, double value = 0.0)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = accumulate ? out[0] : 0.0;
         for (int t = 0; t < n; t++) s += partials[t];
         out[0] = s;
+        if (!accumulate)
+            for (int t = 0; t < nslots; t++) out[1 + t] = 0.0;
+        if (slot >= 0) out[1 + slot] = value;
     }
 }
 

@@ -118,6 +118,8 @@ inline int nccl_load()
 
 // ---- one GPU of a handle -----------------------------------------------------------------------------------------------
 constexpr int MAX_PHASES = 4;   // kernels of one split call (triples_conv in fpt_api.cu)
+constexpr int MAX_WORLD = 16;    // GPUs of one communicator (fpt_create refuses more)
+constexpr int OUT_DOUBLES = 1 + MAX_PHASES * MAX_WORLD;   // E(T) + one time slot per (phase, GPU), see ShardCal
 constexpr int NTL = 6;   // timeline events: upload begin, last H2D done, operands ready, kernel begin, kernel end, result ready
 struct Dev {
     int dev = 0;
@@ -151,17 +153,37 @@ struct Dev {
     int clean_o = -1, clean_v = -1, clean_slabs = 0;
     void* clean_ptr = nullptr;
     int last_grid = 0;
+    double last_ms[MAX_PHASES] = {};     // kernel time of this GPU's shard in the last call, per phase ...
+    int last_gen[MAX_PHASES] = {};       // ... and the generation of boundary fractions it was measured with (0: none)
     i64 shard_b = 0, shard_e = 0;
 };
 
 }  // namespace fpt
+
+// Adaptive balance of the static shards of a multi-GPU handle.  The split is by *estimated* cost (block_cost); at C4 on 8 GPUs the
+// shards' kernel times differ by +-2 %.  Repeated calls of one shape (the 6 N_atoms calls of a finite-difference gradient) correct it:
+// every GPU's kernel time of call n travels with the scalar all-reduce of call n+1 (one slot per phase and GPU in the reduced
+// vector), so after two calls with the same boundaries every process holds all times measured with them and moves the boundaries to
+// where the measured time density says equal times lie (damped).  All processes see the same vector and run the same arithmetic,
+// so the new boundaries agree everywhere without further communication.
+struct ShardCal {
+    int o = -1, v = -1, world = 0, order = -1;
+    fpt::i64 tw_begin = -1, tw_count = -1, b = -1, e = -1;      // what was split
+    int gen = 0;                                                // generation of `frac` (0: uniform, nothing measured)
+    std::vector<double> frac;                                   // world + 1 boundary fractions in use
+    bool pending = false;                                       // all times of this generation are known: move the boundaries at the next launch
+    std::vector<double> ms;                                     // the times (per GPU)
+};
 
 struct fpt_handle {
     std::vector<fpt::Dev*> devs;   // the GPUs this process drives
     int world = 1;                 // GPUs in the communicator (== devs.size() unless created with fpt_create_rank)
     bool rank_mode = false;        // one process per GPU: uploads and computes are collective calls over `world` processes
     fpt::StagePool pool;           // host threads + pinned bounce slots for pageable inputs
-    double* res_pinned = nullptr;  // the 8-byte result lands here
+    double* res_pinned = nullptr;  // E(T) (and the time slots of the adaptive balance) land here: OUT_DOUBLES doubles
+    ShardCal cal[fpt::MAX_PHASES];
+    int adaptive = 1;              // fpt_set_adaptive_shards
+    bool ring_call = false;        // the evaluation in flight / last finished used the DF slab ring (no time slots)
     // problem (identical on every GPU)
     int o = 0, v = 0;
     std::vector<fpt::BlockTabEntry> tab;

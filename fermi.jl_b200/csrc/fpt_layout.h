@@ -460,7 +460,9 @@ FPT_HD void item_decode_cf(const Problem& P, i64 item, ItemDesc& it, i64& block,
 // Static split of the item range [b, e) into `world` contiguous parts of equal estimated cost; part `rank` is [*sb, *se).
 // In block-major order an item's cost depends on its block (diagonal and edge blocks are cheaper), so boundaries are placed on
 // the prefix sum of block_cost (one entry per block); in triplet-major order every stretch of nb items costs the same.
-inline void shard_items(const Problem& P, const double* cost, i64 b, i64 e, int rank, int world, i64* sb, i64* se)
+// `frac` (optional, world + 1 values rising from 0 to 1): boundary r sits at that fraction of the range's estimated cost instead of
+// r / world -- how the adaptive balance of a multi-GPU handle shifts the shards (fpt_api_compute.inl).
+inline void shard_items(const Problem& P, const double* cost, i64 b, i64 e, int rank, int world, i64* sb, i64* se, const double* frac = nullptr)
 {
     if (P.order != 1 || P.tw_count <= 0) {
         *sb = b + (e - b) * rank / world;
@@ -479,7 +481,7 @@ inline void shard_items(const Problem& P, const double* cost, i64 b, i64 e, int 
     auto boundary = [&](int r) -> i64 {
         if (r <= 0) return b;
         if (r >= world) return e;
-        const double target = c0 + (c1 - c0) * r / world;
+        const double target = c0 + (c1 - c0) * (frac ? frac[r] : (double)r / world);
         double c = 0.0;
         for (i64 blk = 0; blk < P.nb; blk++) {
             const double cb = cost[blk] * (double)P.tw_count;
