@@ -33,25 +33,10 @@ static const double* shard_fractions(fpt_handle* h, const Problem& P, i64 b, i64
         c.o = P.o; c.v = P.v; c.world = W; c.order = P.order; c.tw_begin = P.tw_begin; c.tw_count = P.tw_count; c.b = b; c.e = e;
         c.frac.resize(W + 1);
         for (int r = 0; r <= W; r++) c.frac[r] = (double)r / W;
-        c.gen = 1;
+        c.gen = ++h->gen_counter;   // unique per handle: a time measured with other boundaries (or another problem) never matches
     } else if (c.pending) {
-        // time density of the old segment r: ms[r] / (frac[r+1] - frac[r]); new boundary k where the cumulative time reaches k T / W
-        double T = 0.0;
-        for (int r = 0; r < W; r++) T += c.ms[r];
         std::vector<double> nf(W + 1, 0.0);
-        nf[W] = 1.0;
-        int r = 0;
-        double acc = 0.0;   // time of the segments before r
-        for (int k = 1; k < W; k++) {
-            const double target = T * k / W;
-            while (r < W - 1 && acc + c.ms[r] < target) acc += c.ms[r++];
-            const double w = c.frac[r + 1] - c.frac[r];
-            const double u = c.ms[r] > 0.0 ? c.frac[r] + w * (target - acc) / c.ms[r] : c.frac[r];
-            nf[k] = c.frac[k] + 0.8 * (u - c.frac[k]);
-        }
-        bool ok = true;
-        for (int k = 0; k < W; k++) ok = ok && nf[k + 1] > nf[k];
-        if (ok) { c.frac = nf; c.gen++; }
+        if (rebalance_fractions(W, c.frac.data(), c.ms.data(), 0.8, nf.data())) { c.frac = nf; c.gen = ++h->gen_counter; }
         c.pending = false;
     }
     return c.frac.data();

@@ -182,7 +182,8 @@ struct fpt_handle {
     fpt::StagePool pool;           // host threads + pinned bounce slots for pageable inputs
     double* res_pinned = nullptr;  // E(T) (and the time slots of the adaptive balance) land here: OUT_DOUBLES doubles
     ShardCal cal[fpt::MAX_PHASES];
-    int adaptive = 1;              // fpt_set_adaptive_shards
+    int adaptive = 1;              // fpt_set_adaptive_shards (must be the same on every rank of a communicator: it sizes the all-reduce)
+    int gen_counter = 0;           // source of ShardCal::gen
     bool ring_call = false;        // the evaluation in flight / last finished used the DF slab ring (no time slots)
     // problem (identical on every GPU)
     int o = 0, v = 0;

@@ -497,6 +497,29 @@ inline void shard_items(const Problem& P, const double* cost, i64 b, i64 e, int 
     *se = boundary(rank + 1);
 }
 
+// Adaptive balance: `frac` (W + 1 boundary fractions, 0 = frac[0] < ... < frac[W] = 1) gave the shards the measured times ms[0..W).
+// With the time density of old segment r taken as ms[r] / (frac[r+1] - frac[r]), boundary k belongs where the cumulative time reaches
+// k T / W; the move towards it is damped.  Returns false (and leaves `out` unspecified) if the result would not be strictly rising.
+inline bool rebalance_fractions(int W, const double* frac, const double* ms, double damping, double* out)
+{
+    double T = 0.0;
+    for (int r = 0; r < W; r++) T += ms[r];
+    out[0] = 0.0;
+    out[W] = 1.0;
+    int r = 0;
+    double acc = 0.0;   // time of the segments before r
+    for (int k = 1; k < W; k++) {
+        const double target = T * k / W;
+        while (r < W - 1 && acc + ms[r] < target) acc += ms[r++];
+        const double w = frac[r + 1] - frac[r];
+        const double u = ms[r] > 0.0 ? frac[r] + w * (target - acc) / ms[r] : frac[r];
+        out[k] = frac[k] + damping * (u - frac[k]);
+    }
+    for (int k = 0; k < W; k++)
+        if (!(out[k + 1] > out[k])) return false;
+    return true;
+}
+
 // ---- energy of one (a,b,c) point, ijk.jl:127-133 ---------------------------------------------------------
 // w[m], vv[m] in perm order m: (abc),(acb),(bac),(bca),(cab),(cba)
 FPT_HD double point_energy(const double* w, const double* vv, double Dd, int a, int b, int c, double wijk)

@@ -94,7 +94,7 @@ int fpt_triples_df(fpt_handle* h, int o, int v, int naux, const double* T1, cons
 /* Handles over several GPUs split the work list into shards of equal ESTIMATED cost.  With on = 1 (default) repeated calls of one
  * shape refine the split from the shards' measured kernel times, which travel with the scalar all-reduce of the next call: after every
  * second call the boundaries move to where equal times lie (measured at C4 on 8 GPUs: shard times within +-2 % before, see DESIGN.md
- * for after).  0: always the model's split. */
+ * for after).  0: always the model's split.  Rank handles: set it identically on every rank (it sizes the all-reduce). */
 int fpt_set_adaptive_shards(fpt_handle* h, int on);
 
 /* E(T) is a sum of per-CTA partial sums added in a fixed order; by default the CTAs pull work items off a global counter, so which

@@ -236,3 +236,9 @@ extern "C" int fpt_emul_shard(int o, int v, int order, int rank, int world, long
     return 0;
 }
 
+
+// The adaptive balance's boundary update (rebalance_fractions in fpt_layout.h), for the CPU tests.
+extern "C" int fpt_emul_rebalance(int W, const double* frac, const double* ms, double damping, double* out)
+{
+    return rebalance_fractions(W, frac, ms, damping, out) ? 0 : 1;
+}
