@@ -15,8 +15,11 @@ A second case pins it on a value the reference's own test suite asserts: water /
 A third case is BASELINE config C2 itself: water / cc-pVTZ (o = 5, v = 53; d and f shells), for which test/test_pT.jl:5,31 holds
 Psi4's CCSD(T) and CCSD totals, i.e. E(T) = -0.008051775570 -> tests/golden/water_ccpvtz.npz (integrals: oracle/mini_ints.py, numba).
 
+A fourth case takes another molecule of the reference's test table: glycine / STO-3G (o = 20, v = 10; geometry test/xyz/glycine.xyz), for which
+test/test_pT.jl:10,36 holds CCSD(T) and CCSD totals, E(T) = -0.007503098657 -> tests/golden/glycine_sto3g.npz.
+
 Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
-    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz] [numba]
+    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g] [numba]
 """
 from __future__ import annotations
 
@@ -34,7 +37,15 @@ BOHR_TO_ANGSTROM = 0.529177210903  # src/Backend/PhysicalConstants.jl:38
 GEOM = [("O", (1.2091536548, 1.7664118189, -0.0171613972)),
         ("H", (2.1984800075, 1.7977100627, 0.0121161719)),
         ("H", (0.9197881882, 2.4580185570, 0.6297938830))]
-Z = {"H": 1, "O": 8}
+Z = {"H": 1, "C": 6, "N": 7, "O": 8}
+# other molecules of the reference's test suite: geometries as in /root/reference/test/xyz/<name>.xyz (Angstrom)
+MOLECULES = {
+    "water": GEOM,
+    "glycine": [("C", (0.0000000, 0.5506150, 0.0000000)), ("O", (1.1776070, 0.8118730, 0.0000000)), ("O", (-0.9694240, 1.4927290, 0.0000000)),
+                ("C", (-0.5847620, -0.8563810, 0.0000000)), ("N", (0.4006580, -1.9277700, 0.0000000)), ("H", (-0.5071000, 2.3458330, 0.0000000)),
+                ("H", (-1.2456590, -0.9456040, 0.8813150)), ("H", (-1.2456590, -0.9456040, -0.8813150)),
+                ("H", (1.0184570, -1.7812290, 0.8032340)), ("H", (1.0184570, -1.7812290, -0.8032340))],
+}
 
 # STO-3G (Basis Set Exchange), shells as (l, exponents, coefficients)
 STO3G = {
@@ -42,6 +53,12 @@ STO3G = {
     "O": [(0, [0.1307093214e+03, 0.2380886605e+02, 0.6443608313e+01], [0.1543289673e+00, 0.5353281423e+00, 0.4446345422e+00]),
           (0, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [-0.9996722919e-01, 0.3995128261e+00, 0.7001154689e+00]),
           (1, [0.5033151319e+01, 0.1169596125e+01, 0.3803889600e+00], [0.1559162750e+00, 0.6076837186e+00, 0.3919573931e+00])],
+    "C": [(0, [0.7161683735e+02, 0.1304509632e+02, 0.3530512160e+01], [0.1543289673e+00, 0.5353281423e+00, 0.4446345422e+00]),
+          (0, [0.2941249355e+01, 0.6834830964e+00, 0.2222899159e+00], [-0.9996722919e-01, 0.3995128261e+00, 0.7001154689e+00]),
+          (1, [0.2941249355e+01, 0.6834830964e+00, 0.2222899159e+00], [0.1559162750e+00, 0.6076837186e+00, 0.3919573931e+00])],
+    "N": [(0, [0.9910616896e+02, 0.1805231239e+02, 0.4885660238e+01], [0.1543289673e+00, 0.5353281423e+00, 0.4446345422e+00]),
+          (0, [0.3780455879e+01, 0.8784966449e+00, 0.2857143744e+00], [-0.9996722919e-01, 0.3995128261e+00, 0.7001154689e+00]),
+          (1, [0.3780455879e+01, 0.8784966449e+00, 0.2857143744e+00], [0.1559162750e+00, 0.6076837186e+00, 0.3919573931e+00])],
 }
 
 
@@ -80,7 +97,9 @@ REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd"
                         "e_ccsd_t": -75.0187834019},
              "6-31g": {"e_ccsd_t": -76.121147867765558},
              # Psi4 totals the reference's test suite holds for water / cc-pVTZ / df false (test/test_pT.jl:5 Econv[1], :31 CCSDconv[1])
-             "cc-pvtz": {"e_ccsd": -76.335767822597347, "e_ccsd_t": -76.343819598166903, "e_t": -76.343819598166903 + 76.335767822597347}}
+             "cc-pvtz": {"e_ccsd": -76.335767822597347, "e_ccsd_t": -76.343819598166903, "e_t": -76.343819598166903 + 76.335767822597347},
+             # glycine / STO-3G / df false: test/test_pT.jl:10 Econv[6], :36 CCSDconv[6] (o = 20, v = 10)
+             "glycine/sto-3g": {"e_ccsd": -279.415437830677774, "e_ccsd_t": -279.422940929335255, "e_t": -279.422940929335255 + 279.415437830677774}}
 
 
 def dfact(n):
@@ -389,14 +408,20 @@ def integrals_numba(basis):
 
 
 def main(basis="sto-3g", engine="auto"):
+    global GEOM
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
+    molecule, case = "water", basis
+    if "/" in basis:                      # "glycine/sto-3g"
+        molecule, basis = basis.split("/")
+        engine = "numba" if engine == "auto" else engine
+    GEOM = MOLECULES[molecule]
     if engine == "numba" or (engine == "auto" and basis == "cc-pvtz"):
         S, T, V, ERI, enuc = integrals_numba(basis)
     else:
         bfs, atoms = build_basis(basis)
         S, T, V, ERI, enuc = integrals(bfs, atoms)
-    ndocc = 5
+    ndocc = sum(Z[sym] for sym, _ in GEOM) // 2
     e_el, eps, C = rhf(S, T + V, ERI, ndocc)
     e_rhf = e_el + enuc
     MO = np.einsum("pqrs,pi,qj,rk,sl->ijkl", ERI, C, C, C, C, optimize=True)
@@ -414,16 +439,16 @@ def main(basis="sto-3g", engine="auto"):
     fo, fv = eps[:o].copy(), eps[o:].copy()
     from oracle import pt_numpy as P
     e_t = P.pt_ijk(T1, T2, OVVV, OOOV, OVOV, fo, fv)
-    ref = REFERENCE[basis]
+    ref = REFERENCE[case]
     note = lambda k: f"   (reference {ref[k]:.10f})" if k in ref else ""
-    print(f"water / {basis}: o={o} v={v}")
+    print(f"{molecule} / {basis}: o={o} v={v}")
     print(f"E_nuc   {enuc:.10f}" + note("e_nuc"))
     print(f"E_RHF   {e_rhf:.10f}")
     print(f"E_corr  {e_cc:.10f}" + note("e_corr"))
     print(f"E_CCSD  {e_rhf + e_cc:.10f}" + note("e_ccsd"))
     print(f"E(T)    {e_t:.10f}" + note("e_t") + f"   spin-orbital formula: {e_t_so:.10f}")
     print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}" + note("e_ccsd_t"))
-    out = os.path.join(root, "tests", "golden", "water_" + basis.replace("-", "") + ".npz")
+    out = os.path.join(root, "tests", "golden", molecule + "_" + basis.replace("-", "") + ".npz")
     extra = {}
     if basis == "cc-pvtz":   # 5 x 53^3 doubles: keep only b >= c of (ia|bc) = (ia|cb) (tests/test_oracle_kat.py unpacks it)
         iu = np.triu_indices(v)
@@ -432,7 +457,7 @@ def main(basis="sto-3g", engine="auto"):
         np.savez_compressed(out, T1=T1, T2=T2, OVVV_packed=packed, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t)
         print("wrote", out)
         return
-    if basis == "sto-3g":   # small enough to keep: lets the AO -> MO route (fpt_triples_ao) be checked on a real molecule
+    if basis == "sto-3g" and molecule == "water":   # small enough to keep: lets the AO -> MO route (fpt_triples_ao) be checked on a real molecule
         extra = {"AOERI": np.asfortranarray(ERI), "C": np.asfortranarray(C)}
     np.savez(out, T1=T1, T2=T2, OVVV=OVVV, OOOV=OOOV, OVOV=OVOV, fo=fo, fv=fv, e_nuc=enuc, e_rhf=e_rhf, e_corr=e_cc, e_t=e_t,
              e_t_spinorbital=e_t_so, **extra)

@@ -146,3 +146,38 @@ def test_gpu_matches_reference_test_value_ccpvtz(engine):
     assert abs(res.correction - REF3_ET) < 1e-9
     assert abs(res.energy - REF3_ECCSDT) < 1e-9
     assert abs(res.correction - float(G3["e_t"])) < 1e-12
+
+
+# ---- glycine / STO-3G: a second molecule of the reference's Psi4 table, with twenty occupied orbitals (test/test_pT.jl:10,36) ----------
+# `python oracle/mini_ccsd.py glycine/sto-3g` (geometry test/xyz/glycine.xyz, all-electron, o = 20, v = 10) reproduces Psi4's CCSD total to
+# 6e-8 Eh (2e-10 relative; the reference's own tolerance is 1e-8 relative) and its E(T) = CCSD(T) - CCSD = -0.007503098657 to 1.6e-10 Eh.
+G4 = np.load(os.path.join(os.path.dirname(__file__), "golden", "glycine_sto3g.npz"))
+REF4_ECCSDT = -279.422940929335255   # test/test_pT.jl:10  Econv[6]
+REF4_ECCSD = -279.415437830677774    # test/test_pT.jl:36  CCSDconv[6]
+REF4_ET = REF4_ECCSDT - REF4_ECCSD
+
+
+def _args4():
+    return tuple(np.asfortranarray(G4[k]) for k in ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv"))
+
+
+@pytest.mark.parametrize("impl", ["naive", "gemm", "numpy_ijk2"])
+def test_oracle_matches_reference_test_value_glycine(impl):
+    f = {"naive": oracle.pt_naive, "gemm": oracle.pt_gemm, "numpy_ijk2": P.pt_ijk2}[impl]
+    assert G4["T1"].shape == (20, 10) and G4["T2"].shape == (20, 20, 10, 10)
+    e = f(*_args4())
+    assert abs(e - REF4_ET) < 1e-9, (e, REF4_ET)                                   # measured: 1.6e-10
+    assert abs(float(G4["e_rhf"]) + float(G4["e_corr"]) - REF4_ECCSD) < 1e-8 * abs(REF4_ECCSD)
+    assert abs(e - float(G4["e_t"])) < 1e-14
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_test_value_glycine(engine):
+    import fermi_jl_b200 as fb
+    a = _args4()
+    ccsd = fb.RCCSD(0.0, float(G4["e_corr"]), float(G4["e_rhf"]) + float(G4["e_corr"]), a[0], a[1])
+    moints = fb.IntegralHelper({"OVVV": a[2], "OOOV": a[3], "OVOV": a[4], "Fii": a[5], "Faa": a[6]})
+    res = fb.RCCSDpT(ccsd, moints, fb.B200())          # o = 20: a split call (two occupied phases)
+    assert abs(res.correction - REF4_ET) < 1e-9
+    assert abs(res.correction - float(G4["e_t"])) < 1e-13
+    assert abs(res.energy - REF4_ECCSDT) < 1e-8 * abs(REF4_ECCSDT)
