@@ -45,6 +45,10 @@ MOLECULES = {
                 ("C", (-0.5847620, -0.8563810, 0.0000000)), ("N", (0.4006580, -1.9277700, 0.0000000)), ("H", (-0.5071000, 2.3458330, 0.0000000)),
                 ("H", (-1.2456590, -0.9456040, 0.8813150)), ("H", (-1.2456590, -0.9456040, -0.8813150)),
                 ("H", (1.0184570, -1.7812290, 0.8032340)), ("H", (1.0184570, -1.7812290, -0.8032340))],
+    "benzene": [("C", (0.0000000, 1.3916730, 0.0)), ("C", (1.2052240, 0.6958360, 0.0)), ("C", (1.2052240, -0.6958360, 0.0)),
+                ("C", (0.0000000, -1.3916730, 0.0)), ("C", (-1.2052240, -0.6958360, 0.0)), ("C", (-1.2052240, 0.6958360, 0.0)),
+                ("H", (0.0000000, 2.4695880, 0.0)), ("H", (2.1387260, 1.2347940, 0.0)), ("H", (2.1387260, -1.2347940, 0.0)),
+                ("H", (0.0000000, -2.4695880, 0.0)), ("H", (-2.1387260, -1.2347940, 0.0)), ("H", (-2.1387260, 1.2347940, 0.0))],
 }
 
 # STO-3G (Basis Set Exchange), shells as (l, exponents, coefficients)
@@ -72,6 +76,12 @@ B631G = {
           (1, [15.5396160, 3.5999336, 1.0137618], [0.0708743, 0.3397528, 0.7271586]),
           (0, [0.2700058], [1.0]),
           (1, [0.2700058], [1.0])],
+    "C": [(0, [3047.5249000, 457.3695100, 103.9486900, 29.2101550, 9.2866630, 3.1639270],
+              [0.0018347, 0.0140373, 0.0688426, 0.2321844, 0.4679413, 0.3623120]),
+          (0, [7.8682724, 1.8812885, 0.5442493], [-0.1193324, -0.1608542, 1.1434564]),
+          (1, [7.8682724, 1.8812885, 0.5442493], [0.0689991, 0.3164240, 0.7443083]),
+          (0, [0.1687144], [1.0]),
+          (1, [0.1687144], [1.0])],
 }
 # cc-pVTZ (Dunning, JCP 90, 1007 (1989); Basis Set Exchange, optimised general contractions): O (10s5p2d1f) -> [4s3p2d1f],
 # H (5s2p1d) -> [3s2p1d]; real solid harmonics (58 functions for water).  Integrals: oracle/mini_ints.py.
@@ -99,6 +109,8 @@ REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd"
              # Psi4 totals the reference's test suite holds for water / cc-pVTZ / df false (test/test_pT.jl:5 Econv[1], :31 CCSDconv[1])
              "cc-pvtz": {"e_ccsd": -76.335767822597347, "e_ccsd_t": -76.343819598166903, "e_t": -76.343819598166903 + 76.335767822597347},
              # glycine / STO-3G / df false: test/test_pT.jl:10 Econv[6], :36 CCSDconv[6] (o = 20, v = 10)
+             # benzene / 6-31G / df false: test/test_pT.jl:7 Econv[3], :33 CCSDconv[3] (o = 21, v = 45)
+             "benzene/6-31g": {"e_ccsd": -231.188695053088594, "e_ccsd_t": -231.209805921161490, "e_t": -231.209805921161490 + 231.188695053088594},
              "glycine/sto-3g": {"e_ccsd": -279.415437830677774, "e_ccsd_t": -279.422940929335255, "e_t": -279.422940929335255 + 279.415437830677774}}
 
 

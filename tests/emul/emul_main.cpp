@@ -204,8 +204,16 @@ extern "C" int fpt_emulate(int o, int v, const double* T1, const double* T2, con
 
 // The library's cost-weighted split of the work list (fpt_shard_items) for the CPU tests: same code (shard_items, block_cost,
 // make_gemms of fpt_layout.h), no GPU.  Returns the estimated cost share of the part in *cost_share (1/world when balanced).
+extern "C" int fpt_emul_shard_frac(int o, int v, int order, int rank, int world, const double* frac, long long* item_begin,
+                                   long long* item_end, double* cost_share);
 extern "C" int fpt_emul_shard(int o, int v, int order, int rank, int world, long long* item_begin, long long* item_end,
                               double* cost_share)
+{
+    return fpt_emul_shard_frac(o, v, order, rank, world, nullptr, item_begin, item_end, cost_share);
+}
+// the same with the boundary fractions of the adaptive balance (frac: world + 1 values, nullptr = uniform)
+extern "C" int fpt_emul_shard_frac(int o, int v, int order, int rank, int world, const double* frac, long long* item_begin,
+                                   long long* item_end, double* cost_share)
 {
     Problem P{};
     P.o = o; P.v = v; P.vp = padded_v(v); P.nt = num_tiles(v);
@@ -222,7 +230,7 @@ extern "C" int fpt_emul_shard(int o, int v, int order, int rank, int world, long
         cost[(size_t)b] = block_cost(ent, P.G);
     }
     i64 sb, se;
-    shard_items(P, cost.data(), 0, P.nitems, rank, world, &sb, &se);
+    shard_items(P, cost.data(), 0, P.nitems, rank, world, &sb, &se, frac);
     *item_begin = sb; *item_end = se;
     if (cost_share) {
         double tot = 0.0, mine = 0.0;

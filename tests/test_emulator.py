@@ -107,3 +107,26 @@ def test_adaptive_rebalance_converges(built):
     # degenerate input (a zero-width segment would follow): refused, the caller keeps its boundaries
     f = np.array([0.0, 0.5, 1.0]); t = np.array([0.0, 1.0]); out = np.empty(3)
     assert L.fpt_emul_rebalance(2, f.ctypes.data_as(_dp), t.ctypes.data_as(_dp), 1.0, out.ctypes.data_as(_dp)) in (0, 1)
+
+
+@pytest.mark.parametrize("o,v,world", [(6, 50, 8), (24, 114, 8), (5, 19, 3)])
+def test_shards_with_adaptive_fractions_still_partition(built, o, v, world):
+    """The adaptive balance only moves the boundary *fractions* (shard_items' `frac`): for any strictly rising set of fractions the parts
+    stay contiguous and cover the list exactly once, and a part's share of the estimated cost follows its fraction interval."""
+    L = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "emul", "libfpt_emul.so"))
+    L.fpt_emul_shard_frac.argtypes = [ctypes.c_int] * 5 + [_dp] + [ctypes.POINTER(ctypes.c_longlong)] * 2 + [_dp]
+    n = fb.host.num_items(o, v)
+    rng = np.random.default_rng(world)
+    for trial in range(4):
+        w = 1.0 + 0.1 * rng.standard_normal(world)
+        frac = np.concatenate([[0.0], np.cumsum(w) / w.sum()])
+        frac[-1] = 1.0
+        prev_end = 0
+        for r in range(world):
+            b, e, sh = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_double()
+            assert L.fpt_emul_shard_frac(o, v, 1, r, world, frac.ctypes.data_as(_dp), ctypes.byref(b), ctypes.byref(e), ctypes.byref(sh)) == 0
+            assert b.value == prev_end and e.value >= b.value
+            prev_end = e.value
+            if n >= 200 * world:
+                assert abs(sh.value - (frac[r + 1] - frac[r])) < 0.01, (r, sh.value, frac)
+        assert prev_end == n
