@@ -18,6 +18,9 @@ Psi4's CCSD(T) and CCSD totals, i.e. E(T) = -0.008051775570 -> tests/golden/wate
 A fourth case takes another molecule of the reference's test table: glycine / STO-3G (o = 20, v = 10; geometry test/xyz/glycine.xyz), for which
 test/test_pT.jl:10,36 holds CCSD(T) and CCSD totals, E(T) = -0.007503098657 -> tests/golden/glycine_sto3g.npz.
 
+A fifth case, benzene / 6-31G (o = 21, v = 45; test/test_pT.jl:7,33: E(T) = -0.021110868073), is too big to keep as arrays (33 MB): only its
+record is stored, tests/golden/pin_benzene_631g.json (oracle E(T) 3e-11 Eh from the held value; about 20 minutes on 8 cores).
+
 Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
     python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g] [numba]
 """
@@ -462,6 +465,16 @@ def main(basis="sto-3g", engine="auto"):
     print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}" + note("e_ccsd_t"))
     out = os.path.join(root, "tests", "golden", molecule + "_" + basis.replace("-", "") + ".npz")
     extra = {}
+    if o * v ** 3 * 8 > (8 << 20) and basis != "cc-pvtz":   # (ia|bc) alone above 8 MB (benzene / 6-31G: 33 MB in all): keep the record, not the arrays
+        import json
+        rec = {"molecule": molecule, "basis": basis, "o": o, "v": v, "e_nuc": enuc, "e_rhf": e_rhf, "e_corr": e_cc, "e_ccsd": e_rhf + e_cc,
+               "e_t_oracle_pt_ijk": e_t, "e_ccsd_t": e_rhf + e_cc + e_t, "reference": ref,
+               "d_e_ccsd": e_rhf + e_cc - ref.get("e_ccsd", float("nan")), "d_e_t": e_t - ref.get("e_t", float("nan")),
+               "command": "python oracle/mini_ccsd.py " + case}
+        path = os.path.join(root, "tests", "golden", "pin_" + molecule + "_" + basis.replace("-", "") + ".json")
+        json.dump(rec, open(path, "w"), indent=1)
+        print("wrote", path)
+        return
     if basis == "cc-pvtz":   # 5 x 53^3 doubles: keep only b >= c of (ia|bc) = (ia|cb) (tests/test_oracle_kat.py unpacks it)
         iu = np.triu_indices(v)
         packed = np.ascontiguousarray(OVVV[:, :, iu[1], iu[0]])      # [i, a, (b >= c)]

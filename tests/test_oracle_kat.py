@@ -181,3 +181,13 @@ def test_gpu_matches_reference_test_value_glycine(engine):
     assert abs(res.correction - REF4_ET) < 1e-9
     assert abs(res.correction - float(G4["e_t"])) < 1e-13
     assert abs(res.energy - REF4_ECCSDT) < 1e-8 * abs(REF4_ECCSDT)
+
+
+def test_recorded_benzene_pin():
+    """benzene / 6-31G (test/test_pT.jl:7,33; o = 21, v = 45) is too big to keep as arrays: the record of the run that rebuilt it
+    (oracle/mini_ccsd.py benzene/6-31g) must sit within 1e-9 Eh of the values the reference holds."""
+    import json
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pin_benzene_631g.json")))
+    ref_t = -231.209805921161490 - (-231.188695053088594)
+    assert abs(rec["e_t_oracle_pt_ijk"] - ref_t) < 1e-9 and abs(rec["d_e_t"]) < 1e-9
+    assert abs(rec["e_ccsd"] - (-231.188695053088594)) < 1e-9
