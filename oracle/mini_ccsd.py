@@ -18,11 +18,12 @@ Psi4's CCSD(T) and CCSD totals, i.e. E(T) = -0.008051775570 -> tests/golden/wate
 A fourth case takes another molecule of the reference's test table: glycine / STO-3G (o = 20, v = 10; geometry test/xyz/glycine.xyz), for which
 test/test_pT.jl:10,36 holds CCSD(T) and CCSD totals, E(T) = -0.007503098657 -> tests/golden/glycine_sto3g.npz.
 
-A fifth case, benzene / 6-31G (o = 21, v = 45; test/test_pT.jl:7,33: E(T) = -0.021110868073), is too big to keep as arrays (33 MB): only its
+A further case, ammonia / aug-cc-pVDZ (o = 5, v = 45, diffuse functions; test/test_pT.jl:6,32: E(T) = -0.005496117261), is kept like the
+cc-pVTZ one -> tests/golden/ammonia_augccpvdz.npz.  And benzene / 6-31G (o = 21, v = 45; test/test_pT.jl:7,33: E(T) = -0.021110868073), is too big to keep as arrays (33 MB): only its
 record is stored, tests/golden/pin_benzene_631g.json (oracle E(T) 3e-11 Eh from the held value; about 20 minutes on 8 cores).
 
 Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
-    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g] [numba]
+    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g|ammonia/aug-cc-pvdz|benzene/6-31g] [numba]
 """
 from __future__ import annotations
 
@@ -48,6 +49,8 @@ MOLECULES = {
                 ("C", (-0.5847620, -0.8563810, 0.0000000)), ("N", (0.4006580, -1.9277700, 0.0000000)), ("H", (-0.5071000, 2.3458330, 0.0000000)),
                 ("H", (-1.2456590, -0.9456040, 0.8813150)), ("H", (-1.2456590, -0.9456040, -0.8813150)),
                 ("H", (1.0184570, -1.7812290, 0.8032340)), ("H", (1.0184570, -1.7812290, -0.8032340))],
+    "ammonia": [("N", (0.0, 0.0, 0.1173470)), ("H", (0.0, 0.9326490, -0.2738090)), ("H", (0.8076980, -0.4663250, -0.2738090)),
+                ("H", (-0.8076980, -0.4663250, -0.2738090))],
     "benzene": [("C", (0.0000000, 1.3916730, 0.0)), ("C", (1.2052240, 0.6958360, 0.0)), ("C", (1.2052240, -0.6958360, 0.0)),
                 ("C", (0.0000000, -1.3916730, 0.0)), ("C", (-1.2052240, -0.6958360, 0.0)), ("C", (-1.2052240, 0.6958360, 0.0)),
                 ("H", (0.0000000, 2.4695880, 0.0)), ("H", (2.1387260, 1.2347940, 0.0)), ("H", (2.1387260, -1.2347940, 0.0)),
@@ -103,7 +106,21 @@ CCPVTZ = {
           (2, [2.314], [1.0]), (2, [0.645], [1.0]),
           (3, [1.428], [1.0])],
 }
-BASES = {"sto-3g": STO3G, "6-31g": B631G, "cc-pvtz": CCPVTZ}
+# aug-cc-pVDZ (Dunning 1989; Kendall, Dunning, Harrison 1992): N (10s5p2d) -> [4s3p2d], H (5s2p) -> [3s2p]
+AUGCCPVDZ = {
+    "H": [(0, [13.01, 1.962, 0.4446], [0.019685, 0.137977, 0.478148]),
+          (0, [0.122], [1.0]), (0, [0.02974], [1.0]),
+          (1, [0.727], [1.0]), (1, [0.141], [1.0])],
+    "N": [(0, [9046.0, 1357.0, 309.3, 87.73, 28.56, 10.21, 3.838, 0.7466],
+              [0.000700, 0.005389, 0.027406, 0.103207, 0.278723, 0.448540, 0.278238, 0.015440]),
+          (0, [9046.0, 1357.0, 309.3, 87.73, 28.56, 10.21, 3.838, 0.7466],
+              [-0.000153, -0.001208, -0.005992, -0.024544, -0.067459, -0.158078, -0.121831, 0.549003]),
+          (0, [0.2248], [1.0]), (0, [0.06124], [1.0]),
+          (1, [13.55, 2.917, 0.7973], [0.039919, 0.217169, 0.510319]),
+          (1, [0.2185], [1.0]), (1, [0.05611], [1.0]),
+          (2, [0.817], [1.0]), (2, [0.230], [1.0])],
+}
+BASES = {"sto-3g": STO3G, "6-31g": B631G, "cc-pvtz": CCPVTZ, "aug-cc-pvdz": AUGCCPVDZ}
 # What the reference holds for each case: the printed run of examples/Juliacon2022.ipynb:497-615 (STO-3G) and the Psi4 total
 # energy its own test asserts for `@energy ccsd(t)`, water / 6-31G / df false (test/test_pT.jl:69-72, rtol 2e-8).
 REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd": -75.0187095932, "e_t": -0.0000738086,
@@ -114,6 +131,8 @@ REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd"
              # glycine / STO-3G / df false: test/test_pT.jl:10 Econv[6], :36 CCSDconv[6] (o = 20, v = 10)
              # benzene / 6-31G / df false: test/test_pT.jl:7 Econv[3], :33 CCSDconv[3] (o = 21, v = 45)
              "benzene/6-31g": {"e_ccsd": -231.188695053088594, "e_ccsd_t": -231.209805921161490, "e_t": -231.209805921161490 + 231.188695053088594},
+             # ammonia / aug-cc-pVDZ / df false: test/test_pT.jl:6 Econv[2], :32 CCSDconv[2] (o = 5, v = 45)
+             "ammonia/aug-cc-pvdz": {"e_ccsd": -56.422272522003723, "e_ccsd_t": -56.427768639264869, "e_t": -56.427768639264869 + 56.422272522003723},
              "glycine/sto-3g": {"e_ccsd": -279.415437830677774, "e_ccsd_t": -279.422940929335255, "e_t": -279.422940929335255 + 279.415437830677774}}
 
 
@@ -465,7 +484,7 @@ def main(basis="sto-3g", engine="auto"):
     print(f"CCSD(T) {e_rhf + e_cc + e_t:.10f}" + note("e_ccsd_t"))
     out = os.path.join(root, "tests", "golden", molecule + "_" + basis.replace("-", "") + ".npz")
     extra = {}
-    if o * v ** 3 * 8 > (8 << 20) and basis != "cc-pvtz":   # (ia|bc) alone above 8 MB (benzene / 6-31G: 33 MB in all): keep the record, not the arrays
+    if o * v ** 3 * 8 > (8 << 20):   # (ia|bc) alone above 8 MB (benzene / 6-31G: 33 MB in all): keep the record, not the arrays
         import json
         rec = {"molecule": molecule, "basis": basis, "o": o, "v": v, "e_nuc": enuc, "e_rhf": e_rhf, "e_corr": e_cc, "e_ccsd": e_rhf + e_cc,
                "e_t_oracle_pt_ijk": e_t, "e_ccsd_t": e_rhf + e_cc + e_t, "reference": ref,
@@ -475,7 +494,7 @@ def main(basis="sto-3g", engine="auto"):
         json.dump(rec, open(path, "w"), indent=1)
         print("wrote", path)
         return
-    if basis == "cc-pvtz":   # 5 x 53^3 doubles: keep only b >= c of (ia|bc) = (ia|cb) (tests/test_oracle_kat.py unpacks it)
+    if o * v ** 3 * 8 > (1 << 20):   # e.g. 5 x 53^3 doubles: keep only b >= c of (ia|bc) = (ia|cb) (tests/test_oracle_kat.py unpacks it)
         iu = np.triu_indices(v)
         packed = np.ascontiguousarray(OVVV[:, :, iu[1], iu[0]])      # [i, a, (b >= c)]
         assert np.max(np.abs(OVVV - OVVV.transpose(0, 1, 3, 2))) < 1e-12

@@ -191,3 +191,44 @@ def test_recorded_benzene_pin():
     ref_t = -231.209805921161490 - (-231.188695053088594)
     assert abs(rec["e_t_oracle_pt_ijk"] - ref_t) < 1e-9 and abs(rec["d_e_t"]) < 1e-9
     assert abs(rec["e_ccsd"] - (-231.188695053088594)) < 1e-9
+
+
+# ---- ammonia / aug-cc-pVDZ: diffuse functions, a second molecule with d shells (test/test_pT.jl:6,32) ---------------------------------
+# `python oracle/mini_ccsd.py ammonia/aug-cc-pvdz numba` (geometry test/xyz/ammonia.xyz, all-electron, o = 5, v = 45) reproduces Psi4's
+# CCSD total to 3e-12 Eh and E(T) = CCSD(T) - CCSD = -0.005496117261 to 8e-13 Eh; (ia|bc) is stored packed over b >= c.
+G5 = np.load(os.path.join(os.path.dirname(__file__), "golden", "ammonia_augccpvdz.npz"))
+REF5_ECCSDT = -56.427768639264869    # test/test_pT.jl:6   Econv[2]
+REF5_ECCSD = -56.422272522003723     # test/test_pT.jl:32  CCSDconv[2]
+REF5_ET = REF5_ECCSDT - REF5_ECCSD
+
+
+def _args5():
+    v = G5["T1"].shape[1]
+    iu = np.triu_indices(v)
+    ovvv = np.empty((5, v, v, v))
+    ovvv[:, :, iu[1], iu[0]] = G5["OVVV_packed"]
+    ovvv[:, :, iu[0], iu[1]] = G5["OVVV_packed"]
+    return tuple(np.asfortranarray(a) for a in (G5["T1"], G5["T2"], ovvv, G5["OOOV"], G5["OVOV"], G5["fo"], G5["fv"]))
+
+
+@pytest.mark.parametrize("impl", ["gemm", "numpy_ijk2"])
+def test_oracle_matches_reference_test_value_ammonia(impl):
+    f = {"gemm": oracle.pt_gemm, "numpy_ijk2": P.pt_ijk2}[impl]
+    assert G5["T1"].shape == (5, 45) and G5["T2"].shape == (5, 5, 45, 45)
+    assert abs(float(G5["e_rhf"]) + float(G5["e_corr"]) - REF5_ECCSD) < 1e-9      # measured: 3e-12
+    e = f(*_args5())
+    assert abs(e - REF5_ET) < 1e-9, (e, REF5_ET)                                   # measured: 8e-13
+    assert abs(float(G5["e_rhf"]) + float(G5["e_corr"]) + e - REF5_ECCSDT) < 1e-9
+    assert abs(e - float(G5["e_t"])) < 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_test_value_ammonia(engine):
+    import fermi_jl_b200 as fb
+    a = _args5()
+    ccsd = fb.RCCSD(0.0, float(G5["e_corr"]), float(G5["e_rhf"]) + float(G5["e_corr"]), a[0], a[1])
+    moints = fb.IntegralHelper({"OVVV": a[2], "OOOV": a[3], "OVOV": a[4], "Fii": a[5], "Faa": a[6]})
+    res = fb.RCCSDpT(ccsd, moints, fb.B200())
+    assert abs(res.correction - REF5_ET) < 1e-9
+    assert abs(res.energy - REF5_ECCSDT) < 1e-9
+    assert abs(res.correction - float(G5["e_t"])) < 1e-12
