@@ -480,7 +480,7 @@ def test_nine_group_k_all_distinct_tile_triples(engine, o, v):
 
 def test_randomised_sweep(engine):
     """tools/gpu_fuzz.py: random shapes x routes (conventional / DF / AO / sparse AO) x item orders x kernel variants x
-    triplet windows x shard counts against the oracle (40 cases here; profiles/r01e_gpu_fuzz_250.json holds a 250-case run of the final build)."""
+    triplet windows x shard counts against the oracle (40 cases here; profiles/r02c_gpu_fuzz_250_7.json holds a 250-case run of tools/gpu_fuzz.py)."""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_fuzz.py"), "40", "11"], capture_output=True, text=True, cwd=root)
