@@ -21,9 +21,11 @@ test/test_pT.jl:10,36 holds CCSD(T) and CCSD totals, E(T) = -0.007503098657 -> t
 A further case, ammonia / aug-cc-pVDZ (o = 5, v = 45, diffuse functions; test/test_pT.jl:6,32: E(T) = -0.005496117261), is kept like the
 cc-pVTZ one -> tests/golden/ammonia_augccpvdz.npz.  And benzene / 6-31G (o = 21, v = 45; test/test_pT.jl:7,33: E(T) = -0.021110868073), is too big to keep as arrays (33 MB): only its
 record is stored, tests/golden/pin_benzene_631g.json (oracle E(T) 3e-11 Eh from the held value; about 20 minutes on 8 cores).
+Likewise methane / cc-pVTZ (o = 5, v = 81; test/test_pT.jl:11,37: E(T) = -0.006426288342): tests/golden/pin_methane_ccpvtz.json (CCSD total
+1e-11 Eh, oracle E(T) 5e-12 Eh from the held values; about 25 minutes, 37 GB of memory).
 
 Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
-    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g|ammonia/aug-cc-pvdz|benzene/6-31g] [numba]
+    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g|ammonia/aug-cc-pvdz|benzene/6-31g|methane/cc-pvtz] [numba]
 """
 from __future__ import annotations
 
@@ -49,6 +51,8 @@ MOLECULES = {
                 ("C", (-0.5847620, -0.8563810, 0.0000000)), ("N", (0.4006580, -1.9277700, 0.0000000)), ("H", (-0.5071000, 2.3458330, 0.0000000)),
                 ("H", (-1.2456590, -0.9456040, 0.8813150)), ("H", (-1.2456590, -0.9456040, -0.8813150)),
                 ("H", (1.0184570, -1.7812290, 0.8032340)), ("H", (1.0184570, -1.7812290, -0.8032340))],
+    "methane": [("C", (0.0, 0.0, 0.0)), ("H", (0.6268910, 0.6268910, 0.6268910)), ("H", (-0.6268910, -0.6268910, 0.6268910)),
+                ("H", (-0.6268910, 0.6268910, -0.6268910)), ("H", (0.6268910, -0.6268910, -0.6268910))],
     "ammonia": [("N", (0.0, 0.0, 0.1173470)), ("H", (0.0, 0.9326490, -0.2738090)), ("H", (0.8076980, -0.4663250, -0.2738090)),
                 ("H", (-0.8076980, -0.4663250, -0.2738090))],
     "benzene": [("C", (0.0000000, 1.3916730, 0.0)), ("C", (1.2052240, 0.6958360, 0.0)), ("C", (1.2052240, -0.6958360, 0.0)),
@@ -105,6 +109,15 @@ CCPVTZ = {
           (1, [0.7156], [1.0]), (1, [0.2140], [1.0]),
           (2, [2.314], [1.0]), (2, [0.645], [1.0]),
           (3, [1.428], [1.0])],
+    "C": [(0, [8236.0, 1235.0, 280.8, 79.27, 25.59, 8.997, 3.319, 0.3643],
+              [0.000531, 0.004108, 0.021087, 0.081853, 0.234817, 0.434401, 0.346129, -0.008983]),
+          (0, [8236.0, 1235.0, 280.8, 79.27, 25.59, 8.997, 3.319, 0.3643],
+              [-0.000113, -0.000878, -0.004540, -0.018133, -0.055760, -0.126895, -0.170352, 0.598684]),
+          (0, [0.9059], [1.0]), (0, [0.1285], [1.0]),
+          (1, [18.71, 4.133, 1.200], [0.014031, 0.086866, 0.290216]),
+          (1, [0.3827], [1.0]), (1, [0.1209], [1.0]),
+          (2, [1.097], [1.0]), (2, [0.318], [1.0]),
+          (3, [0.761], [1.0])],
 }
 # aug-cc-pVDZ (Dunning 1989; Kendall, Dunning, Harrison 1992): N (10s5p2d) -> [4s3p2d], H (5s2p) -> [3s2p]
 AUGCCPVDZ = {
@@ -131,6 +144,8 @@ REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd"
              # glycine / STO-3G / df false: test/test_pT.jl:10 Econv[6], :36 CCSDconv[6] (o = 20, v = 10)
              # benzene / 6-31G / df false: test/test_pT.jl:7 Econv[3], :33 CCSDconv[3] (o = 21, v = 45)
              "benzene/6-31g": {"e_ccsd": -231.188695053088594, "e_ccsd_t": -231.209805921161490, "e_t": -231.209805921161490 + 231.188695053088594},
+             # methane / cc-pVTZ / df false: test/test_pT.jl:11 Econv[7], :37 CCSDconv[7] (o = 5, v = 81)
+             "methane/cc-pvtz": {"e_ccsd": -40.448675124014166, "e_ccsd_t": -40.455101412356250, "e_t": -40.455101412356250 + 40.448675124014166},
              # ammonia / aug-cc-pVDZ / df false: test/test_pT.jl:6 Econv[2], :32 CCSDconv[2] (o = 5, v = 45)
              "ammonia/aug-cc-pvdz": {"e_ccsd": -56.422272522003723, "e_ccsd_t": -56.427768639264869, "e_t": -56.427768639264869 + 56.422272522003723},
              "glycine/sto-3g": {"e_ccsd": -279.415437830677774, "e_ccsd_t": -279.422940929335255, "e_t": -279.422940929335255 + 279.415437830677774}}

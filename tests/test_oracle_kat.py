@@ -193,6 +193,18 @@ def test_recorded_benzene_pin():
     assert abs(rec["e_ccsd"] - (-231.188695053088594)) < 1e-9
 
 
+def test_recorded_methane_pin():
+    """methane / cc-pVTZ (test/test_pT.jl:11,37; o = 5, v = 81: the C2 basis on a second molecule, (ia|bc) 21 MB) -- record of
+    `python oracle/mini_ccsd.py methane/cc-pvtz` (about 25 minutes, 37 GB): measured 1e-11 Eh (CCSD total) and 5e-12 Eh (E(T))."""
+    import json
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pin_methane_ccpvtz.json")))
+    ref_t = -40.455101412356250 - (-40.448675124014166)
+    assert (rec["o"], rec["v"]) == (5, 81)
+    assert abs(rec["e_t_oracle_pt_ijk"] - ref_t) < 1e-9 and abs(rec["d_e_t"]) < 1e-9
+    assert abs(rec["e_ccsd"] - (-40.448675124014166)) < 1e-9
+    assert abs(rec["e_ccsd_t"] - (-40.455101412356250)) < 1e-9
+
+
 # ---- ammonia / aug-cc-pVDZ: diffuse functions, a second molecule with d shells (test/test_pT.jl:6,32) ---------------------------------
 # `python oracle/mini_ccsd.py ammonia/aug-cc-pvdz numba` (geometry test/xyz/ammonia.xyz, all-electron, o = 5, v = 45) reproduces Psi4's
 # CCSD total to 3e-12 Eh and E(T) = CCSD(T) - CCSD = -0.005496117261 to 8e-13 Eh; (ia|bc) is stored packed over b >= c.
