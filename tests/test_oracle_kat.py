@@ -244,3 +244,24 @@ def test_gpu_matches_reference_test_value_ammonia(engine):
     assert abs(res.correction - REF5_ET) < 1e-9
     assert abs(res.energy - REF5_ECCSDT) < 1e-9
     assert abs(res.correction - float(G5["e_t"])) < 1e-12
+
+
+# ---- formaldehyde / 6-31G*: a polarised Pople set, eight occupied orbitals (test/test_pT.jl:9,35) --------------------------------------
+# `python oracle/mini_ccsd.py "formaldehyde/6-31g*"` (geometry test/xyz/formaldehyde.xyz, all-electron, o = 8, v = 24 with five spherical d
+# functions per shell -- six Cartesian ones miss the held CCSD total by 6.9 mEh) lands 2e-12 Eh from Psi4's CCSD total and 6e-12 Eh from
+# E(T) = CCSD(T) - CCSD = -0.009118186572.  Oracle only: this case has no GPU test (added after the round's GPU time was spent).
+G6 = np.load(os.path.join(os.path.dirname(__file__), "golden", "formaldehyde_631gs.npz"))
+REF6_ECCSDT = -114.189827180824139   # test/test_pT.jl:9   Econv[5]
+REF6_ECCSD = -114.180708994251702    # test/test_pT.jl:35  CCSDconv[5]
+REF6_ET = REF6_ECCSDT - REF6_ECCSD
+
+
+@pytest.mark.parametrize("impl", ["naive", "gemm", "numpy_ijk2"])
+def test_oracle_matches_reference_test_value_formaldehyde(impl):
+    f = {"naive": oracle.pt_naive, "gemm": oracle.pt_gemm, "numpy_ijk2": P.pt_ijk2}[impl]
+    assert G6["T1"].shape == (8, 24) and G6["T2"].shape == (8, 8, 24, 24)
+    assert abs(float(G6["e_rhf"]) + float(G6["e_corr"]) - REF6_ECCSD) < 1e-9       # measured: 2e-12
+    e = f(*(np.asfortranarray(G6[k]) for k in ("T1", "T2", "OVVV", "OOOV", "OVOV", "fo", "fv")))
+    assert abs(e - REF6_ET) < 1e-9, (e, REF6_ET)                                    # measured: 6e-12
+    assert abs(float(G6["e_rhf"]) + float(G6["e_corr"]) + e - REF6_ECCSDT) < 1e-9
+    assert abs(e - float(G6["e_t"])) < 1e-13
