@@ -25,9 +25,11 @@ Formaldehyde / 6-31G* (o = 8, v = 24 with spherical d shells; test/test_pT.jl:9,
 (CCSD total 2e-12 Eh, oracle E(T) 6e-12 Eh from the held values; half a minute).
 Likewise methane / cc-pVTZ (o = 5, v = 81; test/test_pT.jl:11,37: E(T) = -0.006426288342): tests/golden/pin_methane_ccpvtz.json (CCSD total
 1e-11 Eh, oracle E(T) 5e-12 Eh from the held values; about 25 minutes, 37 GB of memory).
+And ethanol / cc-pVDZ (o = 13, v = 59; test/test_pT.jl:8,34: E(T) = -0.012492525191): tests/golden/pin_ethanol_ccpvdz.json (CCSD total 8e-11 Eh,
+oracle E(T) 1.2e-11 Eh from the held values; about 8 minutes).
 
 Run from the repo root (pure-Python integrals: about a minute for sto-3g, several for 6-31g; numba: a few minutes for cc-pvtz):
-    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g|ammonia/aug-cc-pvdz|benzene/6-31g|methane/cc-pvtz|formaldehyde/6-31g*] [numba]
+    python oracle/mini_ccsd.py [sto-3g|6-31g|cc-pvtz|glycine/sto-3g|ammonia/aug-cc-pvdz|benzene/6-31g|methane/cc-pvtz|formaldehyde/6-31g*|ethanol/cc-pvdz] [numba]
 """
 from __future__ import annotations
 
@@ -53,6 +55,9 @@ MOLECULES = {
                 ("C", (-0.5847620, -0.8563810, 0.0000000)), ("N", (0.4006580, -1.9277700, 0.0000000)), ("H", (-0.5071000, 2.3458330, 0.0000000)),
                 ("H", (-1.2456590, -0.9456040, 0.8813150)), ("H", (-1.2456590, -0.9456040, -0.8813150)),
                 ("H", (1.0184570, -1.7812290, 0.8032340)), ("H", (1.0184570, -1.7812290, -0.8032340))],
+    "ethanol": [("C", (1.1615830, -0.4067550, 0.0)), ("C", (0.0, 0.5527180, 0.0)), ("O", (-1.1871140, -0.2128600, 0.0)),
+                ("H", (-1.9324340, 0.3838170, 0.0)), ("H", (2.1028600, 0.1358400, 0.0)), ("H", (1.1223470, -1.0398290, 0.8811340)),
+                ("H", (1.1223470, -1.0398290, -0.8811340)), ("H", (0.0561470, 1.1935530, 0.8808960)), ("H", (0.0561470, 1.1935530, -0.8808960))],
     "formaldehyde": [("O", (0.0, 0.0, 0.6744930)), ("C", (0.0, 0.0, -0.5297240)), ("H", (0.0, 0.9347280, -1.1087990)),
                      ("H", (0.0, -0.9347280, -1.1087990))],
     "methane": [("C", (0.0, 0.0, 0.0)), ("H", (0.6268910, 0.6268910, 0.6268910)), ("H", (-0.6268910, -0.6268910, 0.6268910)),
@@ -137,11 +142,33 @@ AUGCCPVDZ = {
           (1, [0.2185], [1.0]), (1, [0.05611], [1.0]),
           (2, [0.817], [1.0]), (2, [0.230], [1.0])],
 }
+# cc-pVDZ (Dunning 1989): C, O (9s4p1d) -> [3s2p1d], H (4s1p) -> [2s1p]
+CCPVDZ = {
+    "H": [(0, [13.01, 1.962, 0.4446], [0.019685, 0.137977, 0.478148]),
+          (0, [0.122], [1.0]),
+          (1, [0.727], [1.0])],
+    "C": [(0, [6665.0, 1000.0, 228.0, 64.71, 21.06, 7.495, 2.797, 0.5215],
+              [0.000692, 0.005329, 0.027077, 0.101718, 0.274740, 0.448564, 0.285074, 0.015204]),
+          (0, [6665.0, 1000.0, 228.0, 64.71, 21.06, 7.495, 2.797, 0.5215],
+              [-0.000146, -0.001154, -0.005725, -0.023312, -0.063955, -0.149981, -0.127262, 0.544529]),
+          (0, [0.1596], [1.0]),
+          (1, [9.439, 2.002, 0.5456], [0.038109, 0.209480, 0.508557]),
+          (1, [0.1517], [1.0]),
+          (2, [0.55], [1.0])],
+    "O": [(0, [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013],
+              [0.000710, 0.005470, 0.027837, 0.104800, 0.283062, 0.448719, 0.270952, 0.015458]),
+          (0, [11720.0, 1759.0, 400.8, 113.7, 37.03, 13.27, 5.025, 1.013],
+              [-0.000160, -0.001263, -0.006267, -0.025716, -0.070924, -0.165411, -0.116955, 0.557368]),
+          (0, [0.3023], [1.0]),
+          (1, [17.70, 3.854, 1.046], [0.043018, 0.228913, 0.508728]),
+          (1, [0.2753], [1.0]),
+          (2, [1.185], [1.0])],
+}
 # 6-31G* (Hariharan, Pople 1973): 6-31G plus one d shell (exponent 0.8) on C and O.  Five real solid harmonics per d shell, like every
 # other set here: the values the reference holds for formaldehyde correspond to that (six Cartesian d functions give a CCSD total
 # 6.9 mEh lower -- tried, does not match).
 B631GS = {sym: shells + ([(2, [0.8], [1.0])] if sym != "H" else []) for sym, shells in B631G.items()}
-BASES = {"sto-3g": STO3G, "6-31g": B631G, "cc-pvtz": CCPVTZ, "aug-cc-pvdz": AUGCCPVDZ, "6-31g*": B631GS}
+BASES = {"sto-3g": STO3G, "6-31g": B631G, "cc-pvtz": CCPVTZ, "aug-cc-pvdz": AUGCCPVDZ, "6-31g*": B631GS, "cc-pvdz": CCPVDZ}
 # What the reference holds for each case: the printed run of examples/Juliacon2022.ipynb:497-615 (STO-3G) and the Psi4 total
 # energy its own test asserts for `@energy ccsd(t)`, water / 6-31G / df false (test/test_pT.jl:69-72, rtol 2e-8).
 REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd": -75.0187095932, "e_t": -0.0000738086,
@@ -152,6 +179,8 @@ REFERENCE = {"sto-3g": {"e_nuc": 8.8880641743, "e_corr": -0.0537066985, "e_ccsd"
              # glycine / STO-3G / df false: test/test_pT.jl:10 Econv[6], :36 CCSDconv[6] (o = 20, v = 10)
              # benzene / 6-31G / df false: test/test_pT.jl:7 Econv[3], :33 CCSDconv[3] (o = 21, v = 45)
              "benzene/6-31g": {"e_ccsd": -231.188695053088594, "e_ccsd_t": -231.209805921161490, "e_t": -231.209805921161490 + 231.188695053088594},
+             # ethanol / cc-pVDZ / df false: test/test_pT.jl:8 Econv[4], :34 CCSDconv[4] (o = 13, v = 59)
+             "ethanol/cc-pvdz": {"e_ccsd": -154.616795317070142, "e_ccsd_t": -154.629287842261505, "e_t": -154.629287842261505 + 154.616795317070142},
              # formaldehyde / 6-31G* / df false: test/test_pT.jl:9 Econv[5], :35 CCSDconv[5] (o = 8, v = 24: spherical d shells)
              "formaldehyde/6-31g*": {"e_ccsd": -114.180708994251702, "e_ccsd_t": -114.189827180824139, "e_t": -114.189827180824139 + 114.180708994251702},
              # methane / cc-pVTZ / df false: test/test_pT.jl:11 Econv[7], :37 CCSDconv[7] (o = 5, v = 81)

@@ -193,16 +193,20 @@ def test_recorded_benzene_pin():
     assert abs(rec["e_ccsd"] - (-231.188695053088594)) < 1e-9
 
 
-def test_recorded_methane_pin():
-    """methane / cc-pVTZ (test/test_pT.jl:11,37; o = 5, v = 81: the C2 basis on a second molecule, (ia|bc) 21 MB) -- record of
-    `python oracle/mini_ccsd.py methane/cc-pvtz` (about 25 minutes, 37 GB): measured 1e-11 Eh (CCSD total) and 5e-12 Eh (E(T))."""
+@pytest.mark.parametrize("name,o,v,e_ccsd,e_ccsd_t", [
+    ("methane_ccpvtz", 5, 81, -40.448675124014166, -40.455101412356250),      # test/test_pT.jl:37, :11 (row 7)
+    ("ethanol_ccpvdz", 13, 59, -154.616795317070142, -154.629287842261505),   # test/test_pT.jl:34, :8  (row 4)
+])
+def test_recorded_pin(name, o, v, e_ccsd, e_ccsd_t):
+    """Cases whose (ia|bc) is too big to keep (21 MB each): the record of the `python oracle/mini_ccsd.py <molecule>/<basis>` run that
+    rebuilt them must sit within 1e-9 Eh of the totals the reference holds.  Measured: methane / cc-pVTZ 1e-11 Eh (CCSD total) and
+    5e-12 Eh (E(T)), about 25 minutes and 37 GB; ethanol / cc-pVDZ 8e-11 and 1.2e-11 Eh, about 8 minutes."""
     import json
-    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pin_methane_ccpvtz.json")))
-    ref_t = -40.455101412356250 - (-40.448675124014166)
-    assert (rec["o"], rec["v"]) == (5, 81)
-    assert abs(rec["e_t_oracle_pt_ijk"] - ref_t) < 1e-9 and abs(rec["d_e_t"]) < 1e-9
-    assert abs(rec["e_ccsd"] - (-40.448675124014166)) < 1e-9
-    assert abs(rec["e_ccsd_t"] - (-40.455101412356250)) < 1e-9
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pin_" + name + ".json")))
+    assert (rec["o"], rec["v"]) == (o, v)
+    assert abs(rec["e_t_oracle_pt_ijk"] - (e_ccsd_t - e_ccsd)) < 1e-9 and abs(rec["d_e_t"]) < 1e-9
+    assert abs(rec["e_ccsd"] - e_ccsd) < 1e-9
+    assert abs(rec["e_ccsd_t"] - e_ccsd_t) < 1e-9
 
 
 # ---- ammonia / aug-cc-pVDZ: diffuse functions, a second molecule with d shells (test/test_pT.jl:6,32) ---------------------------------
