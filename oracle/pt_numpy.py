@@ -224,6 +224,30 @@ def mo_blocks_from_ao(AOERI, C, ndocc, drop_occ=0, drop_vir=0):
     return F(OVVV), F(OOOV), F(OVOV)
 
 
+def df_factors_from_ao(Bmn, C, ndocc, drop_occ=0, drop_vir=0):
+    """MO-basis DF factors from the AO-basis ones, Bmn[Q, mu, nu] -- transcription of
+    src/Core/Integrals/ROIntegrals/DFERI.jl: compute_BOO! (:15-29), compute_BOV! (:31-51), compute_BVV! (:53-69).
+    Returns (BOO, BOV, BVV) with the auxiliary index first, Fortran-ordered (what fpt_triples_df is handed)."""
+    nmo = C.shape[1]
+    Co = C[:, drop_occ:ndocc]
+    Cv = C[:, ndocc:nmo - drop_vir]
+    F = np.asfortranarray
+    BOO = np.einsum("Qmn,mi,nj->Qij", Bmn, Co, Co, optimize=True)   # :26
+    BOV = np.einsum("Qmn,mi,na->Qia", Bmn, Co, Cv, optimize=True)   # :48
+    BVV = np.einsum("Qmn,ma,nb->Qab", Bmn, Cv, Cv, optimize=True)   # :66
+    return F(BOO), F(BOV), F(BVV)
+
+
+def mo_blocks_from_df(BOO, BOV, BVV):
+    """The three blocks the (T) path reads, assembled from DF factors -- transcription of DFERI.jl: compute_OOOV! (:88-112),
+    compute_OVOV! (:139-154), compute_OVVV! (:156-180).  Returns (OVVV, OOOV, OVOV), Fortran-ordered."""
+    F = np.asfortranarray
+    OOOV = np.einsum("Qij,Qka->ijka", BOO, BOV, optimize=True)      # :109
+    OVOV = np.einsum("Qia,Qjb->iajb", BOV, BOV, optimize=True)      # :151
+    OVVV = np.einsum("Qia,Qbc->iabc", BOV, BVV, optimize=True)      # :177
+    return F(OVVV), F(OOOV), F(OVOV)
+
+
 def _index2(i, j):
     """Backend/Arrays.jl:34-40."""
     return (j * (j + 1)) // 2 + i if i < j else (i * (i + 1)) // 2 + j

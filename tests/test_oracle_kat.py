@@ -91,6 +91,42 @@ def test_stored_ao_tensor_reproduces_stored_mo_blocks():
     assert np.abs(OVOV - G["OVOV"]).max() < 1e-13
 
 
+def _exact_factors():
+    """Exact "density-fitting" factors of the stored AO tensor: (mn|rs) = sum_Q B[Q,mn] B[Q,rs] with B from the eigen-decomposition of
+    the 49 x 49 matrix (mn|rs) -- the limit a complete auxiliary basis reaches.  The reference's DF totals cannot be pinned here (their
+    auxiliary basis sets are not restated), but with exact factors the DF route has to land on the CONVENTIONAL value the reference printed."""
+    n = G["C"].shape[0]
+    M = G["AOERI"].reshape(n * n, n * n)
+    w, U = np.linalg.eigh(0.5 * (M + M.T))
+    keep = w > 1e-12
+    assert w.min() > -1e-10                       # positive semi-definite, as an ERI matrix is
+    B = (U[:, keep] * np.sqrt(w[keep])).T.reshape(-1, n, n)
+    assert np.abs(np.einsum("Qmn,Qrs->mnrs", B, B) - G["AOERI"]).max() < 1e-12
+    return B
+
+
+def test_df_route_of_the_oracle_lands_on_the_reference_known_answer():
+    """DFERI.jl transcriptions (B factors AO -> MO, then the three blocks) fed with exact factors reproduce the stored conventional MO
+    blocks and, through the (T) oracle, the reference's printed E(T)."""
+    BOO, BOV, BVV = P.df_factors_from_ao(_exact_factors(), G["C"], ndocc=5)          # DFERI.jl:15-69
+    assert BOO.shape[1:] == (5, 5) and BOV.shape[1:] == (5, 2) and BVV.shape[1:] == (2, 2)
+    OVVV, OOOV, OVOV = P.mo_blocks_from_df(BOO, BOV, BVV)                             # DFERI.jl:88-180
+    assert np.abs(OVVV - G["OVVV"]).max() < 1e-12 and np.abs(OOOV - G["OOOV"]).max() < 1e-12
+    assert np.abs(OVOV - G["OVOV"]).max() < 1e-12
+    a = _args()
+    e = oracle.pt_gemm(a[0], a[1], OVVV, OOOV, OVOV, a[5], a[6])
+    assert abs(e - REF_ET) < 5e-11, (e, REF_ET)
+
+
+def test_synthetic_df_inputs_follow_the_df_transcription():
+    """The synthetic inputs of the GPU parity tests (fermi.jl_b200/synth.py) build their conventional blocks from their B factors: that
+    construction must be the DFERI.jl transcription, or the DF parity tests would compare the GPU with something else."""
+    import fermi_jl_b200 as fb
+    x = fb.synth.make_inputs(4, 9, naux=11, seed=3)
+    OVVV, OOOV, OVOV = P.mo_blocks_from_df(x.BOO, x.BOV, x.BVV)
+    assert np.abs(OVVV - x.OVVV).max() < 1e-13 and np.abs(OOOV - x.OOOV).max() < 1e-13 and np.abs(OVOV - x.OVOV).max() < 1e-13
+
+
 @pytest.mark.gpu
 def test_gpu_ao_route_matches_reference_known_answer(engine):
     import fermi_jl_b200 as fb
