@@ -130,3 +130,32 @@ def test_shards_with_adaptive_fractions_still_partition(built, o, v, world):
             if n >= 200 * world:
                 assert abs(sh.value - (frac[r + 1] - frac[r])) < 0.01, (r, sh.value, frac)
         assert prev_end == n
+
+
+# ---- the kernel's index algebra on the real molecules whose E(T) the reference holds (tests/test_oracle_kat.py has the sources) ---------
+_HELD = [("water_sto3g", -0.0000738086, 5e-11),                                             # examples/Juliacon2022.ipynb:614 (10 decimals)
+         ("water_ccpvtz", -76.343819598166903 + 76.335767822597347, 1e-9),                  # test/test_pT.jl:5,31    v = 53: 16+16+16+8 (vp 56)
+         ("ammonia_augccpvdz", -56.427768639264869 + 56.422272522003723, 1e-9),             # test/test_pT.jl:6,32    v = 45: 16+16+16 (vp 48)
+         ("formaldehyde_631gs", -114.189827180824139 + 114.180708994251702, 1e-9),          # test/test_pT.jl:9,35    v = 24: 16+8
+         ("glycine_sto3g", -279.422940929335255 + 279.415437830677774, 1e-9)]               # test/test_pT.jl:10,36   o = 20
+
+
+@pytest.mark.parametrize("name,held,tol", _HELD)
+def test_emulator_lands_on_reference_held_values(emul, name, held, tol):
+    """Not only the oracle but the product's own index algebra (fpt_layout.h: tiles, blocks, slots, GEMM descriptors, symmetric classes,
+    energy stage), run with plain loops, gives the E(T) the reference holds for these molecules."""
+    from types import SimpleNamespace
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    o, v = g["T1"].shape
+    if "OVVV" in g.files:
+        ovvv = g["OVVV"]
+    else:                                   # stored packed over b >= c
+        iu = np.triu_indices(v)
+        ovvv = np.empty((o, v, v, v))
+        ovvv[:, :, iu[1], iu[0]] = g["OVVV_packed"]
+        ovvv[:, :, iu[0], iu[1]] = g["OVVV_packed"]
+    x = SimpleNamespace(o=o, v=v, T1=g["T1"], T2=g["T2"], OVVV=ovvv, OOOV=g["OOOV"], OVOV=g["OVOV"], fo=g["fo"], fv=g["fv"])
+    e, n = emul(x)
+    assert abs(e - held) < tol, (e, held)
+    assert abs(e - float(g["e_t"])) < 1e-13
+    assert n == fb.host.num_items(o, v)
