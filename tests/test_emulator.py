@@ -58,7 +58,7 @@ def test_item_shards_add_up_and_match_triplet_ranges(emul, order):
     assert abs(part2 - ref2) < 1e-14
 
 
-@pytest.mark.parametrize("o,v,world", [(4, 21, 3), (6, 50, 8), (24, 114, 8), (5, 19, 2)])
+@pytest.mark.parametrize("o,v,world", [(4, 21, 3), (6, 50, 8), (24, 114, 8), (5, 19, 2), (40, 400, 8)])   # the last one: C5, 33.5 M items
 @pytest.mark.parametrize("order", [0, 1])
 def test_cost_weighted_shards_partition_the_work_list(built, o, v, world, order):
     """fpt_shard_items' split (shard_items / block_cost in fpt_layout.h, run here on the CPU): the parts are contiguous,
